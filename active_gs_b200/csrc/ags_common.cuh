@@ -1,0 +1,114 @@
+// ags_common.cuh -- shared definitions for the sm_100a kernels behind include/ags_b200.h
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/ags_b200.h"
+
+#define TILE AGS_TILE
+#define TILE_PIX (TILE * TILE)
+
+// rasterizer constants (oracle/rasterizer_ref.py)
+#define AGS_NEAR_CULL 0.2f
+#define AGS_LOWPASS 0.3f
+#define AGS_ALPHA_MAX 0.99f
+#define AGS_ALPHA_MIN (1.0f / 255.0f)
+#define AGS_T_EPS 1e-4f
+#define AGS_SLOPE_COS_MIN 0.1f
+
+// ------------------------------------------------------------------------------------------------
+// Workspace layout (all offsets 256-byte aligned). One workspace serves one batch of B views and
+// carries everything the backward needs.
+struct AgsWorkspace {
+    float4* geom0;      // (B*N) x, y, conic_a, conic_b
+    float4* geom1;      // (B*N) conic_c, opacity, slope_x, slope_y
+    float4* feat0;      // (B*N) r, g, b, depth
+    float4* feat1;      // (B*N) nx, ny, nz, confidence
+    uint2* rect;        // (B*N) packed tile rect: x = minx | maxx<<16, y = miny | maxy<<16
+    float* dsplat;      // (B*N*16) per-view per-Gaussian gradient record (backward)
+    int32_t* tile_count;   // (B*tiles)
+    int32_t* tile_offset;  // (B*tiles)
+    int32_t* tile_fill;    // (B*tiles)
+    int32_t* counters;     // (8) [0] = instance allocator
+    uint64_t* inst_key;    // (inst_cap) depth_bits<<32 | gaussian id, grouped per tile
+    uint64_t* inst_key_alt;// (inst_cap) ping-pong buffer for oversize tiles
+    int32_t* inst_sorted;  // (inst_cap) gaussian ids, front-to-back per tile
+    float* final_T;        // (B*P)
+    int32_t* n_contrib;    // (B*P) index+1 of the last instance that contributed
+    size_t total;
+};
+
+__host__ __device__ inline size_t ags_align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+inline AgsWorkspace ags_carve(void* base, int N, int B, int H, int W, int inst_cap) {
+    AgsWorkspace w;
+    size_t off = 0;
+    char* p = (char*)base;
+    const size_t BN = (size_t)B * N;
+    const int tiles = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    const size_t BT = (size_t)B * tiles, BP = (size_t)B * H * W;
+    auto take = [&](size_t bytes) { char* q = p + off; off += ags_align256(bytes); return (void*)q; };
+    w.geom0 = (float4*)take(BN * 16);
+    w.geom1 = (float4*)take(BN * 16);
+    w.feat0 = (float4*)take(BN * 16);
+    w.feat1 = (float4*)take(BN * 16);
+    w.rect = (uint2*)take(BN * 8);
+    w.dsplat = (float*)take(BN * 64);
+    w.tile_count = (int32_t*)take(BT * 4);
+    w.tile_offset = (int32_t*)take(BT * 4);
+    w.tile_fill = (int32_t*)take(BT * 4);
+    w.counters = (int32_t*)take(8 * 4);
+    w.inst_key = (uint64_t*)take((size_t)inst_cap * 8);
+    w.inst_key_alt = (uint64_t*)take((size_t)inst_cap * 8);
+    w.inst_sorted = (int32_t*)take((size_t)inst_cap * 4);
+    w.final_T = (float*)take(BP * 4);
+    w.n_contrib = (int32_t*)take(BP * 4);
+    w.total = off;
+    return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing (thread-local message, no exceptions across the C boundary)
+void ags_set_error(const char* fmt, ...);
+#define AGS_CHECK_ARG(cond, ...)            \
+    do {                                    \
+        if (!(cond)) {                      \
+            ags_set_error(__VA_ARGS__);     \
+            return -1;                      \
+        }                                   \
+    } while (0)
+#define AGS_CHECK_CUDA(expr)                                                        \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) {                                                    \
+            ags_set_error("%s failed: %s", #expr, cudaGetErrorString(_e));          \
+            return (int)_e;                                                         \
+        }                                                                           \
+    } while (0)
+
+// kernel launchers implemented in the individual .cu files
+int ags_launch_project_fwd(const AgsRenderArgs& a, const AgsWorkspace& w, bool for_backward);
+int ags_launch_binning(const AgsRenderArgs& a, const AgsWorkspace& w);
+int ags_launch_composite_fwd(const AgsRenderArgs& a, const AgsWorkspace& w);
+int ags_launch_composite_bwd(const AgsRenderArgs& a, const AgsRenderGradArgs& g, const AgsWorkspace& w);
+int ags_launch_project_bwd(const AgsRenderArgs& a, const AgsRenderGradArgs& g, const AgsWorkspace& w);
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+struct Cam {
+    float V[16];  // viewmatrix, row-vector convention: t_j = sum_k p_k V[4k+j] + V[12+j]
+    float M[16];  // projmatrix, same convention
+    float tanx, tany;
+};
+
+__device__ __forceinline__ void load_cam(Cam& c, const float* vm, const float* pm, const float* tf, int v) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        c.V[k] = __ldg(vm + v * 16 + k);
+        c.M[k] = __ldg(pm + v * 16 + k);
+    }
+    c.tanx = __ldg(tf + v * 2);
+    c.tany = __ldg(tf + v * 2 + 1);
+}

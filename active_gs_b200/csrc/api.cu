@@ -1,0 +1,74 @@
+// api.cu -- the extern "C" surface declared in include/ags_b200.h (argument checking, workspace
+// carving, kernel sequencing).  No torch types, no allocation, no synchronisation.
+#include <stdarg.h>
+#include <string.h>
+#include "ags_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void ags_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* ags_last_error(void) { return g_err; }
+extern "C" int ags_version(void) { return 100; }
+
+extern "C" size_t ags_scratch_bytes(int32_t N, int32_t B, int32_t H, int32_t W, int32_t inst_cap) {
+    if (N < 0 || B <= 0 || H <= 0 || W <= 0 || inst_cap < 0) return 0;
+    return ags_carve(nullptr, N, B, H, W, inst_cap).total;
+}
+
+static int check_render_args(const AgsRenderArgs* a) {
+    AGS_CHECK_ARG(a != nullptr, "args is NULL");
+    AGS_CHECK_ARG(a->N >= 0 && a->B > 0 && a->H > 0 && a->W > 0, "bad sizes N=%d B=%d H=%d W=%d", a->N, a->B, a->H, a->W);
+    AGS_CHECK_ARG((a->W + TILE - 1) / TILE < 65536 && (a->H + TILE - 1) / TILE < 65536, "image too large");
+    AGS_CHECK_ARG(a->param_mode == AGS_PARAMS_ACTIVATED || a->param_mode == AGS_PARAMS_RAW, "bad param_mode %d", a->param_mode);
+    AGS_CHECK_ARG(a->inst_cap >= 0, "negative inst_cap");
+    if (a->N > 0)
+        AGS_CHECK_ARG(a->means3D && a->scales && a->rotations && a->opacities && a->colors,
+                      "NULL per-Gaussian input");
+    AGS_CHECK_ARG(a->viewmatrix && a->projmatrix && a->tanfov && a->bg, "NULL per-view input");
+    AGS_CHECK_ARG(a->out_rgb && a->out_normal && a->out_depth && a->out_opacity && a->out_confidence,
+                  "NULL output image");
+    AGS_CHECK_ARG(a->stats != nullptr, "NULL stats");
+    if (a->N > 0) AGS_CHECK_ARG(a->radii != nullptr, "NULL radii");
+    AGS_CHECK_ARG(!a->require_importance || a->N == 0 || (a->importance && a->count), "require_importance needs importance/count");
+    AGS_CHECK_ARG(a->workspace != nullptr, "NULL workspace");
+    const size_t need = ags_scratch_bytes(a->N, a->B, a->H, a->W, a->inst_cap);
+    AGS_CHECK_ARG(a->workspace_bytes >= need, "workspace too small: %zu < %zu", a->workspace_bytes, need);
+    AGS_CHECK_ARG(((uintptr_t)a->workspace & 255) == 0, "workspace must be 256-byte aligned");
+    return 0;
+}
+
+static int render_forward_impl(const AgsRenderArgs* a, bool for_backward) {
+    int rc = check_render_args(a);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)a->stream;
+    AgsWorkspace w = ags_carve(a->workspace, a->N, a->B, a->H, a->W, a->inst_cap);
+    // tile_count, tile_offset, tile_fill and the counters are contiguous in the workspace
+    const size_t zero_bytes = (char*)w.inst_key - (char*)w.tile_count;
+    AGS_CHECK_CUDA(cudaMemsetAsync(w.tile_count, 0, zero_bytes, st));
+    AGS_CHECK_CUDA(cudaMemsetAsync(a->stats, 0, AGS_NUM_STATS * sizeof(int32_t), st));
+    if ((rc = ags_launch_project_fwd(*a, w, for_backward))) return rc;
+    if ((rc = ags_launch_binning(*a, w))) return rc;
+    if ((rc = ags_launch_composite_fwd(*a, w))) return rc;
+    return 0;
+}
+
+extern "C" int ags_render_forward(const AgsRenderArgs* a) { return render_forward_impl(a, true); }
+
+extern "C" int ags_render_backward(const AgsRenderArgs* a, const AgsRenderGradArgs* g) {
+    int rc = check_render_args(a);
+    if (rc) return rc;
+    AGS_CHECK_ARG(g != nullptr, "grads is NULL");
+    if (a->N > 0)
+        AGS_CHECK_ARG(g->d_means3D && g->d_scales && g->d_rotations && g->d_opacities && g->d_colors,
+                      "NULL gradient output");
+    AgsWorkspace w = ags_carve(a->workspace, a->N, a->B, a->H, a->W, a->inst_cap);
+    if ((rc = ags_launch_composite_bwd(*a, *g, w))) return rc;
+    if ((rc = ags_launch_project_bwd(*a, *g, w))) return rc;
+    return 0;
+}

@@ -1,0 +1,281 @@
+// composite.cu -- K4 composite_fwd and K5 composite_bwd: per-pixel front-to-back alpha compositing
+// of rgb / normal / plane depth / opacity / confidence and its backward.
+//
+// Replaces renderCUDA fwd/bwd of the native extension behind
+// /root/reference/utils/operations.py:701-713 (semantics: DESIGN.md section 2, oracle/rasterizer_ref.py).
+//
+// One CTA = one 16x16 tile of one view (grid.z = view: all B views of an iteration in one launch).
+// The tile's depth-sorted splat records (4 x float4 = 64 B each) are staged through shared memory in
+// batches of 256 with 128-bit loads, every thread then walks the batch for its pixel (shared-memory
+// broadcast reads).  The backward walks the SAME front-to-back order (no 1/(1-alpha) recurrences:
+// the "remaining" sum is total - prefix, computed from the saved forward outputs), reduces the 15
+// per-Gaussian partial gradients across the warp with a multi-value butterfly (16 shuffles instead
+// of 75) and issues one 16-lane vector RED per (warp, Gaussian) into a 64 B gradient record.
+#include "ags_common.cuh"
+
+namespace {
+
+constexpr int BATCH = 256;
+
+struct SplatEval {
+    float dx, dy, power, alpha;
+    bool skip;
+};
+
+__device__ __forceinline__ SplatEval eval_alpha(const float4 g0, const float4 g1, float pxf, float pyf) {
+    SplatEval e;
+    e.dx = g0.x - pxf;
+    e.dy = g0.y - pyf;
+    e.power = -0.5f * (g0.z * e.dx * e.dx + g1.x * e.dy * e.dy) - g0.w * e.dx * e.dy;
+    e.alpha = fminf(AGS_ALPHA_MAX, g1.y * __expf(e.power));
+    e.skip = (e.power > 0.f) || (e.alpha < AGS_ALPHA_MIN);
+    return e;
+}
+
+// K4 ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
+    __shared__ float4 s_g0[BATCH], s_g1[BATCH], s_f0[BATCH], s_f1[BATCH];
+    __shared__ int s_id[BATCH];
+    const int v = blockIdx.z;
+    const int tiles_x = gridDim.x, tiles_y = gridDim.y;
+    const int tile = blockIdx.y * tiles_x + blockIdx.x;
+    const size_t gt = (size_t)v * tiles_x * tiles_y + tile;
+    const int tid = threadIdx.y * TILE + threadIdx.x;
+    const int px = blockIdx.x * TILE + threadIdx.x, py = blockIdx.y * TILE + threadIdx.y;
+    const bool inside = (px < a.W) && (py < a.H);
+    const float pxf = (float)px, pyf = (float)py;
+    const bool overflow = w.counters[0] > a.inst_cap;
+    const int n = overflow ? 0 : w.tile_count[gt];
+    const int off = overflow ? 0 : w.tile_offset[gt];
+    const size_t vN = (size_t)v * a.N;
+    const size_t P = (size_t)a.H * a.W;
+    const size_t pix = (size_t)py * a.W + px;
+    const bool want_imp = a.require_importance != 0;
+    bool imp_pix = false;
+    if (want_imp && inside) imp_pix = a.render_mask ? (a.render_mask[(size_t)v * P + pix] == 1.f) : true;
+
+    float T = 1.f;
+    float C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f, D = 0.f, Cf = 0.f;
+    int last = 0;
+    bool done = !inside;
+    for (int base = 0; base < n; base += BATCH) {
+        if (__syncthreads_and(done)) break;
+        const int j = base + tid;
+        if (j < n) {
+            const int id = w.inst_sorted[off + j];
+            const size_t idx = vN + id;
+            s_id[tid] = id;
+            s_g0[tid] = ldg4(w.geom0 + idx);
+            s_g1[tid] = ldg4(w.geom1 + idx);
+            s_f0[tid] = ldg4(w.feat0 + idx);
+            s_f1[tid] = ldg4(w.feat1 + idx);
+        }
+        __syncthreads();
+        const int cnt = min(BATCH, n - base);
+        for (int k = 0; !done && k < cnt; ++k) {
+            const float4 g0 = s_g0[k], g1 = s_g1[k];
+            const SplatEval e = eval_alpha(g0, g1, pxf, pyf);
+            if (e.skip) continue;
+            const float test_T = T * (1.f - e.alpha);
+            if (test_T < AGS_T_EPS) { done = true; continue; }
+            const float wgt = e.alpha * T;
+            const float4 f0 = s_f0[k], f1 = s_f1[k];
+            C0 += wgt * f0.x; C1 += wgt * f0.y; C2 += wgt * f0.z;
+            D += wgt * (f0.w - g1.z * e.dx - g1.w * e.dy);
+            N0 += wgt * f1.x; N1 += wgt * f1.y; N2 += wgt * f1.z;
+            Cf += wgt * f1.w;
+            T = test_T;
+            last = base + k + 1;
+            if (imp_pix && wgt > a.weight_thres) {
+                atomicAdd(a.count + vN + s_id[k], 1);
+                atomicAdd(a.importance + vN + s_id[k], wgt);
+            }
+        }
+    }
+    if (inside) {
+        const float A = 1.f - T;
+        const float bg0 = __ldg(a.bg), bg1 = __ldg(a.bg + 1), bg2 = __ldg(a.bg + 2);
+        float* o = a.out_rgb + (size_t)v * 3 * P + pix;
+        o[0] = C0 + T * bg0; o[P] = C1 + T * bg1; o[2 * P] = C2 + T * bg2;
+        o = a.out_normal + (size_t)v * 3 * P + pix;
+        o[0] = N0; o[P] = N1; o[2 * P] = N2;
+        a.out_depth[(size_t)v * P + pix] = (A > 0.f) ? D / A : 0.f;
+        a.out_opacity[(size_t)v * P + pix] = A;
+        a.out_confidence[(size_t)v * P + pix] = Cf;
+        w.final_T[(size_t)v * P + pix] = T;
+        w.n_contrib[(size_t)v * P + pix] = last;
+    }
+}
+
+// K5 ---------------------------------------------------------------------------------------------
+// multi-value butterfly: v[0..15] per lane -> lane L holds sum over the warp of v[L>>1]
+__device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
+    const unsigned full = 0xffffffffu;
+    float a8[8];
+    {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float send = up ? v[k] : v[k + 8];
+            const float keep = up ? v[k + 8] : v[k];
+            a8[k] = keep + __shfl_xor_sync(full, send, 16);
+        }
+    }
+    float a4[4];
+    {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float send = up ? a8[k] : a8[k + 4];
+            const float keep = up ? a8[k + 4] : a8[k];
+            a4[k] = keep + __shfl_xor_sync(full, send, 8);
+        }
+    }
+    float a2[2];
+    {
+        const bool up = (lane & 4) != 0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float send = up ? a4[k] : a4[k + 2];
+            const float keep = up ? a4[k + 2] : a4[k];
+            a2[k] = keep + __shfl_xor_sync(full, send, 4);
+        }
+    }
+    float a1;
+    {
+        const bool up = (lane & 2) != 0;
+        const float send = up ? a2[0] : a2[1];
+        const float keep = up ? a2[1] : a2[0];
+        a1 = keep + __shfl_xor_sync(full, send, 2);
+    }
+    a1 += __shfl_xor_sync(full, a1, 1);
+    return a1;
+}
+
+__global__ void __launch_bounds__(256)
+composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
+    __shared__ float4 s_g0[BATCH], s_g1[BATCH], s_f0[BATCH], s_f1[BATCH];
+    __shared__ int s_id[BATCH];
+    __shared__ int s_max_last;
+    const int v = blockIdx.z;
+    const int tiles_x = gridDim.x, tiles_y = gridDim.y;
+    const int tile = blockIdx.y * tiles_x + blockIdx.x;
+    const size_t gt = (size_t)v * tiles_x * tiles_y + tile;
+    const int tid = threadIdx.y * TILE + threadIdx.x;
+    const int lane = tid & 31;
+    const int px = blockIdx.x * TILE + threadIdx.x, py = blockIdx.y * TILE + threadIdx.y;
+    const bool inside = (px < a.W) && (py < a.H);
+    const float pxf = (float)px, pyf = (float)py;
+    if (w.counters[0] > a.inst_cap) return;
+    const int n = w.tile_count[gt];
+    if (n == 0) return;
+    const int off = w.tile_offset[gt];
+    const size_t vN = (size_t)v * a.N;
+    const size_t P = (size_t)a.H * a.W;
+    const size_t pix = (size_t)py * a.W + px;
+    const size_t vp = (size_t)v * P + pix;
+
+    // per-pixel upstream gradients and the "remaining" sum
+    float gC0 = 0.f, gC1 = 0.f, gC2 = 0.f, gN0 = 0.f, gN1 = 0.f, gN2 = 0.f, gD = 0.f, gCf = 0.f;
+    float rem = 0.f;
+    int my_last = 0;
+    if (inside) {
+        my_last = w.n_contrib[vp];
+        const float Tf = w.final_T[vp];
+        const float A = 1.f - Tf;
+        if (gr.d_rgb) { const float* p = gr.d_rgb + (size_t)v * 3 * P + pix; gC0 = p[0]; gC1 = p[P]; gC2 = p[2 * P]; }
+        if (gr.d_normal) { const float* p = gr.d_normal + (size_t)v * 3 * P + pix; gN0 = p[0]; gN1 = p[P]; gN2 = p[2 * P]; }
+        const float gdep = gr.d_depth ? gr.d_depth[vp] : 0.f;
+        float gA = gr.d_opacity ? gr.d_opacity[vp] : 0.f;
+        if (gr.d_confidence) gCf = gr.d_confidence[vp];
+        const float depth_out = a.out_depth[vp];
+        if (A > 0.f) { gD = gdep / A; gA -= gdep * depth_out / A; }
+        const float bg0 = __ldg(a.bg), bg1 = __ldg(a.bg + 1), bg2 = __ldg(a.bg + 2);
+        const float* c = a.out_rgb + (size_t)v * 3 * P + pix;
+        const float* nn = a.out_normal + (size_t)v * 3 * P + pix;
+        const float bgdot = gC0 * bg0 + gC1 * bg1 + gC2 * bg2;
+        const float S_all = gC0 * (c[0] - Tf * bg0) + gC1 * (c[P] - Tf * bg1) + gC2 * (c[2 * P] - Tf * bg2)
+                          + gN0 * nn[0] + gN1 * nn[P] + gN2 * nn[2 * P]
+                          + gD * (depth_out * A) + gCf * a.out_confidence[vp];
+        rem = S_all + Tf * (bgdot - gA);
+    }
+    if (tid == 0) s_max_last = 0;
+    __syncthreads();
+    if (my_last > 0) atomicMax(&s_max_last, my_last);
+    __syncthreads();
+    const int n_eff = min(n, s_max_last);
+
+    float T = 1.f;
+    for (int base = 0; base < n_eff; base += BATCH) {
+        __syncthreads();
+        const int j = base + tid;
+        if (j < n_eff) {
+            const int id = w.inst_sorted[off + j];
+            const size_t idx = vN + id;
+            s_id[tid] = id;
+            s_g0[tid] = ldg4(w.geom0 + idx);
+            s_g1[tid] = ldg4(w.geom1 + idx);
+            s_f0[tid] = ldg4(w.feat0 + idx);
+            s_f1[tid] = ldg4(w.feat1 + idx);
+        }
+        __syncthreads();
+        const int cnt = min(BATCH, n_eff - base);
+        for (int k = 0; k < cnt; ++k) {
+            const float4 g0 = s_g0[k], g1 = s_g1[k];
+            const SplatEval e = eval_alpha(g0, g1, pxf, pyf);
+            const bool active = (base + k < my_last) && !e.skip;
+            if (__ballot_sync(0xffffffffu, active) == 0u) continue;
+            float val[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) val[q] = 0.f;
+            if (active) {
+                const float4 f0 = s_f0[k], f1 = s_f1[k];
+                const float wgt = e.alpha * T;
+                const float one_m = 1.f - e.alpha;
+                const float dpix = f0.w - g1.z * e.dx - g1.w * e.dy;
+                const float s = gC0 * f0.x + gC1 * f0.y + gC2 * f0.z + gN0 * f1.x + gN1 * f1.y + gN2 * f1.z
+                              + gD * dpix + gCf * f1.w;
+                rem -= wgt * s;
+                const float dalpha = T * s - rem / one_m;
+                T *= one_m;
+                // alpha = min(0.99, o*G): clamped -> no gradient
+                const float G = __expf(e.power);
+                const bool unclamped = (g1.y * G <= AGS_ALPHA_MAX);
+                const float dpower = unclamped ? e.alpha * dalpha : 0.f;
+                const float wgD = wgt * gD;
+                val[0] = dpower * (-g0.z * e.dx - g0.w * e.dy) - wgD * g1.z;    // d x
+                val[1] = dpower * (-g1.x * e.dy - g0.w * e.dx) - wgD * g1.w;    // d y
+                val[2] = -0.5f * e.dx * e.dx * dpower;                          // d conic a
+                val[3] = -e.dx * e.dy * dpower;                                 // d conic b
+                val[4] = -0.5f * e.dy * e.dy * dpower;                          // d conic c
+                val[5] = unclamped ? G * dalpha : 0.f;                          // d opacity
+                val[6] = wgt * gC0; val[7] = wgt * gC1; val[8] = wgt * gC2;     // d rgb
+                val[9] = wgt * gN0; val[10] = wgt * gN1; val[11] = wgt * gN2;   // d normal
+                val[12] = wgD;                                                  // d depth
+                val[13] = -wgD * e.dx;                                          // d slope x
+                val[14] = -wgD * e.dy;                                          // d slope y
+            }
+            const float r = butterfly16(val, lane);
+            if ((lane & 1) == 0 && lane < 30) atomicAdd(w.dsplat + (vN + s_id[k]) * 16 + (lane >> 1), r);
+        }
+    }
+}
+
+}  // namespace
+
+int ags_launch_composite_fwd(const AgsRenderArgs& a, const AgsWorkspace& w) {
+    dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE, a.B);
+    dim3 block(TILE, TILE);
+    composite_fwd_kernel<<<grid, block, 0, (cudaStream_t)a.stream>>>(a, w);
+    AGS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ags_launch_composite_bwd(const AgsRenderArgs& a, const AgsRenderGradArgs& g, const AgsWorkspace& w) {
+    dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE, a.B);
+    dim3 block(TILE, TILE);
+    composite_bwd_kernel<<<grid, block, 0, (cudaStream_t)a.stream>>>(a, g, w);
+    AGS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,333 @@
+// loss.cu -- K8: fused per-pixel post-processing + training loss + gradients w.r.t. the rasterizer
+// outputs.  Replaces ~150 small ATen launches per iteration of the reference:
+//   /root/reference/utils/operations.py:714-718   mask = opacity>1e-2, normalize(normal)*mask,
+//                                                 depth2normal (:172-219, quirk Q2 kept)
+//   /root/reference/mapping/gaussian_map.py:106-124  masked L1 rgb/depth, normal TV, consistency
+//                                                 (quirk Q1: (B,H,W)*(B,1,H,W) -> (B,B,H,W) mean)
+//   /root/reference/mapping/utils.py:14-16,28-62,120-121
+//   /root/reference/mapping/gaussian_map.py:132-139  track_performance per-frame means
+// and the autograd backward of all of it down to d rgb / d depth / d normal(raw).
+//
+// Two stencil passes, one thread per pixel, looping over the B frames (needed anyway for Q1):
+//   pass A: unit normal, d2n, adjoint of the un-normalised d2n vector, rgb gradient, loss sums
+//   pass B: depth gradient (L1 + gather of the d2n adjoints over the 3x3 window), normal gradient
+//           (consistency + gather of the TV terms, then through normalize*mask), TV loss sum
+// HBM roofline: reads 15 planes + writes 13 planes of B*H*W floats (+3 scratch planes twice).
+#include "ags_common.cuh"
+
+namespace {
+
+struct F3 { float x, y, z; };
+__device__ __forceinline__ F3 f3(float x, float y, float z) { F3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ F3 operator+(F3 a, F3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ F3 operator-(F3 a, F3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ F3 operator*(F3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float dot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ F3 cross(F3 a, F3 b) {
+    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+
+struct FrameGeom {       // per-frame constants of depth2normal (quirk Q2)
+    float ik00, ik11;    // 1/fov2focal(fov[0], H), 1/fov2focal(fov[1], W)
+    float cx, cy;        // W/2, H/2
+};
+
+__device__ __forceinline__ FrameGeom frame_geom(const float* fov, int f, int H, int W) {
+    FrameGeom g;
+    const float f0 = __ldg(fov + 2 * f), f1 = __ldg(fov + 2 * f + 1);
+    g.ik00 = (2.f * tanf(0.5f * f0)) / (float)H;
+    g.ik11 = (2.f * tanf(0.5f * f1)) / (float)W;
+    g.cx = 0.5f * W;
+    g.cy = 0.5f * H;
+    return g;
+}
+
+// camera-space point of pixel (y,x) and its d2n mask (opacity > 1e-2)
+__device__ __forceinline__ F3 cam_point(const float* depth, const float* opac, const FrameGeom& g, int W,
+                                        int y, int x, float& m) {
+    const float d = depth[(size_t)y * W + x];
+    m = (opac[(size_t)y * W + x] > 1e-2f) ? 1.f : 0.f;
+    return f3((x - g.cx) * d * g.ik00, (y - g.cy) * d * g.ik11, d);
+}
+
+// the four masked difference vectors of depth2normal at pixel (y,x); replicate padding makes the
+// out-of-image neighbour equal to the pixel itself, whose difference is exactly zero for a 0/1 mask
+struct D2N {
+    F3 pu, pl, pb, pr;
+    float mu, ml, mb, mr, mc;
+};
+
+__device__ __forceinline__ D2N d2n_vectors(const float* depth, const float* opac, const FrameGeom& g,
+                                           int H, int W, int y, int x) {
+    D2N r;
+    const F3 c = cam_point(depth, opac, g, W, y, x, r.mc);
+    const F3 pc = c * r.mc;
+    const F3 zero = f3(0.f, 0.f, 0.f);
+    r.mu = r.ml = r.mb = r.mr = 0.f;
+    r.pu = r.pl = r.pb = r.pr = zero;
+    float m;
+    if (y > 0)     { F3 q = cam_point(depth, opac, g, W, y - 1, x, m); r.mu = m; r.pu = (q - pc) * m; }
+    if (x > 0)     { F3 q = cam_point(depth, opac, g, W, y, x - 1, m); r.ml = m; r.pl = (q - pc) * m; }
+    if (y < H - 1) { F3 q = cam_point(depth, opac, g, W, y + 1, x, m); r.mb = m; r.pb = (q - pc) * m; }
+    if (x < W - 1) { F3 q = cam_point(depth, opac, g, W, y, x + 1, m); r.mr = m; r.pr = (q - pc) * m; }
+    return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-level accumulate of K values into global with one atomic per block per value
+template <int K>
+__device__ __forceinline__ void block_accumulate(float (&v)[K], float* const (&dst)[K]) {
+    __shared__ float sm[K][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float s = warp_sum(v[k]);
+        if (lane == 0) sm[k][wid] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        float s = 0.f;
+        const int nw = (blockDim.x + 31) >> 5;
+        for (int w = 0; w < nw; ++w) s += sm[threadIdx.x][w];
+        if (s != 0.f) atomicAdd(dst[threadIdx.x], s);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+loss_pass_a(AgsLossArgs a, float* g_nsum) {
+    const int H = a.H, W = a.W;
+    const size_t P = (size_t)H * W;
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = p < P;
+    const int y = in ? (int)(p / W) : 0, x = in ? (int)(p % W) : 0;
+    const float Bt = (float)a.B_total;
+    const float inv_rgb = 1.f / (Bt * 3.f * (float)P);
+    const float inv_d = 1.f / (Bt * (float)P);
+    const float inv_cons = 1.f / (Bt * Bt * (float)P);
+    float msum = 0.f;
+    if (in) {
+        if (a.vis_count) msum = (float)a.vis_count[p];
+        else for (int f = 0; f < a.B; ++f) msum += (a.opacity[(size_t)f * P + p] > 1e-3f) ? 1.f : 0.f;
+    }
+    float acc_rgb = 0.f, acc_d = 0.f, acc_cons = 0.f;
+    for (int f = 0; f < a.B; ++f) {
+        float fr_rgb = 0.f, fr_d = 0.f;
+        if (in) {
+            const float* opac = a.opacity + (size_t)f * P;
+            const float* depth = a.depth + (size_t)f * P;
+            const float A = opac[p];
+            const float mvis = (A > 1e-3f) ? 1.f : 0.f;
+            const float m2 = (A > 1e-2f) ? 1.f : 0.f;
+            // ---- L1 rgb + gradient
+            const float* rp = a.rgb + (size_t)f * 3 * P + p;
+            const float* rg = a.rgb_gt + (size_t)f * 3 * P + p;
+            float* drgb = a.d_rgb + (size_t)f * 3 * P + p;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float e = (rp[c * P] - rg[c * P]) * mvis;
+                fr_rgb += fabsf(e);
+                drgb[c * P] = (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f)) * mvis * inv_rgb;
+            }
+            // ---- L1 depth (gradient is finished in pass B)
+            const float dg = a.depth_gt[(size_t)f * P + p];
+            const float md = (dg > 0.f) ? 1.f : 0.f;
+            fr_d = fabsf((depth[p] - dg) * md);
+            // ---- unit normal
+            const float* np_ = a.normal + (size_t)f * 3 * P + p;
+            const F3 n = f3(np_[0], np_[P], np_[2 * P]);
+            const float nn = fmaxf(sqrtf(dot(n, n)), 1e-12f);
+            const F3 nu = n * (m2 / nn);
+            float* no = a.normal_unit + (size_t)f * 3 * P + p;
+            no[0] = nu.x; no[P] = nu.y; no[2 * P] = nu.z;
+            // ---- depth2normal
+            const FrameGeom g = frame_geom(a.fov, f, H, W);
+            const D2N v = d2n_vectors(depth, opac, g, H, W, y, x);
+            const F3 ns = cross(v.pu, v.pl) + cross(v.pr, v.pu) + cross(v.pb, v.pr) + cross(v.pl, v.pb);
+            const float nsn = fmaxf(sqrtf(dot(ns, ns)), 1e-12f);
+            const F3 u = ns * (1.f / nsn);
+            const F3 d2n = u * m2;
+            float* dn = a.d2n + (size_t)f * 3 * P + p;
+            dn[0] = d2n.x; dn[P] = d2n.y; dn[2 * P] = d2n.z;
+            // ---- consistency loss and the adjoint of the un-normalised d2n vector
+            acc_cons += (1.f - dot(nu, d2n)) * msum;
+            const float wc = -a.w_cons * msum * inv_cons;                // dL/d(nu . d2n)
+            const F3 gd = nu * (wc * m2);                                // dL/d u  (d2n = u*m2)
+            const F3 gns = (gd - u * dot(u, gd)) * (1.f / nsn);
+            float* gs = g_nsum + (size_t)f * 3 * P + p;
+            gs[0] = gns.x; gs[P] = gns.y; gs[2 * P] = gns.z;
+        }
+        acc_rgb += fr_rgb;
+        acc_d += fr_d;
+        float v2[2] = {fr_rgb / (3.f * (float)P), fr_d / (float)P};
+        float* const d2[2] = {a.loss_terms + 4 + 2 * f, a.loss_terms + 4 + 2 * f + 1};
+        block_accumulate<2>(v2, d2);
+    }
+    float v3[3] = {acc_rgb * inv_rgb, acc_d * inv_d, acc_cons * inv_cons};
+    float* const d3[3] = {a.loss_terms + 0, a.loss_terms + 1, a.loss_terms + 2};
+    block_accumulate<3>(v3, d3);
+}
+
+// TV helper: value and derivative factor of one one-sided difference
+__device__ __forceinline__ void tv_term(F3 np_, F3 nq, float dp, float dq, float md, float inv2s2,
+                                        float& val, float& coef) {
+    const F3 dl = np_ - nq;
+    const float nd = dot(dl, dl);
+    const float dd = (dp - dq) * (dp - dq);
+    const float gate = (dd <= 1e-4f) ? md : 0.f;
+    const float e = __expf(-nd * inv2s2);
+    val = gate * e * nd;
+    coef = gate * e * (1.f - nd * inv2s2);       // d val / d nd
+}
+
+__global__ void __launch_bounds__(256)
+loss_pass_b(AgsLossArgs a, const float* g_nsum) {
+    const int H = a.H, W = a.W;
+    const size_t P = (size_t)H * W;
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = p < P;
+    const int y = in ? (int)(p / W) : 0, x = in ? (int)(p % W) : 0;
+    const float Bt = (float)a.B_total;
+    const float inv_d = 1.f / (Bt * (float)P);
+    const float inv_cons = 1.f / (Bt * Bt * (float)P);
+    const float inv_tv = 1.f / (Bt * 4.f * (float)P);
+    const float inv2s2 = 1.f / (2.f * 0.3f * 0.3f);
+    float msum = 0.f;
+    if (in) {
+        if (a.vis_count) msum = (float)a.vis_count[p];
+        else for (int f = 0; f < a.B; ++f) msum += (a.opacity[(size_t)f * P + p] > 1e-3f) ? 1.f : 0.f;
+    }
+    float acc_tv = 0.f;
+    for (int f = 0; f < a.B && in; ++f) {
+        const float* opac = a.opacity + (size_t)f * P;
+        const float* depth = a.depth + (size_t)f * P;
+        const float* dgt = a.depth_gt + (size_t)f * P;
+        const float* nu_ = a.normal_unit + (size_t)f * 3 * P;
+        const float* gs_ = g_nsum + (size_t)f * 3 * P;
+        const FrameGeom g = frame_geom(a.fov, f, H, W);
+        auto NU = [&](int yy, int xx) { const size_t q = (size_t)yy * W + xx; return f3(nu_[q], nu_[P + q], nu_[2 * P + q]); };
+        auto GS = [&](int yy, int xx) { const size_t q = (size_t)yy * W + xx; return f3(gs_[q], gs_[P + q], gs_[2 * P + q]); };
+        const float dp = depth[p];
+        const float md_p = (dgt[p] > 0.f) ? 1.f : 0.f;
+        const float m2 = (opac[p] > 1e-2f) ? 1.f : 0.f;
+
+        // ---------------- depth gradient: L1 + d2n gather
+        const float e = (dp - dgt[p]) * md_p;
+        float ddepth = a.w_depth * (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f)) * md_p * inv_d;
+        {
+            F3 dc = f3(0.f, 0.f, 0.f);
+            // own pixel: p_c enters all four difference vectors with a minus sign
+            {
+                const D2N v = d2n_vectors(depth, opac, g, H, W, y, x);
+                const F3 gq = GS(y, x);
+                const F3 dpu = cross(v.pl, gq) + cross(gq, v.pr);
+                const F3 dpl = cross(gq, v.pu) + cross(v.pb, gq);
+                const F3 dpb = cross(v.pr, gq) + cross(gq, v.pl);
+                const F3 dpr = cross(v.pu, gq) + cross(gq, v.pb);
+                const F3 dpc = (dpu * v.mu + dpl * v.ml + dpb * v.mb + dpr * v.mr) * (-1.f);
+                dc = dc + dpc * v.mc;
+            }
+            // neighbours q for which this pixel is the up / left / bottom / right sample
+            if (y < H - 1) {   // q below: p is q's "up"
+                const D2N v = d2n_vectors(depth, opac, g, H, W, y + 1, x);
+                const F3 gq = GS(y + 1, x);
+                dc = dc + (cross(v.pl, gq) + cross(gq, v.pr)) * v.mu;
+            }
+            if (x < W - 1) {   // q right: p is q's "left"
+                const D2N v = d2n_vectors(depth, opac, g, H, W, y, x + 1);
+                const F3 gq = GS(y, x + 1);
+                dc = dc + (cross(gq, v.pu) + cross(v.pb, gq)) * v.ml;
+            }
+            if (y > 0) {       // q above: p is q's "bottom"
+                const D2N v = d2n_vectors(depth, opac, g, H, W, y - 1, x);
+                const F3 gq = GS(y - 1, x);
+                dc = dc + (cross(v.pr, gq) + cross(gq, v.pl)) * v.mb;
+            }
+            if (x > 0) {       // q left: p is q's "right"
+                const D2N v = d2n_vectors(depth, opac, g, H, W, y, x - 1);
+                const F3 gq = GS(y, x - 1);
+                dc = dc + (cross(v.pu, gq) + cross(gq, v.pb)) * v.mr;
+            }
+            ddepth += dc.x * (x - g.cx) * g.ik00 + dc.y * (y - g.cy) * g.ik11 + dc.z;
+        }
+        a.d_depth[(size_t)f * P + p] = ddepth;
+
+        // ---------------- normal gradient: consistency + TV gather, then through normalize*mask
+        const F3 nu = NU(y, x);
+        const float* d2p = a.d2n + (size_t)f * 3 * P + p;
+        const F3 d2n = f3(d2p[0], d2p[P], d2p[2 * P]);
+        F3 gnu = d2n * (-a.w_cons * msum * inv_cons);
+        {
+            const float ctv = a.w_tv * inv_tv;
+            float val, coef;
+            // own four differences
+            if (x < W - 1) { const F3 nq = NU(y, x + 1); tv_term(nu, nq, dp, depth[p + 1], md_p, inv2s2, val, coef);
+                             acc_tv += val; gnu = gnu + (nu - nq) * (2.f * coef * ctv); }
+            if (x > 0)     { const F3 nq = NU(y, x - 1); tv_term(nu, nq, dp, depth[p - 1], md_p, inv2s2, val, coef);
+                             acc_tv += val; gnu = gnu + (nu - nq) * (2.f * coef * ctv); }
+            if (y < H - 1) { const F3 nq = NU(y + 1, x); tv_term(nu, nq, dp, depth[p + W], md_p, inv2s2, val, coef);
+                             acc_tv += val; gnu = gnu + (nu - nq) * (2.f * coef * ctv); }
+            if (y > 0)     { const F3 nq = NU(y - 1, x); tv_term(nu, nq, dp, depth[p - W], md_p, inv2s2, val, coef);
+                             acc_tv += val; gnu = gnu + (nu - nq) * (2.f * coef * ctv); }
+            // differences of the neighbours that reference this pixel (their mask, their centre)
+            if (x > 0)     { const F3 nq = NU(y, x - 1); const float mdq = (dgt[p - 1] > 0.f) ? 1.f : 0.f;
+                             tv_term(nq, nu, depth[p - 1], dp, mdq, inv2s2, val, coef);
+                             gnu = gnu - (nq - nu) * (2.f * coef * ctv); }
+            if (x < W - 1) { const F3 nq = NU(y, x + 1); const float mdq = (dgt[p + 1] > 0.f) ? 1.f : 0.f;
+                             tv_term(nq, nu, depth[p + 1], dp, mdq, inv2s2, val, coef);
+                             gnu = gnu - (nq - nu) * (2.f * coef * ctv); }
+            if (y > 0)     { const F3 nq = NU(y - 1, x); const float mdq = (dgt[p - W] > 0.f) ? 1.f : 0.f;
+                             tv_term(nq, nu, depth[p - W], dp, mdq, inv2s2, val, coef);
+                             gnu = gnu - (nq - nu) * (2.f * coef * ctv); }
+            if (y < H - 1) { const F3 nq = NU(y + 1, x); const float mdq = (dgt[p + W] > 0.f) ? 1.f : 0.f;
+                             tv_term(nq, nu, depth[p + W], dp, mdq, inv2s2, val, coef);
+                             gnu = gnu - (nq - nu) * (2.f * coef * ctv); }
+        }
+        {
+            const float* np_ = a.normal + (size_t)f * 3 * P + p;
+            const F3 n = f3(np_[0], np_[P], np_[2 * P]);
+            const float nn = fmaxf(sqrtf(dot(n, n)), 1e-12f);
+            const F3 uh = n * (1.f / nn);
+            const F3 gn = (gnu - uh * dot(uh, gnu)) * (m2 / nn);
+            float* dn = a.d_normal + (size_t)f * 3 * P + p;
+            dn[0] = gn.x; dn[P] = gn.y; dn[2 * P] = gn.z;
+        }
+    }
+    float v1[1] = {acc_tv * inv_tv};
+    float* const d1[1] = {a.loss_terms + 3};
+    block_accumulate<1>(v1, d1);
+}
+
+}  // namespace
+
+extern "C" size_t ags_loss_scratch_bytes(int32_t B, int32_t H, int32_t W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    return ags_align256((size_t)B * 3 * H * W * sizeof(float));
+}
+
+extern "C" int ags_loss_forward_backward(const AgsLossArgs* a) {
+    AGS_CHECK_ARG(a != nullptr, "args is NULL");
+    AGS_CHECK_ARG(a->B > 0 && a->H > 0 && a->W > 0 && a->B_total >= a->B, "bad sizes B=%d H=%d W=%d B_total=%d",
+                  a->B, a->H, a->W, a->B_total);
+    AGS_CHECK_ARG(a->rgb && a->normal && a->depth && a->opacity && a->rgb_gt && a->depth_gt && a->fov,
+                  "NULL input");
+    AGS_CHECK_ARG(a->normal_unit && a->d2n && a->d_rgb && a->d_normal && a->d_depth && a->loss_terms,
+                  "NULL output");
+    AGS_CHECK_ARG(a->workspace && a->workspace_bytes >= ags_loss_scratch_bytes(a->B, a->H, a->W),
+                  "loss workspace too small");
+    cudaStream_t st = (cudaStream_t)a->stream;
+    AGS_CHECK_CUDA(cudaMemsetAsync(a->loss_terms, 0, (4 + 2 * (size_t)a->B) * sizeof(float), st));
+    const size_t P = (size_t)a->H * a->W;
+    const int blocks = (int)((P + 255) / 256);
+    float* g_nsum = (float*)a->workspace;
+    loss_pass_a<<<blocks, 256, 0, st>>>(*a, g_nsum);
+    AGS_CHECK_CUDA(cudaGetLastError());
+    loss_pass_b<<<blocks, 256, 0, st>>>(*a, g_nsum);
+    AGS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,419 @@
+// project.cu -- K1 project_fwd (+ per-tile counting) and K6 project_bwd.
+//
+// Replaces the per-Gaussian stage of the native extension behind
+// /root/reference/utils/operations.py:701-713 and, in RAW mode, the activations of
+// /root/reference/mapping/gaussian_map.py:529-545 (fused here and in the backward).
+// One thread owns one Gaussian and loops over the B views of the batch: the rotation matrix and the
+// 3D covariance are view independent and are built once.
+//
+// HBM roofline: K1 reads 60 B/Gaussian and writes 72+8 B per (view, Gaussian); K6 reads 64 B grad
+// record + 56 B params per visible (view, Gaussian) and writes 56 B/Gaussian. Pure streaming.
+#include "ags_common.cuh"
+
+namespace {
+
+struct GaussAct {          // activated parameters of one Gaussian + what the activation backward needs
+    float px, py, pz;
+    float s[3];
+    float q[4];            // unit quaternion r,x,y,z (as used)
+    float o;
+    float R[9];
+    float Sig[6];          // xx xy xz yy yz zz
+    // RAW mode bookkeeping
+    float qn;              // |raw q|
+    bool s_pass[3];        // clamp passes gradient
+};
+
+__device__ __forceinline__ void activate(GaussAct& g, const AgsRenderArgs& a, int i) {
+    g.px = __ldg(a.means3D + 3 * i);
+    g.py = __ldg(a.means3D + 3 * i + 1);
+    g.pz = __ldg(a.means3D + 3 * i + 2);
+    float sr[3] = {__ldg(a.scales + 3 * i), __ldg(a.scales + 3 * i + 1), __ldg(a.scales + 3 * i + 2)};
+    float qr[4] = {__ldg(a.rotations + 4 * i), __ldg(a.rotations + 4 * i + 1),
+                   __ldg(a.rotations + 4 * i + 2), __ldg(a.rotations + 4 * i + 3)};
+    float orw = __ldg(a.opacities + i);
+    if (a.param_mode == AGS_PARAMS_RAW) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float e = a.scale_factor * expf(sr[k]);
+            g.s_pass[k] = (e <= a.scale_max);       // torch.clamp passes the gradient on [min,max]
+            g.s[k] = fminf(fmaxf(e, 0.f), a.scale_max) * a.scale_modifier;
+        }
+        float n = sqrtf(qr[0] * qr[0] + qr[1] * qr[1] + qr[2] * qr[2] + qr[3] * qr[3]);
+        g.qn = fmaxf(n, 1e-12f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) g.q[k] = qr[k] / g.qn;
+        g.o = 1.f / (1.f + expf(-orw));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { g.s[k] = sr[k] * a.scale_modifier; g.s_pass[k] = true; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) g.q[k] = qr[k];
+        g.qn = 1.f;
+        g.o = orw;
+    }
+    const float r = g.q[0], x = g.q[1], y = g.q[2], z = g.q[3];
+    g.R[0] = 1.f - 2.f * (y * y + z * z); g.R[1] = 2.f * (x * y - r * z); g.R[2] = 2.f * (x * z + r * y);
+    g.R[3] = 2.f * (x * y + r * z); g.R[4] = 1.f - 2.f * (x * x + z * z); g.R[5] = 2.f * (y * z - r * x);
+    g.R[6] = 2.f * (x * z - r * y); g.R[7] = 2.f * (y * z + r * x); g.R[8] = 1.f - 2.f * (x * x + y * y);
+    const float s0 = g.s[0] * g.s[0], s1 = g.s[1] * g.s[1], s2 = g.s[2] * g.s[2];
+    const float* R = g.R;
+    g.Sig[0] = R[0] * R[0] * s0 + R[1] * R[1] * s1 + R[2] * R[2] * s2;
+    g.Sig[1] = R[0] * R[3] * s0 + R[1] * R[4] * s1 + R[2] * R[5] * s2;
+    g.Sig[2] = R[0] * R[6] * s0 + R[1] * R[7] * s1 + R[2] * R[8] * s2;
+    g.Sig[3] = R[3] * R[3] * s0 + R[4] * R[4] * s1 + R[5] * R[5] * s2;
+    g.Sig[4] = R[3] * R[6] * s0 + R[4] * R[7] * s1 + R[5] * R[8] * s2;
+    g.Sig[5] = R[6] * R[6] * s0 + R[7] * R[7] * s1 + R[8] * R[8] * s2;
+}
+
+struct ViewProj {          // forward intermediates of one (view, Gaussian)
+    float t[3];
+    float homx, homy, inv_w, ndcx, ndcy;
+    float xg, yg;
+    float fx, fy;
+    float ux, uy;          // clamped t.x/t.z , t.y/t.z
+    bool ux_free, uy_free; // not clamped
+    float J00, J02, J11, J12;
+    float T0[3], T1[3];
+    float ST0[3], ST1[3];  // Sigma*T0, Sigma*T1
+    float a, b, c, det;
+    float ca, cb, cc;
+    float nv[3];           // flipped view-space normal
+    float sigma_n;         // +1 / -1 flip
+    float cosv;            // n.t before the flip
+    float c0, Dc;          // after the flip / clamped cos
+    bool Dc_free;
+    float sx, sy;
+    int radius;
+    bool valid;
+    int minx, miny, maxx, maxy;
+};
+
+__device__ __forceinline__ void sym_mul(const float* S, const float* v, float* o) {
+    o[0] = S[0] * v[0] + S[1] * v[1] + S[2] * v[2];
+    o[1] = S[1] * v[0] + S[3] * v[1] + S[4] * v[2];
+    o[2] = S[2] * v[0] + S[4] * v[1] + S[5] * v[2];
+}
+
+__device__ __forceinline__ void project_view(ViewProj& o, const GaussAct& g, const Cam& c, int H, int W,
+                                              bool front_only) {
+    const float* V = c.V;
+    const float* M = c.M;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) o.t[j] = g.px * V[j] + g.py * V[4 + j] + g.pz * V[8 + j] + V[12 + j];
+    o.homx = g.px * M[0] + g.py * M[4] + g.pz * M[8] + M[12];
+    o.homy = g.px * M[1] + g.py * M[5] + g.pz * M[9] + M[13];
+    const float homw = g.px * M[3] + g.py * M[7] + g.pz * M[11] + M[15];
+    o.inv_w = 1.f / (homw + 1e-7f);
+    o.ndcx = o.homx * o.inv_w;
+    o.ndcy = o.homy * o.inv_w;
+    o.xg = ((o.ndcx + 1.f) * W - 1.f) * 0.5f;
+    o.yg = ((o.ndcy + 1.f) * H - 1.f) * 0.5f;
+    o.fx = W / (2.f * c.tanx);
+    o.fy = H / (2.f * c.tany);
+    const float tz = o.t[2];
+    const float limx = 1.3f * c.tanx, limy = 1.3f * c.tany;
+    const float rx = o.t[0] / tz, ry = o.t[1] / tz;
+    o.ux = fminf(fmaxf(rx, -limx), limx);
+    o.uy = fminf(fmaxf(ry, -limy), limy);
+    o.ux_free = (rx >= -limx) && (rx <= limx);
+    o.uy_free = (ry >= -limy) && (ry <= limy);
+    o.J00 = o.fx / tz;
+    o.J11 = o.fy / tz;
+    o.J02 = -o.fx * (o.ux * tz) / (tz * tz);
+    o.J12 = -o.fy * (o.uy * tz) / (tz * tz);
+    // Wr[j][k] = V[4k + j]
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        o.T0[k] = o.J00 * V[4 * k + 0] + o.J02 * V[4 * k + 2];
+        o.T1[k] = o.J11 * V[4 * k + 1] + o.J12 * V[4 * k + 2];
+    }
+    sym_mul(g.Sig, o.T0, o.ST0);
+    sym_mul(g.Sig, o.T1, o.ST1);
+    o.a = o.T0[0] * o.ST0[0] + o.T0[1] * o.ST0[1] + o.T0[2] * o.ST0[2] + AGS_LOWPASS;
+    o.b = o.T0[0] * o.ST1[0] + o.T0[1] * o.ST1[1] + o.T0[2] * o.ST1[2];
+    o.c = o.T1[0] * o.ST1[0] + o.T1[1] * o.ST1[1] + o.T1[2] * o.ST1[2] + AGS_LOWPASS;
+    o.det = o.a * o.c - o.b * o.b;
+    const float det_safe = (o.det == 0.f) ? 1.f : o.det;
+    o.ca = o.c / det_safe;
+    o.cb = -o.b / det_safe;
+    o.cc = o.a / det_safe;
+    const float mid = 0.5f * (o.a + o.c);
+    const float lam1 = mid + sqrtf(fmaxf(mid * mid - o.det, 0.1f));
+    o.radius = (int)ceilf(3.f * sqrtf(lam1));
+    // normal: third column of R, to view space, flipped toward the camera
+    float nw[3] = {g.R[2], g.R[5], g.R[8]};
+    float nv[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) nv[j] = nw[0] * V[j] + nw[1] * V[4 + j] + nw[2] * V[8 + j];
+    o.cosv = nv[0] * o.t[0] + nv[1] * o.t[1] + nv[2] * o.t[2];
+    o.sigma_n = (o.cosv > 0.f) ? -1.f : 1.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) o.nv[j] = o.sigma_n * nv[j];
+    o.c0 = o.nv[0] * o.t[0] + o.nv[1] * o.t[1] + o.nv[2] * o.t[2];
+    const float d = o.c0 / tz;
+    o.Dc_free = (d <= -AGS_SLOPE_COS_MIN);
+    o.Dc = fminf(d, -AGS_SLOPE_COS_MIN);
+    o.sx = -tz * o.nv[0] / (o.Dc * o.fx);
+    o.sy = -tz * o.nv[1] / (o.Dc * o.fy);
+    // culling + tile rect
+    bool valid = (tz > AGS_NEAR_CULL) && (o.det != 0.f);
+    if (front_only && o.cosv >= 0.f) valid = false;
+    const int tiles_x = (W + TILE - 1) / TILE, tiles_y = (H + TILE - 1) / TILE;
+    const float rf = (float)o.radius;
+    o.minx = min(tiles_x, max(0, (int)((o.xg - rf) / TILE)));
+    o.miny = min(tiles_y, max(0, (int)((o.yg - rf) / TILE)));
+    o.maxx = min(tiles_x, max(0, (int)((o.xg + rf + TILE - 1) / TILE)));
+    o.maxy = min(tiles_y, max(0, (int)((o.yg + rf + TILE - 1) / TILE)));
+    if ((o.maxx - o.minx) * (o.maxy - o.miny) <= 0) valid = false;
+    if (!(o.xg == o.xg) || !(o.yg == o.yg) || !(rf == rf)) valid = false;   // NaN guard
+    o.valid = valid;
+    if (!valid) o.radius = 0;
+}
+
+// K1 ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+project_fwd_kernel(AgsRenderArgs a, AgsWorkspace w, int for_backward) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    GaussAct g;
+    activate(g, a, i);
+    const float cr = __ldg(a.colors + 3 * i), cg = __ldg(a.colors + 3 * i + 1), cb = __ldg(a.colors + 3 * i + 2);
+    const float conf = a.confidences ? __ldg(a.confidences + i) : 0.f;
+    const int tiles_x = (a.W + TILE - 1) / TILE, tiles_y = (a.H + TILE - 1) / TILE;
+    const int tiles = tiles_x * tiles_y;
+    int nvis = 0;
+    for (int v = 0; v < a.B; ++v) {
+        Cam cam;
+        load_cam(cam, a.viewmatrix, a.projmatrix, a.tanfov, v);
+        ViewProj p;
+        project_view(p, g, cam, a.H, a.W, a.front_only != 0);
+        const size_t idx = (size_t)v * a.N + i;
+        a.radii[idx] = p.radius;
+        if (a.importance) a.importance[idx] = 0.f;
+        if (a.count) a.count[idx] = 0;
+        if (!p.valid) {
+            w.rect[idx] = make_uint2(0u, 0u);
+            continue;
+        }
+        ++nvis;
+        w.geom0[idx] = make_float4(p.xg, p.yg, p.ca, p.cb);
+        w.geom1[idx] = make_float4(p.cc, g.o, p.sx, p.sy);
+        w.feat0[idx] = make_float4(cr, cg, cb, p.t[2]);
+        w.feat1[idx] = make_float4(p.nv[0], p.nv[1], p.nv[2], conf);
+        w.rect[idx] = make_uint2((unsigned)p.minx | ((unsigned)p.maxx << 16),
+                                 (unsigned)p.miny | ((unsigned)p.maxy << 16));
+        if (for_backward) {
+            float4* d = reinterpret_cast<float4*>(w.dsplat + idx * 16);
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            d[0] = z; d[1] = z; d[2] = z; d[3] = z;
+        }
+        int32_t* tc = w.tile_count + (size_t)v * tiles;
+        for (int ty = p.miny; ty < p.maxy; ++ty)
+            for (int tx = p.minx; tx < p.maxx; ++tx) atomicAdd(tc + ty * tiles_x + tx, 1);
+    }
+    // visible-count statistic, one atomic per warp
+    unsigned m = __activemask();
+    for (int off = 16; off > 0; off >>= 1) nvis += __shfl_down_sync(m, nvis, off);
+    if ((threadIdx.x & 31) == 0 && nvis) atomicAdd(a.stats + AGS_STAT_VISIBLE, nvis);
+}
+
+// K6 ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+project_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    GaussAct g;
+    activate(g, a, i);
+    float dp[3] = {0.f, 0.f, 0.f};
+    float Gs[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // symmetric (G + G^T) of dL/dSigma: xx xy xz yy yz zz
+    float dnw[3] = {0.f, 0.f, 0.f};
+    float d_o = 0.f, dcol[3] = {0.f, 0.f, 0.f};
+    for (int v = 0; v < a.B; ++v) {
+        const size_t idx = (size_t)v * a.N + i;
+        const bool vis = a.radii[idx] > 0;
+        if (gr.d_means2D) {
+            float gx = 0.f, gy = 0.f;
+            if (vis) { gx = w.dsplat[idx * 16 + 0]; gy = w.dsplat[idx * 16 + 1]; }
+            gr.d_means2D[idx * 3 + 0] = gx; gr.d_means2D[idx * 3 + 1] = gy; gr.d_means2D[idx * 3 + 2] = 0.f;
+        }
+        if (!vis) continue;
+        Cam cam;
+        load_cam(cam, a.viewmatrix, a.projmatrix, a.tanfov, v);
+        ViewProj p;
+        project_view(p, g, cam, a.H, a.W, false);
+        const float4* dr = reinterpret_cast<const float4*>(w.dsplat + idx * 16);
+        const float4 d0 = dr[0], d1 = dr[1], d2 = dr[2], d3 = dr[3];
+        const float dxg = d0.x, dyg = d0.y, dca = d0.z, dcb = d0.w;
+        const float dcc = d1.x;
+        d_o += d1.y;
+        dcol[0] += d1.z; dcol[1] += d1.w; dcol[2] += d2.x;
+        float dnv[3] = {d2.y, d2.z, d2.w};
+        const float dz = d3.x, dsx = d3.y, dsy = d3.z;
+        const float* V = cam.V;
+        const float* M = cam.M;
+        const float tz = p.t[2];
+        float dt[3] = {0.f, 0.f, 0.f};
+        // ---- screen position -> mean
+        {
+            const float dndcx = dxg * 0.5f * a.W, dndcy = dyg * 0.5f * a.H;
+            const float dhx = dndcx * p.inv_w, dhy = dndcy * p.inv_w;
+            const float dhw = -(p.ndcx * dndcx + p.ndcy * dndcy) * p.inv_w;
+            dp[0] += M[0] * dhx + M[1] * dhy + M[3] * dhw;
+            dp[1] += M[4] * dhx + M[5] * dhy + M[7] * dhw;
+            dp[2] += M[8] * dhx + M[9] * dhy + M[11] * dhw;
+        }
+        // ---- conic -> cov2
+        float da, db, dc;
+        {
+            const float id2 = 1.f / (p.det * p.det);
+            da = (-p.c * p.c * dca + p.b * p.c * dcb - p.b * p.b * dcc) * id2;
+            db = (2.f * p.b * p.c * dca - (p.a * p.c + p.b * p.b) * dcb + 2.f * p.a * p.b * dcc) * id2;
+            dc = (-p.b * p.b * dca + p.a * p.b * dcb - p.a * p.a * dcc) * id2;
+        }
+        // ---- cov2 = T Sigma T^T
+        {
+            const float* T0 = p.T0; const float* T1 = p.T1;
+            Gs[0] += 2.f * da * T0[0] * T0[0] + 2.f * db * T0[0] * T1[0] + 2.f * dc * T1[0] * T1[0];
+            Gs[1] += 2.f * da * T0[0] * T0[1] + db * (T0[0] * T1[1] + T0[1] * T1[0]) + 2.f * dc * T1[0] * T1[1];
+            Gs[2] += 2.f * da * T0[0] * T0[2] + db * (T0[0] * T1[2] + T0[2] * T1[0]) + 2.f * dc * T1[0] * T1[2];
+            Gs[3] += 2.f * da * T0[1] * T0[1] + 2.f * db * T0[1] * T1[1] + 2.f * dc * T1[1] * T1[1];
+            Gs[4] += 2.f * da * T0[1] * T0[2] + db * (T0[1] * T1[2] + T0[2] * T1[1]) + 2.f * dc * T1[1] * T1[2];
+            Gs[5] += 2.f * da * T0[2] * T0[2] + 2.f * db * T0[2] * T1[2] + 2.f * dc * T1[2] * T1[2];
+            float dT0[3], dT1[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                dT0[k] = 2.f * da * p.ST0[k] + db * p.ST1[k];
+                dT1[k] = 2.f * dc * p.ST1[k] + db * p.ST0[k];
+            }
+            // T0 = J00*Wr[0,:] + J02*Wr[2,:],  Wr[j][k] = V[4k+j]
+            float dJ00 = 0.f, dJ02 = 0.f, dJ11 = 0.f, dJ12 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                dJ00 += dT0[k] * V[4 * k + 0];
+                dJ02 += dT0[k] * V[4 * k + 2];
+                dJ11 += dT1[k] * V[4 * k + 1];
+                dJ12 += dT1[k] * V[4 * k + 2];
+            }
+            const float itz = 1.f / tz, itz2 = itz * itz;
+            // J00 = fx/tz ; J02 = -fx*u/tz (u = clamp(tx/tz))
+            dt[2] += -dJ00 * p.fx * itz2 - dJ11 * p.fy * itz2;
+            dt[2] += dJ02 * p.fx * p.ux * itz2 + dJ12 * p.fy * p.uy * itz2;
+            const float dux = -dJ02 * p.fx * itz, duy = -dJ12 * p.fy * itz;
+            if (p.ux_free) { dt[0] += dux * itz; dt[2] += -dux * p.t[0] * itz2; }
+            if (p.uy_free) { dt[1] += duy * itz; dt[2] += -duy * p.t[1] * itz2; }
+        }
+        // ---- depth + plane slopes + normal
+        {
+            dt[2] += dz;
+            // sx = -tz*nv.x/(Dc*fx)
+            dnv[0] += -tz / (p.Dc * p.fx) * dsx;
+            dnv[1] += -tz / (p.Dc * p.fy) * dsy;
+            dt[2] += -p.nv[0] / (p.Dc * p.fx) * dsx - p.nv[1] / (p.Dc * p.fy) * dsy;
+            const float dDc = -(p.sx * dsx + p.sy * dsy) / p.Dc;
+            if (p.Dc_free) {
+                const float dc0 = dDc / tz;
+                dt[2] += -dDc * p.c0 / (tz * tz);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { dnv[j] += dc0 * p.t[j]; dt[j] += dc0 * p.nv[j]; }
+            }
+            // nv = sigma * Wr nw  -> dnw_k = sigma * sum_j V[4k+j] dnv_j
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                dnw[k] += p.sigma_n * (V[4 * k] * dnv[0] + V[4 * k + 1] * dnv[1] + V[4 * k + 2] * dnv[2]);
+        }
+        // ---- t = Wr p + tr
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dp[k] += V[4 * k] * dt[0] + V[4 * k + 1] * dt[1] + V[4 * k + 2] * dt[2];
+    }
+    // ---- Sigma = M3 M3^T, M3 = R diag(s):  dM3 = Gs * M3
+    const float* R = g.R;
+    float dR[9], ds[3];
+    {
+        float M3[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) M3[3 * r + k] = R[3 * r + k] * g.s[k];
+        float dM3[9];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float col[3] = {M3[k], M3[3 + k], M3[6 + k]}, o3[3];
+            sym_mul(Gs, col, o3);
+            dM3[k] = o3[0]; dM3[3 + k] = o3[1]; dM3[6 + k] = o3[2];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            ds[k] = dM3[k] * R[k] + dM3[3 + k] * R[3 + k] + dM3[6 + k] * R[6 + k];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) dR[3 * r + k] = dM3[3 * r + k] * g.s[k];
+        }
+        dR[2] += dnw[0]; dR[5] += dnw[1]; dR[8] += dnw[2];
+    }
+    float dq[4];
+    {
+        const float r = g.q[0], x = g.q[1], y = g.q[2], z = g.q[3];
+        dq[0] = 2.f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]);
+        dq[1] = 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.f * x * dR[8]);
+        dq[2] = 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.f * y * dR[8]);
+        dq[3] = 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]);
+    }
+    float dsr[3], dqr[4], dor;
+    if (a.param_mode == AGS_PARAMS_RAW) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            // s = clamp(sf*exp(raw)) * modifier ; d/draw = s (when the clamp passes)
+            dsr[k] = g.s_pass[k] ? ds[k] * g.s[k] : 0.f;
+        }
+        const float qd = g.q[0] * dq[0] + g.q[1] * dq[1] + g.q[2] * dq[2] + g.q[3] * dq[3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dqr[k] = (dq[k] - g.q[k] * qd) / g.qn;
+        dor = d_o * g.o * (1.f - g.o);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dsr[k] = ds[k] * a.scale_modifier;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dqr[k] = dq[k];
+        dor = d_o;
+    }
+    if (gr.accumulate) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            gr.d_means3D[3 * i + k] += dp[k];
+            gr.d_scales[3 * i + k] += dsr[k];
+            gr.d_colors[3 * i + k] += dcol[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gr.d_rotations[4 * i + k] += dqr[k];
+        gr.d_opacities[i] += dor;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            gr.d_means3D[3 * i + k] = dp[k];
+            gr.d_scales[3 * i + k] = dsr[k];
+            gr.d_colors[3 * i + k] = dcol[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gr.d_rotations[4 * i + k] = dqr[k];
+        gr.d_opacities[i] = dor;
+    }
+}
+
+}  // namespace
+
+int ags_launch_project_fwd(const AgsRenderArgs& a, const AgsWorkspace& w, bool for_backward) {
+    if (a.N == 0) return 0;
+    const int threads = 128;
+    project_fwd_kernel<<<(a.N + threads - 1) / threads, threads, 0, (cudaStream_t)a.stream>>>(
+        a, w, for_backward ? 1 : 0);
+    AGS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ags_launch_project_bwd(const AgsRenderArgs& a, const AgsRenderGradArgs& g, const AgsWorkspace& w) {
+    if (a.N == 0) return 0;
+    const int threads = 128;
+    project_bwd_kernel<<<(a.N + threads - 1) / threads, threads, 0, (cudaStream_t)a.stream>>>(a, g, w);
+    AGS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

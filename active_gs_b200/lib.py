@@ -1,0 +1,119 @@
+"""ctypes binding of libags_b200.so (C ABI in include/ags_b200.h).
+
+The library is the product: there is NO CPU or PyTorch fallback.  If the shared object is missing
+or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libags_b200.so")
+
+AGS_NUM_STATS = 8
+STAT_INSTANCES, STAT_OVERFLOW, STAT_VISIBLE = 0, 1, 2
+PARAMS_ACTIVATED, PARAMS_RAW = 0, 1
+ADAM_GROUPS = 5
+
+_f = C.c_void_p  # device pointers travel as void*
+
+
+class RenderArgs(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("param_mode", C.c_int32), ("require_importance", C.c_int32), ("front_only", C.c_int32),
+        ("inst_cap", C.c_int32),
+        ("scale_modifier", C.c_float), ("weight_thres", C.c_float), ("scale_factor", C.c_float),
+        ("scale_max", C.c_float),
+        ("means3D", _f), ("scales", _f), ("rotations", _f), ("opacities", _f), ("colors", _f),
+        ("confidences", _f),
+        ("viewmatrix", _f), ("projmatrix", _f), ("tanfov", _f), ("bg", _f), ("render_mask", _f),
+        ("out_rgb", _f), ("out_normal", _f), ("out_depth", _f), ("out_opacity", _f),
+        ("out_confidence", _f), ("importance", _f), ("count", _f), ("radii", _f), ("stats", _f),
+        ("workspace", _f), ("workspace_bytes", C.c_size_t), ("stream", _f),
+    ]
+
+
+class RenderGradArgs(C.Structure):
+    _fields_ = [
+        ("d_rgb", _f), ("d_normal", _f), ("d_depth", _f), ("d_opacity", _f), ("d_confidence", _f),
+        ("d_means3D", _f), ("d_scales", _f), ("d_rotations", _f), ("d_opacities", _f),
+        ("d_colors", _f), ("d_means2D", _f), ("accumulate", C.c_int32),
+    ]
+
+
+class LossArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("B_total", C.c_int32),
+        ("rgb", _f), ("normal", _f), ("depth", _f), ("opacity", _f),
+        ("rgb_gt", _f), ("depth_gt", _f), ("fov", _f), ("vis_count", _f),
+        ("normal_unit", _f), ("d2n", _f), ("d_rgb", _f), ("d_normal", _f), ("d_depth", _f),
+        ("loss_terms", _f),
+        ("w_depth", C.c_float), ("w_cons", C.c_float), ("w_tv", C.c_float),
+        ("workspace", _f), ("workspace_bytes", C.c_size_t), ("stream", _f),
+    ]
+
+
+class AdamArgs(C.Structure):
+    _fields_ = [
+        ("num_groups", C.c_int32),
+        ("param", _f * ADAM_GROUPS), ("grad", _f * ADAM_GROUPS), ("exp_avg", _f * ADAM_GROUPS),
+        ("exp_avg_sq", _f * ADAM_GROUPS), ("numel", C.c_int64 * ADAM_GROUPS),
+        ("lr", C.c_float * ADAM_GROUPS),
+        ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("step", C.c_int32), ("step_dev", _f), ("stream", _f),
+    ]
+
+
+_lib = None
+
+EXPORTS = ["ags_scratch_bytes", "ags_render_forward", "ags_render_backward",
+           "ags_loss_scratch_bytes", "ags_loss_forward_backward", "ags_adam_step",
+           "ags_last_error", "ags_version"]
+
+
+def load():
+    """Load (once) and return the ctypes handle.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.ags_scratch_bytes.restype = C.c_size_t
+    lib.ags_scratch_bytes.argtypes = [C.c_int32] * 5
+    lib.ags_loss_scratch_bytes.restype = C.c_size_t
+    lib.ags_loss_scratch_bytes.argtypes = [C.c_int32] * 3
+    lib.ags_render_forward.argtypes = [C.POINTER(RenderArgs)]
+    lib.ags_render_backward.argtypes = [C.POINTER(RenderArgs), C.POINTER(RenderGradArgs)]
+    lib.ags_loss_forward_backward.argtypes = [C.POINTER(LossArgs)]
+    lib.ags_adam_step.argtypes = [C.POINTER(AdamArgs)]
+    lib.ags_last_error.restype = C.c_char_p
+    for name in ["ags_render_forward", "ags_render_backward", "ags_loss_forward_backward",
+                 "ags_adam_step", "ags_version"]:
+        getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().ags_last_error().decode()
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a contiguous float32/int32 CUDA tensor (or None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("libags_b200 operates on CUDA tensors only (no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError("tensor must be contiguous")
+    return t.data_ptr()
+
+
+def current_stream(device):
+    return torch.cuda.current_stream(device).cuda_stream

@@ -1,0 +1,70 @@
+"""Thin Python wrappers over the non-rasterizer entry points of libags_b200.so:
+the fused image loss (K8) and the fused Adam (K7)."""
+import ctypes as C
+import torch
+
+from . import lib as L
+
+
+class LossResult:
+    __slots__ = ("normal_unit", "d2n", "d_rgb", "d_normal", "d_depth", "terms", "workspace")
+
+    def total(self, w_depth=0.8, w_cons=0.1, w_tv=0.1):
+        t = self.terms
+        return t[0] + w_depth * t[1] + w_cons * t[2] + w_tv * t[3]
+
+    def frame_perf(self):
+        """what track_performance stores: per-frame rgb-L1 mean + depth-L1 mean"""
+        return self.terms[4::2] + self.terms[5::2]
+
+
+def loss_forward_backward(rgb, normal, depth, opacity, rgb_gt, depth_gt, fov, *, B_total=None,
+                          vis_count=None, w_depth=0.8, w_cons=0.1, w_tv=0.1, out=None):
+    """Post-processing + loss + gradients for a batch of rendered frames (all (B,C,H,W) CUDA fp32).
+    Returns a LossResult; `terms` = [L_rgb, L_depth, L_cons, L_tv, (rgb_f, depth_f) per frame]."""
+    lib = L.load()
+    B, _, H, W = rgb.shape
+    dev = rgb.device
+    r = out or LossResult()
+    if out is None:
+        o = dict(device=dev, dtype=torch.float32)
+        r.normal_unit = torch.empty(B, 3, H, W, **o)
+        r.d2n = torch.empty(B, 3, H, W, **o)
+        r.d_rgb = torch.empty(B, 3, H, W, **o)
+        r.d_normal = torch.empty(B, 3, H, W, **o)
+        r.d_depth = torch.empty(B, 1, H, W, **o)
+        r.terms = torch.empty(4 + 2 * B, **o)
+        r.workspace = torch.empty(lib.ags_loss_scratch_bytes(B, H, W), device=dev, dtype=torch.uint8)
+    a = L.LossArgs()
+    a.B, a.H, a.W = B, H, W
+    a.B_total = int(B_total or B)
+    a.rgb, a.normal, a.depth, a.opacity = L.ptr(rgb), L.ptr(normal), L.ptr(depth), L.ptr(opacity)
+    a.rgb_gt, a.depth_gt, a.fov = L.ptr(rgb_gt), L.ptr(depth_gt), L.ptr(fov)
+    a.vis_count = L.ptr(vis_count)
+    a.normal_unit, a.d2n = L.ptr(r.normal_unit), L.ptr(r.d2n)
+    a.d_rgb, a.d_normal, a.d_depth = L.ptr(r.d_rgb), L.ptr(r.d_normal), L.ptr(r.d_depth)
+    a.loss_terms = L.ptr(r.terms)
+    a.w_depth, a.w_cons, a.w_tv = w_depth, w_cons, w_tv
+    a.workspace, a.workspace_bytes = L.ptr(r.workspace), r.workspace.numel()
+    a.stream = L.current_stream(dev)
+    L.check(lib.ags_loss_forward_backward(C.byref(a)), "ags_loss_forward_backward")
+    return r
+
+
+def adam_step(params, grads, exp_avgs, exp_avg_sqs, lrs, step=None, step_dev=None,
+              betas=(0.9, 0.999), eps=1e-15):
+    """One fused Adam step over up to 5 groups (in place on params / exp_avg / exp_avg_sq)."""
+    lib = L.load()
+    a = L.AdamArgs()
+    n = len(params)
+    a.num_groups = n
+    for k in range(n):
+        a.param[k], a.grad[k] = L.ptr(params[k]), L.ptr(grads[k])
+        a.exp_avg[k], a.exp_avg_sq[k] = L.ptr(exp_avgs[k]), L.ptr(exp_avg_sqs[k])
+        a.numel[k] = params[k].numel()
+        a.lr[k] = lrs[k]
+    a.beta1, a.beta2, a.eps = betas[0], betas[1], eps
+    a.step = int(step or 0)
+    a.step_dev = L.ptr(step_dev)
+    a.stream = L.current_stream(params[0].device)
+    L.check(lib.ags_adam_step(C.byref(a)), "ags_adam_step")
