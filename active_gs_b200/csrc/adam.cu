@@ -20,10 +20,12 @@ struct AdamParams {
     float b1, b2, eps;
     int step;
     const int* step_dev;
+    const int* skip_flag;
 };
 
 __global__ void __launch_bounds__(256)
 adam_kernel(AdamParams P, long long total) {
+    if (P.skip_flag && *P.skip_flag != 0) return;
     const int t = P.step_dev ? (*P.step_dev + 1) : P.step;
     const double bc1 = 1.0 - pow((double)P.b1, (double)t);
     const double bc2 = 1.0 - pow((double)P.b2, (double)t);
@@ -47,7 +49,10 @@ adam_kernel(AdamParams P, long long total) {
     }
 }
 
-__global__ void tick_kernel(int* step_dev) { *step_dev += 1; }
+__global__ void tick_kernel(int* step_dev, const int* skip_flag) {
+    if (skip_flag && *skip_flag != 0) return;
+    *step_dev += 1;
+}
 
 }  // namespace
 
@@ -72,7 +77,7 @@ extern "C" int ags_adam_step(const AgsAdamArgs* a) {
     }
     P.groups = a->num_groups;
     P.b1 = a->beta1; P.b2 = a->beta2; P.eps = a->eps;
-    P.step = a->step; P.step_dev = a->step_dev;
+    P.step = a->step; P.step_dev = a->step_dev; P.skip_flag = a->skip_flag;
     AGS_CHECK_ARG(a->step_dev != nullptr || a->step >= 1, "step must be >= 1");
     if (total == 0) return 0;
     cudaStream_t st = (cudaStream_t)a->stream;
@@ -83,7 +88,7 @@ extern "C" int ags_adam_step(const AgsAdamArgs* a) {
     adam_kernel<<<(int)blocks, threads, 0, st>>>(P, total);
     AGS_CHECK_CUDA(cudaGetLastError());
     if (a->step_dev) {
-        tick_kernel<<<1, 1, 0, st>>>(a->step_dev);
+        tick_kernel<<<1, 1, 0, st>>>(a->step_dev, a->skip_flag);
         AGS_CHECK_CUDA(cudaGetLastError());
     }
     return 0;

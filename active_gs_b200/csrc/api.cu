@@ -60,6 +60,32 @@ static int render_forward_impl(const AgsRenderArgs* a, bool for_backward) {
 
 extern "C" int ags_render_forward(const AgsRenderArgs* a) { return render_forward_impl(a, true); }
 
+// Profiling hook: run ONE stage of the pipeline (bench.py times each stage with CUDA events).
+extern "C" int ags_render_stage(const AgsRenderArgs* a, const AgsRenderGradArgs* g, int stage) {
+    int rc = check_render_args(a);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)a->stream;
+    AgsWorkspace w = ags_carve(a->workspace, a->N, a->B, a->H, a->W, a->inst_cap);
+    switch (stage) {
+        case AGS_STAGE_CLEAR: {
+            const size_t zero_bytes = (char*)w.inst_key - (char*)w.tile_count;
+            AGS_CHECK_CUDA(cudaMemsetAsync(w.tile_count, 0, zero_bytes, st));
+            AGS_CHECK_CUDA(cudaMemsetAsync(a->stats, 0, AGS_NUM_STATS * sizeof(int32_t), st));
+            return 0;
+        }
+        case AGS_STAGE_PROJECT_FWD: return ags_launch_project_fwd(*a, w, true);
+        case AGS_STAGE_BINNING: return ags_launch_binning(*a, w);
+        case AGS_STAGE_COMPOSITE_FWD: return ags_launch_composite_fwd(*a, w);
+        case AGS_STAGE_COMPOSITE_BWD:
+            AGS_CHECK_ARG(g != nullptr, "grads is NULL");
+            return ags_launch_composite_bwd(*a, *g, w);
+        case AGS_STAGE_PROJECT_BWD:
+            AGS_CHECK_ARG(g != nullptr, "grads is NULL");
+            return ags_launch_project_bwd(*a, *g, w);
+        default: ags_set_error("unknown stage %d", stage); return -1;
+    }
+}
+
 extern "C" int ags_render_backward(const AgsRenderArgs* a, const AgsRenderGradArgs* g) {
     int rc = check_render_args(a);
     if (rc) return rc;

@@ -303,7 +303,46 @@ loss_pass_b(AgsLossArgs a, const float* g_nsum) {
     block_accumulate<1>(v1, d1);
 }
 
+// forward-only post-processing of rendered views (planners / eval / GUI): unit normal + d2n
+__global__ void __launch_bounds__(256)
+postprocess_kernel(int B, int H, int W, const float* normal, const float* depth_, const float* opacity,
+                   const float* fov, float* normal_unit, float* d2n_out) {
+    const size_t P = (size_t)H * W;
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    if (p >= P) return;
+    const int y = (int)(p / W), x = (int)(p % W);
+    const float* opac = opacity + (size_t)f * P;
+    const float* depth = depth_ + (size_t)f * P;
+    const float m2 = (opac[p] > 1e-2f) ? 1.f : 0.f;
+    const float* np_ = normal + (size_t)f * 3 * P + p;
+    const F3 n = f3(np_[0], np_[P], np_[2 * P]);
+    const float nn = fmaxf(sqrtf(dot(n, n)), 1e-12f);
+    const F3 nu = n * (m2 / nn);
+    float* no = normal_unit + (size_t)f * 3 * P + p;
+    no[0] = nu.x; no[P] = nu.y; no[2 * P] = nu.z;
+    const FrameGeom g = frame_geom(fov, f, H, W);
+    const D2N v = d2n_vectors(depth, opac, g, H, W, y, x);
+    const F3 ns = cross(v.pu, v.pl) + cross(v.pr, v.pu) + cross(v.pb, v.pr) + cross(v.pl, v.pb);
+    const float nsn = fmaxf(sqrtf(dot(ns, ns)), 1e-12f);
+    const F3 d2n = ns * (m2 / nsn);
+    float* dn = d2n_out + (size_t)f * 3 * P + p;
+    dn[0] = d2n.x; dn[P] = d2n.y; dn[2 * P] = d2n.z;
+}
+
 }  // namespace
+
+extern "C" int ags_postprocess(int32_t B, int32_t H, int32_t W, const float* normal, const float* depth,
+                               const float* opacity, const float* fov, float* normal_unit, float* d2n,
+                               void* stream) {
+    AGS_CHECK_ARG(B > 0 && H > 0 && W > 0, "bad sizes");
+    AGS_CHECK_ARG(normal && depth && opacity && fov && normal_unit && d2n, "NULL pointer");
+    dim3 grid((unsigned)(((size_t)H * W + 255) / 256), B);
+    postprocess_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(B, H, W, normal, depth, opacity, fov,
+                                                              normal_unit, d2n);
+    AGS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
 
 extern "C" size_t ags_loss_scratch_bytes(int32_t B, int32_t H, int32_t W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;

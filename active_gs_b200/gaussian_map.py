@@ -1,0 +1,433 @@
+"""Host-side mirror of the reference's mapping/gaussian_map.py (class GaussianMap) on top of
+libags_b200.so: same public surface -- update/train/save/load/get_attr/get_params, the get_*
+properties, background_color/scene_near/scene_far/view_*/training_data/is_init -- so
+mapping/mapper.py and the planners can use it unchanged (reference lines cited per method).
+
+The per-iteration loop of train() (mapping/gaussian_map.py:76-127) is ONE fused device pipeline:
+    render_forward (RAW params: activations fused, B views per launch)
+      -> loss_forward_backward (post-processing + 4 loss terms + gradients, 2 kernels)
+      -> render_backward (composite_bwd + project_bwd incl. activation backward)
+      -> adam_step (5 groups, 1 kernel)
+with every buffer allocated once per train() call and no autograd graph.  The only host<->device
+traffic per iteration is the (B,) keyframe ids up and (B + stats) floats down for the
+loss-weighted sampler, exactly the dependency the reference has (mapping/utils.py:206-218).
+"""
+import ctypes as C
+import math
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import lib as L
+from . import ops
+from . import operations as O
+from .rasterizer import RenderBatch
+
+
+class WeightedSampler:
+    """mapping/utils.py:190-228 (ids only; the frame tensors are gathered on the device)."""
+
+    def __init__(self, cfg, n_frames):
+        active = min(cfg.active_size, n_frames)
+        ids = np.arange(n_frames)
+        self.active_ids = ids[-active:]
+        self.random_ids_all = ids[:-active]
+        self.selected_num = min(len(self.random_ids_all), cfg.batch_size - active)
+        self.v = len(self.active_ids) + self.selected_num
+
+    def next_ids(self, weight_host):
+        sel = self.active_ids.copy()
+        if self.selected_num > 0:
+            w = torch.as_tensor(weight_host)[self.random_ids_all]
+            w = w / torch.sum(w)
+            drawn = np.random.choice(self.random_ids_all, size=self.selected_num, p=w.numpy(),
+                                     replace=False)
+            sel = np.append(sel, self.random_ids_all[drawn])
+        return sel
+
+
+class _TrainEngine:
+    """Preallocated buffers + the fused iteration for one train() call (fixed N, B, H, W)."""
+
+    def __init__(self, gm, B, H, W, dist_ctx=None):
+        dev = gm.device
+        self.gm, self.B, self.H, self.W, self.dev = gm, B, H, W, dev
+        self.dist = dist_ctx
+        self.B_total = B * (dist_ctx.world if dist_ctx else 1)
+        N = gm._means.shape[0]
+        self.N = N
+        o = dict(device=dev, dtype=torch.float32)
+        self.params = [gm._means, gm._scales, gm._rotations, gm._opacities, gm._harmonics]
+        for p in self.params:
+            assert p.is_contiguous() and p.dtype == torch.float32
+        # gradients are views of ONE flat buffer (14 floats per Gaussian): a single all-reduce
+        # in the frame-sharded multi-GPU path, a single memset if ever needed
+        self.grad_flat = torch.empty(sum(p.numel() for p in self.params), **o)
+        self.grads, off = [], 0
+        for p in self.params:
+            self.grads.append(self.grad_flat[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+        self.m = [torch.zeros_like(p) for p in self.params]
+        self.v = [torch.zeros_like(p) for p in self.params]
+        self.lrs = [gm.cfg.optimizer.mean_lr, gm.cfg.optimizer.scale_lr, gm.cfg.optimizer.rotation_lr,
+                    gm.cfg.optimizer.opacity_lr, gm.cfg.optimizer.harmonic_lr]
+        self.step = 0
+        self.conf = gm.get_confidences.contiguous()
+        self.rgb_gt = torch.empty(B, 3, H, W, **o)
+        self.depth_gt = torch.empty(B, 1, H, W, **o)
+        self.view = torch.empty(B, 16, **o)
+        self.proj = torch.empty(B, 16, **o)
+        self.tanfov = torch.empty(B, 2, **o)
+        self.fov = torch.empty(B, 2, **o)
+        self.bg = gm.background_color.to(dev).float().contiguous()
+        cap = gm._inst_cap_hint(N, B)
+        self.rb = RenderBatch(gm._means, gm._scales, gm._rotations, gm._opacities,
+                              gm._harmonics.reshape(N, 3), self.conf, self.view, self.proj, self.tanfov,
+                              self.bg, H, W, param_mode=L.PARAMS_RAW, scale_factor=gm.scale_factor,
+                              scale_max=0.05, inst_cap=cap)
+        # RenderBatch copies nothing for contiguous fp32 inputs, but make the aliasing explicit
+        self.rb.inputs = [gm._means, gm._scales, gm._rotations, gm._opacities,
+                          gm._harmonics.reshape(N, 3), self.conf]
+        self.rb.view = [self.view, self.proj, self.tanfov, self.bg]
+        self.loss = None
+        self.loss_out = None
+        self.vis_count = torch.empty(H, W, device=dev, dtype=torch.int32) if dist_ctx else None
+        self.host = torch.empty(2 * B + 4, dtype=torch.float32).pin_memory()
+        self.host_stats = torch.empty(L.AGS_NUM_STATS, dtype=torch.int32).pin_memory()
+        self.event = torch.cuda.Event()
+
+    def set_batch(self, rgbs, depths, view, proj, tanfov, fov):
+        """Stage this iteration's keyframes (lists of (3,H,W)/(1,H,W) tensors) and camera blocks in
+        the fixed device buffers.  Pinned host sources make this the per-step H2D of the end-to-end
+        path; device sources are gathered with one stack kernel per tensor."""
+        if rgbs[0].is_cuda:
+            torch.stack(rgbs, out=self.rgb_gt)
+            torch.stack(depths, out=self.depth_gt)
+        else:
+            for k in range(self.B):
+                self.rgb_gt[k].copy_(rgbs[k], non_blocking=True)
+                self.depth_gt[k].copy_(depths[k], non_blocking=True)
+        self.view.copy_(view.reshape(self.B, 16), non_blocking=True)
+        self.proj.copy_(proj.reshape(self.B, 16), non_blocking=True)
+        self.tanfov.copy_(tanfov, non_blocking=True)
+        self.fov.copy_(fov, non_blocking=True)
+
+    def grow(self, need):
+        """re-plan the instance capacity after an overflow (nothing was rendered or updated)"""
+        self.rb.inst_cap = int(need * 1.3) + 65536
+        self.rb._alloc(L.load())
+
+    def iterate(self):
+        """Enqueue one optimisation step on the staged batch.  Order on the stream:
+        forward -> loss(+grads) -> [tiny D2H of loss terms / perf / stats + event] -> backward ->
+        Adam.  The host later waits on the event only, so the backward and the Adam step overlap
+        with the host preparing the next batch.  Adam is gated on the device overflow flag."""
+        lib = L.load()
+        rb = self.rb
+        rb.forward(check_overflow=False)
+        vis = None
+        if self.dist is not None:
+            torch.sum(rb.opacity[:, 0] > 1e-3, dim=0, dtype=torch.int32, out=self.vis_count)
+            self.dist.all_reduce_sum_(self.vis_count)
+            vis = self.vis_count
+        self.loss_out = ops.loss_forward_backward(
+            rb.rgb, rb.normal, rb.depth, rb.opacity, self.rgb_gt, self.depth_gt, self.fov,
+            B_total=self.B_total, vis_count=vis, out=self.loss_out)
+        lo = self.loss_out
+        B = self.B
+        self.host.copy_(lo.terms, non_blocking=True)
+        self.host_stats.copy_(rb.stats, non_blocking=True)
+        self.event.record(torch.cuda.current_stream(self.dev))
+        g = L.RenderGradArgs()
+        g.d_rgb, g.d_normal, g.d_depth = L.ptr(lo.d_rgb), L.ptr(lo.d_normal), L.ptr(lo.d_depth)
+        g.d_opacity = g.d_confidence = None
+        (g.d_means3D, g.d_scales, g.d_rotations, g.d_opacities, g.d_colors) = [
+            L.ptr(t) for t in self.grads]
+        g.d_means2D = None
+        g.accumulate = 0
+        L.check(lib.ags_render_backward(C.byref(rb._args()), C.byref(g)), "ags_render_backward")
+        if self.dist is not None:
+            self.dist.all_reduce_grads_(self.grads)
+        self.step += 1
+        ops.adam_step(self.params, self.grads, self.m, self.v, self.lrs, step=self.step,
+                      skip_flag_ptr=rb.stats.data_ptr() + 4 * L.STAT_OVERFLOW)
+
+    def fetch(self):
+        """Wait for the loss terms / per-frame performance / instance statistics of the step that
+        was just enqueued (the sampler needs them, mapping/utils.py:206-218)."""
+        B = self.B
+        self.event.synchronize()
+        h = self.host.clone()
+        terms = h[:4]
+        perf = h[4:4 + 2 * B:2] + h[5:4 + 2 * B:2]
+        return terms, perf, self.host_stats.to(torch.int64)
+
+
+class GaussianMap:
+    """mapping/gaussian_map.py:17-590."""
+
+    def __init__(self, cfg, device):
+        self.device = torch.device(device)
+        dev = self.device
+        self._means = torch.empty(0, 3, device=dev)
+        self._scales = torch.empty(0, 3, device=dev)
+        self._rotations = torch.empty(0, 4, device=dev)
+        self._opacities = torch.empty(0, device=dev)
+        self._harmonics = torch.empty(0, 1, 3, device=dev)
+        self.view_scores = torch.empty(0, device=dev)
+        self.view_supports = torch.empty(0, device=dev)
+        self.view_means = torch.empty((0, 3), device=dev)
+        self.training_performance = torch.tensor([], device=dev)
+        self.training_data = []
+        self.is_init = False
+        self.use_view_distribution = True
+        self.frames_on_host = False          # bench end-to-end mode: keyframes stay in pinned host memory
+        self.dist = None                     # active_gs_b200.distributed.FrameShard or None
+        self.last_train_log = []
+        self._cap_per_gaussian = 4.0
+        if cfg is not None:
+            self.cfg = cfg
+            self.use_view_distribution = cfg.use_view_distribution
+            self.scene_near, self.scene_far = cfg.bound
+            self.sparse_ratio = cfg.sparse_ratio
+            self.scale_factor = cfg.scale_factor
+            self.error_thres = cfg.error_thres
+            self.prune_interval = cfg.prune_interval
+            self.optimization_steps = cfg.optimization_steps
+            self.background_color = torch.tensor(cfg.background, dtype=torch.float32).to(dev)
+
+    # ------------------------------------------------------------------ public loop (:62-130)
+    def update(self, dataframe):
+        self.add_gaussians(dataframe)
+        self.train()
+
+    def _inst_cap_hint(self, N, B):
+        return int(self._cap_per_gaussian * N * B) + 65536
+
+    def _camera_table(self):
+        """camera blocks of all keyframes, computed on the host once per train() call"""
+        ext = torch.stack([f["extrinsic"].detach().float().cpu() for f in self.training_data])
+        K = torch.stack([f["intrinsic"].detach().float().cpu() for f in self.training_data])
+        fovs, view, proj, _, tanfov = O.camera_blocks(ext, K, (self.scene_near, self.scene_far))
+        return fovs, view.reshape(-1, 16), proj.reshape(-1, 16), tanfov
+
+    def begin_training(self):
+        """Everything train() sets up once per call (mapping/gaussian_map.py:71-74): fresh Adam
+        state, the sampler, the camera table of all keyframes, and the preallocated engine."""
+        from types import SimpleNamespace
+        T = len(self.training_data)
+        self._make_contiguous()
+        sampler = WeightedSampler(self.cfg.sampler, T)
+        B = sampler.v if self.dist is None else self.dist.local_batch(sampler.v)
+        _, H, W = self.training_data[0]["rgb"].shape
+        fovs, views, projs, tanfovs = self._camera_table()
+        place = (lambda t: t.pin_memory()) if self.frames_on_host else (lambda t: t.to(self.device))
+        return SimpleNamespace(
+            sampler=sampler, B=B, H=H, W=W, fovs=place(fovs), views=place(views), projs=place(projs),
+            tanfovs=place(tanfovs), eng=_TrainEngine(self, B, H, W, self.dist),
+            perf_host=self.training_performance.detach().float().cpu().clone(), log=[])
+
+    def train_step(self, ctx, ids=None):
+        """One iteration of mapping/gaussian_map.py:76-127: sample keyframes, stage them, enqueue
+        forward/loss/backward/Adam, wait for the loss terms (sampler dependency)."""
+        eng = ctx.eng
+        ids = np.asarray(ids) if ids is not None else ctx.sampler.next_ids(ctx.perf_host)
+        my = ids if self.dist is None else self.dist.my_frames(ids)
+        idx = torch.as_tensor(my, dtype=torch.long)
+        eng.set_batch([self.training_data[i]["rgb"] for i in my],
+                      [self.training_data[i]["depth"] for i in my],
+                      ctx.views[idx], ctx.projs[idx], ctx.tanfovs[idx], ctx.fovs[idx])
+        while True:
+            eng.iterate()
+            terms, perf, stats = eng.fetch()
+            if stats[L.STAT_OVERFLOW] == 0:
+                break
+            # capacity exceeded: nothing was rendered and the device-side flag turned the Adam
+            # step into a no-op, so grow the workspace and redo the same iteration
+            eng.step -= 1
+            eng.grow(int(stats[L.STAT_INSTANCES]))
+        need = float(stats[L.STAT_INSTANCES]) / max(1, eng.N * ctx.B)
+        self._cap_per_gaussian = max(self._cap_per_gaussian, 1.5 * need)
+        if self.dist is not None:
+            perf = self.dist.gather_perf(perf, ids)
+        ctx.perf_host[torch.as_tensor(ids, dtype=torch.long)] = perf
+        loss = float(terms[0] + 0.8 * terms[1] + 0.1 * terms[2] + 0.1 * terms[3])
+        ctx.log.append((loss, perf.clone(), int(stats[L.STAT_INSTANCES]), int(stats[L.STAT_VISIBLE])))
+        return loss
+
+    def end_training(self, ctx):
+        self.training_performance = ctx.perf_host.to(self.device)
+        self.last_train_log = ctx.log
+
+    def train(self, steps=None, frame_id_batches=None):
+        """mapping/gaussian_map.py:66-130.  `frame_id_batches` (optional) overrides the sampler with
+        explicit keyframe ids per iteration (parity tests)."""
+        iterations = self.optimization_steps if steps is None else steps
+        ctx = self.begin_training()
+        for it in range(iterations):
+            self.train_step(ctx, None if frame_id_batches is None else frame_id_batches[it])
+        self.end_training(ctx)
+        self.post_processing()
+        self.is_init = True
+
+    def _make_contiguous(self):
+        for n in ["_means", "_scales", "_rotations", "_opacities", "_harmonics"]:
+            setattr(self, n, getattr(self, n).detach().float().contiguous())
+
+    # ------------------------------------------------------------------ :141-246
+    def post_processing(self):
+        T = len(self.training_data)
+        require_prune = T % self.prune_interval == 0
+        ids = list(range(T)) if require_prune else [T - 1]
+        ext = torch.stack([self.training_data[i]["extrinsic"] for i in ids]).to(self.device)
+        intr = torch.stack([self.training_data[i]["intrinsic"] for i in ids]).to(self.device)
+        dgt = torch.stack([self.training_data[i]["depth"] for i in ids]).to(self.device)
+        depth_ranges = self.training_data[-1]["depth_range"]
+        _, _, H, W = dgt.shape
+        counts = O.GaussianRenderer(
+            ext, intr, self.get_attr(), self.background_color, (self.scene_near, self.scene_far),
+            (H, W), self.device, render_masks=(dgt > 0.0).float(),
+        ).render_view_all(require_importance=True, front_only=True)[7]
+        update_mask = counts[-1] >= 1.0
+        self.view_supports = self.view_supports + update_mask.float()
+        if self.use_view_distribution:
+            means = self.get_means.detach()
+            normals = self.get_normals.detach()
+            vdir = ext[-1:, :3, 3] - means
+            dist = torch.linalg.norm(vdir, dim=1)
+            vdir = vdir / dist.unsqueeze(-1)
+            delta = vdir[update_mask] - self.view_means[update_mask]
+            self.view_means[update_mask] += delta / self.view_supports[update_mask].unsqueeze(-1)
+            cos = torch.clamp(torch.sum(normals * vdir, 1), min=0, max=1)
+            dfac = torch.clamp(dist / float(depth_ranges[1]), min=0, max=1)
+            self.view_scores[update_mask] += (1 - dfac)[update_mask] * cos[update_mask]
+        if require_prune:
+            vis_mask = torch.sum(counts, dim=0) >= 1.0
+            self.prune(~vis_mask)
+
+    def prune(self, prune_mask):
+        prune_mask += self.get_opacities < 0.1              # quirk Q5: in-place OR on the caller's mask
+        keep = ~prune_mask.bool()
+        for n in ["_means", "_scales", "_rotations", "_opacities", "_harmonics", "view_scores",
+                  "view_supports", "view_means"]:
+            setattr(self, n, getattr(self, n)[keep])
+        print(f"delete {int(torch.sum(prune_mask))} gaussians")
+
+    # ------------------------------------------------------------------ :294-489
+    def add_gaussians(self, dataframe):
+        dev = self.device
+        rgb, depth = dataframe["rgb"].to(dev), dataframe["depth"].to(dev)
+        intrinsic, extrinsic = dataframe["intrinsic"].to(dev), dataframe["extrinsic"].to(dev)
+        _, H, W = rgb.shape
+        smooth = torch.tensor(O.get_smooth_depth(depth.squeeze(0).cpu().numpy()), device=dev).unsqueeze(0)
+        valid = (depth > 0.0).view(-1)
+        origins, directions = O.get_world_rays(H, W, extrinsic, intrinsic, dev)
+        pcd = origins + directions * depth.view(-1, 1)
+        P = H * W
+        normals_w = torch.zeros(P, 3, device=dev)
+        normals_w[:, 2] = 1.0
+        n_cam = O.depth2normal(smooth, valid.view(1, H, W), fov=(np.pi / 3, np.pi / 3)).permute(1, 2, 0).reshape(-1, 3)
+        valid = valid & (torch.sum(n_cam ** 2, dim=-1) > 0.0)
+        n_world = n_cam @ extrinsic[:3, :3].t()
+        normals_w[valid] = n_world[valid]
+        cos = torch.sum(F.normalize(directions, dim=1) * normals_w, dim=-1)
+        valid = valid & (cos < -0.01)
+        pred = None
+        if self.is_init:
+            r = O.GaussianRenderer(extrinsic[None], intrinsic[None], self.get_attr(), self.background_color,
+                                   (self.scene_near, self.scene_far), (H, W), dev).render_view_all()
+            pred = dict(rgb=r[0], depth=r[1].squeeze(1), opacity=r[3].squeeze(1))
+        rot_new, _ = O.normal2rotation(normals_w)
+        valid = valid & ~torch.any(rot_new.isnan(), dim=1)
+        select = self.cal_mask(rgb[None], depth[None], pred).to(dev) & valid
+        sel_idx = torch.nonzero(select).flatten()
+        keep = O.voxel_downsample(pcd[select])
+        sel_idx = sel_idx[keep]
+        n_new = sel_idx.numel()
+        scales_new = torch.zeros(n_new, 3, device=dev)
+        scales_new[:, -1] -= 1e10
+        cat = lambda a, b: torch.cat((a.detach(), b.float()), dim=0)
+        self._means = cat(self._means, pcd[sel_idx])
+        self._scales = cat(self._scales, scales_new)
+        self._harmonics = cat(self._harmonics, rgb.permute(1, 2, 0).reshape(-1, 3)[sel_idx][:, None, :])
+        self._opacities = cat(self._opacities, torch.zeros(n_new, device=dev))
+        self._rotations = cat(self._rotations, rot_new[sel_idx])
+        self.view_scores = cat(self.view_scores, torch.zeros(n_new, device=dev))
+        self.view_supports = cat(self.view_supports, torch.zeros(n_new, device=dev))
+        self.view_means = cat(self.view_means, torch.zeros(n_new, 3, device=dev))
+        self.training_data.append(dataframe)
+        self.training_performance = torch.cat(
+            (self.training_performance, torch.tensor([10.0], device=dev)), 0)
+
+    def cal_mask(self, rgb_gt, depth_gt, pred):
+        """:470-489 -- spawn where rgb MSE > error_thres, opacity < 0.5 or the render is > 5 % behind."""
+        v, _, h, w = rgb_gt.shape
+        if pred is None:
+            return torch.ones(v * h * w, dtype=torch.bool, device=rgb_gt.device)
+        err = torch.mean((rgb_gt - pred["rgb"]) ** 2, dim=1)
+        mask = err > self.error_thres
+        mask = mask | (pred["opacity"] < 0.5)
+        mask = mask | ((depth_gt.squeeze(0) - pred["depth"]) < -0.05 * depth_gt.squeeze(0))
+        return mask.reshape(-1)
+
+    # ------------------------------------------------------------------ :491-527 (.th dict format kept)
+    def save(self, save_path, index="final"):
+        torch.save({
+            "means": self._means.detach(), "scales": self._scales.detach(),
+            "harmonics": self._harmonics.detach(), "opacities": self._opacities.detach(),
+            "rotations": self._rotations.detach(), "view_scores": self.view_scores.detach(),
+            "view_supports": self.view_supports.detach(), "view_means": self.view_means.detach(),
+            "near": self.scene_near, "far": self.scene_far,
+            "use_view_direction": self.use_view_distribution,
+            "background_color": self.background_color, "scale_factor": self.scale_factor,
+        }, f"{save_path}/map_{index}.th")
+
+    def load(self, model_path):
+        s = torch.load(model_path, map_location=self.device, weights_only=False)
+        self._means, self._scales, self._harmonics = s["means"], s["scales"], s["harmonics"]
+        self._opacities, self._rotations = s["opacities"], s["rotations"]
+        self.view_scores, self.view_supports, self.view_means = s["view_scores"], s["view_supports"], s["view_means"]
+        self.scene_near, self.scene_far = s["near"], s["far"]
+        self.background_color = torch.as_tensor(s["background_color"], dtype=torch.float32).to(self.device)
+        self.scale_factor = s["scale_factor"]
+        self.is_init = True
+
+    # ------------------------------------------------------------------ :529-590
+    @property
+    def get_means(self):
+        return self._means
+
+    @property
+    def get_rotations(self):
+        return F.normalize(self._rotations)
+
+    @property
+    def get_scales(self):
+        return torch.clamp(self.scale_factor * torch.exp(self._scales), min=0, max=0.05)
+
+    @property
+    def get_opacities(self):
+        return torch.sigmoid(self._opacities)
+
+    @property
+    def get_harmonics(self):
+        return self._harmonics
+
+    @property
+    def get_confidences(self):
+        if self.use_view_distribution:
+            vv = self.view_means.norm(dim=-1)
+            vv = torch.where(torch.isnan(vv), torch.ones_like(vv), vv)
+            return torch.clamp(torch.exp(1 - vv) * self.view_scores, min=0, max=1)
+        return torch.clamp(1 - 1 / torch.exp(self.view_supports), min=0, max=1)
+
+    @property
+    def get_normals(self):
+        return F.normalize(O.quaternion_to_matrix(self.get_rotations)[:, :3, 2])
+
+    def get_attr(self):
+        return (self.get_means, self.get_harmonics, self.get_opacities, self.get_confidences,
+                self.get_scales, self.get_rotations)
+
+    def get_params(self):
+        return (self._means, self._harmonics, self._opacities, self._scales, self._rotations)

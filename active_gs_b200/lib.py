@@ -61,14 +61,14 @@ class AdamArgs(C.Structure):
         ("exp_avg_sq", _f * ADAM_GROUPS), ("numel", C.c_int64 * ADAM_GROUPS),
         ("lr", C.c_float * ADAM_GROUPS),
         ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-        ("step", C.c_int32), ("step_dev", _f), ("stream", _f),
+        ("step", C.c_int32), ("step_dev", _f), ("skip_flag", _f), ("stream", _f),
     ]
 
 
 _lib = None
 
-EXPORTS = ["ags_scratch_bytes", "ags_render_forward", "ags_render_backward",
-           "ags_loss_scratch_bytes", "ags_loss_forward_backward", "ags_adam_step",
+EXPORTS = ["ags_scratch_bytes", "ags_render_forward", "ags_render_backward", "ags_render_stage",
+           "ags_loss_scratch_bytes", "ags_loss_forward_backward", "ags_postprocess", "ags_adam_step",
            "ags_last_error", "ags_version"]
 
 
@@ -88,8 +88,12 @@ def load():
     lib.ags_loss_scratch_bytes.argtypes = [C.c_int32] * 3
     lib.ags_render_forward.argtypes = [C.POINTER(RenderArgs)]
     lib.ags_render_backward.argtypes = [C.POINTER(RenderArgs), C.POINTER(RenderGradArgs)]
+    lib.ags_render_stage.argtypes = [C.POINTER(RenderArgs), C.POINTER(RenderGradArgs), C.c_int]
+    lib.ags_render_stage.restype = C.c_int
     lib.ags_loss_forward_backward.argtypes = [C.POINTER(LossArgs)]
     lib.ags_adam_step.argtypes = [C.POINTER(AdamArgs)]
+    lib.ags_postprocess.argtypes = [C.c_int32] * 3 + [C.c_void_p] * 7
+    lib.ags_postprocess.restype = C.c_int
     lib.ags_last_error.restype = C.c_char_p
     for name in ["ags_render_forward", "ags_render_backward", "ags_loss_forward_backward",
                  "ags_adam_step", "ags_version"]:

@@ -52,7 +52,7 @@ def loss_forward_backward(rgb, normal, depth, opacity, rgb_gt, depth_gt, fov, *,
 
 
 def adam_step(params, grads, exp_avgs, exp_avg_sqs, lrs, step=None, step_dev=None,
-              betas=(0.9, 0.999), eps=1e-15):
+              betas=(0.9, 0.999), eps=1e-15, skip_flag_ptr=None):
     """One fused Adam step over up to 5 groups (in place on params / exp_avg / exp_avg_sq)."""
     lib = L.load()
     a = L.AdamArgs()
@@ -66,5 +66,18 @@ def adam_step(params, grads, exp_avgs, exp_avg_sqs, lrs, step=None, step_dev=Non
     a.beta1, a.beta2, a.eps = betas[0], betas[1], eps
     a.step = int(step or 0)
     a.step_dev = L.ptr(step_dev)
+    a.skip_flag = skip_flag_ptr
     a.stream = L.current_stream(params[0].device)
     L.check(lib.ags_adam_step(C.byref(a)), "ags_adam_step")
+
+
+def postprocess(normal, depth, opacity, fov):
+    """normalize(normal)*mask and depth2normal for B rendered views (forward only)."""
+    lib = L.load()
+    B, _, H, W = normal.shape
+    nu = torch.empty_like(normal)
+    d2n = torch.empty_like(normal)
+    L.check(lib.ags_postprocess(B, H, W, L.ptr(normal), L.ptr(depth), L.ptr(opacity), L.ptr(fov),
+                                L.ptr(nu), L.ptr(d2n), L.current_stream(normal.device)),
+            "ags_postprocess")
+    return nu, d2n

@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200: training throughput of the ActiveGS
+rasterize-and-optimise loop (BASELINE.json: train iters/s & Mpix/s at 640x480; fwd HBM GB/s vs peak).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+Workload (config[1] of BASELINE.json): synthetic Replica-office0-shaped room,
+200 000 Gaussian surfels, 640x480, keyframe batch B = 8 per GPU, one *step* = one iteration of
+GaussianMap.train() (mapping/gaussian_map.py:76-127): sample 8 keyframes, render them, 4-term loss,
+backward, Adam.  metric = train Mpix/s = B_global*H*W*iters/s/1e6 (weak scaling: every GPU renders
+its own 8 keyframes of an 8N-keyframe batch; gradients are all-reduced).  One JSON line on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from active_gs_b200 import synthetic as syn  # noqa: E402
+from active_gs_b200.config import default_gaussian_map_config  # noqa: E402
+
+CONFIG_IDX = 2
+B_PER_GPU = 8
+METRIC, UNIT = "train_mpix_per_s", "Mpix/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, reasons, mx = [], set(), None
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(dev, rank, world, seed_base=1000 + CONFIG_IDX):
+    """Scene + 8*world keyframes (rendered from the generating scene with our own renderer, then
+    depth noise) + the perturbed start state.  Deterministic; identical on every rank."""
+    from active_gs_b200 import operations as O
+    from active_gs_b200.gaussian_map import GaussianMap
+    box, H, W, N = syn.ROOMS[CONFIG_IDX]
+    T = B_PER_GPU * world
+    state = syn.make_room_scene(N, box=box, seed=seed_base)
+    ext, K = syn.make_cameras(T, box=box, H=H, W=W, seed=seed_base + 1000)
+    cfg = default_gaussian_map_config()
+    cfg.sampler.batch_size = T
+    gm = GaussianMap(cfg, dev)
+    load_state(gm, state, dev)
+    frames = []
+    with torch.no_grad():
+        for i in range(T):
+            out = O.GaussianRenderer(ext[i:i + 1].to(dev), K[i:i + 1].to(dev), gm.get_attr(), gm.background_color,
+                                     (gm.scene_near, gm.scene_far), (H, W), dev).render_view_all()
+            depth = syn.noisy_depth(out[1][0].cpu(), seed=4000 + i)
+            frames.append(dict(rgb=out[0][0].clamp(0, 1).cpu(), depth=depth, extrinsic=ext[i], intrinsic=K[i],
+                               depth_range=torch.tensor([0.0, 5.0])))
+    start = syn.perturb_state(state, seed=seed_base + 2000)
+    return state, start, frames, cfg, (H, W, N, T)
+
+
+def load_state(gm, state, dev):
+    gm._means, gm._scales = state["means"].clone().to(dev), state["scales"].clone().to(dev)
+    gm._rotations, gm._opacities = state["rotations"].clone().to(dev), state["opacities"].clone().to(dev)
+    gm._harmonics = state["harmonics"].clone().to(dev)
+    gm.view_scores, gm.view_supports = state["view_scores"].clone().to(dev), state["view_supports"].clone().to(dev)
+    gm.view_means = state["view_means"].clone().to(dev)
+
+
+def fresh_map(cfg, start, frames, dev, on_host, shard):
+    from active_gs_b200.gaussian_map import GaussianMap
+    gm = GaussianMap(cfg, dev)
+    load_state(gm, start, dev)
+    place = (lambda t: t.pin_memory()) if on_host else (lambda t: t.to(dev))
+    gm.training_data = [{k: (place(v) if k in ("rgb", "depth") else v) for k, v in f.items()} for f in frames]
+    gm.training_performance = torch.full((len(frames),), 10.0, device=dev)
+    gm.frames_on_host = on_host
+    gm.dist = shard
+    return gm
+
+
+def stage_profile(eng, reps=5):
+    """Average device time of every kernel of one step, CUDA events on the launching stream."""
+    import ctypes as C
+    from active_gs_b200 import lib as L, ops
+    lib = L.load()
+    rb = eng.rb
+    names = ["clear", "project_fwd", "binning", "composite_fwd", "loss", "composite_bwd", "project_bwd", "adam"]
+    acc = {n: 0.0 for n in names}
+    st = torch.cuda.current_stream()
+    for _ in range(reps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+        a = rb._args()
+        ev[0].record(st)
+        for k, stage in enumerate([0, 1, 2, 3]):
+            L.check(lib.ags_render_stage(C.byref(a), None, stage), "stage")
+            ev[k + 1].record(st)
+        eng.loss_out = ops.loss_forward_backward(rb.rgb, rb.normal, rb.depth, rb.opacity, eng.rgb_gt, eng.depth_gt,
+                                                 eng.fov, B_total=eng.B_total, out=eng.loss_out)
+        ev[5].record(st)
+        lo = eng.loss_out
+        g = L.RenderGradArgs()
+        g.d_rgb, g.d_normal, g.d_depth = L.ptr(lo.d_rgb), L.ptr(lo.d_normal), L.ptr(lo.d_depth)
+        (g.d_means3D, g.d_scales, g.d_rotations, g.d_opacities, g.d_colors) = [L.ptr(t) for t in eng.grads]
+        L.check(lib.ags_render_stage(C.byref(a), C.byref(g), 4), "stage"); ev[6].record(st)
+        L.check(lib.ags_render_stage(C.byref(a), C.byref(g), 5), "stage"); ev[7].record(st)
+        eng.step += 1
+        ops.adam_step(eng.params, eng.grads, eng.m, eng.v, eng.lrs, step=eng.step); ev[8].record(st)
+        torch.cuda.synchronize()
+        for k, n in enumerate(names):
+            acc[n] += ev[k].elapsed_time(ev[k + 1])
+    return {n: v / reps for n, v in acc.items()}
+
+
+def algorithmic_bytes(N, B, P, I, V, tiles):
+    """SURVEY.md 8(d) / DESIGN.md: bytes each kernel must move per launch (B views per launch)."""
+    sort_bytes = 8 * I * 2 + 4 * I + 12 * B * tiles   # keys written+read once, ids written; tile tables
+    return {
+        "project_fwd": 60 * N + 72 * V, "binning": sort_bytes, "composite_fwd": 68 * I + 44 * B * P,
+        "loss": (60 + 28) * B * P, "composite_bwd": 68 * I + 76 * B * P + 60 * V,
+        "project_bwd": 116 * V + 56 * N, "adam": 392 * N,
+    }
+
+
+def run_ours(args, rank, world, local_rank):
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    shard = None
+    if world > 1:
+        import torch.distributed as dist
+        from active_gs_b200.distributed import FrameShard
+        dist.init_process_group("nccl", device_id=dev)
+        shard = FrameShard()
+    state, start, frames, cfg, (H, W, N, T) = build_workload(dev, rank, world)
+    B = B_PER_GPU
+    P = H * W
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm: K steps of the train-loop body
+    np.random.seed(1234)
+    gm = fresh_map(cfg, start, frames, dev, on_host=False, shard=shard)
+    ctx = gm.begin_training()
+    for _ in range(args.warmup):
+        gm.train_step(ctx)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        gm.train_step(ctx)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    inst = int(np.mean([l[2] for l in ctx.log[-args.steps:]]))
+    vis = int(np.mean([l[3] for l in ctx.log[-args.steps:]]))
+    loss_first, loss_last = ctx.log[0][0], ctx.log[-1][0]
+    stages = stage_profile(ctx.eng) if world == 1 else None
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---------------- end-to-end arm: the public call GaussianMap.train(steps=K) with the
+    # keyframes in pinned HOST memory (per step: H2D of the 8 sampled frames, D2H of the loss terms)
+    np.random.seed(1234)
+    gm2 = fresh_map(cfg, start, frames, dev, on_host=True, shard=shard)
+    gm2.train(steps=max(1, args.warmup))
+    barrier()
+    gm2 = fresh_map(cfg, start, frames, dev, on_host=True, shard=shard)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    gm2.train(steps=args.steps)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        return None
+    Bg = B * world
+    value = Bg * P * args.steps / (ms / 1e3) / 1e6
+    e2e = Bg * P * args.steps / (ms_e2e / 1e3) / 1e6
+    peaks, which = measured_peaks()
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "iters_per_s": args.steps / (ms / 1e3),
+        "config": {"workload": "BASELINE config[1]: office0-shaped room, 200k Gaussian surfels, 640x480, "
+                               "train-loop iteration (render 8 keyframes fwd+bwd, 4-term loss, Adam)",
+                   "gaussians": N, "H": H, "W": W, "keyframes_per_gpu": B, "global_batch": Bg,
+                   "parallelism": f"frame-shard x{world}", "instances_per_step": inst, "visible_per_step": vis,
+                   "l2": "inputs+outputs per step (~%.0f MB) exceed the 126 MB L2; no explicit flush"
+                         % ((88 * B * P + 136 * inst + 500 * N) / 1e6),
+                   "loss_first": loss_first, "loss_last": loss_last},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * P * 16 + B * 36 * 4,
+                "d2h_bytes_per_step": (4 + 2 * B) * 4 + 32, "ms_per_step": ms_e2e / args.steps,
+                "what": "GaussianMap.train(steps=K) incl. engine set-up and post_processing, keyframes in pinned host memory"},
+        "gpu_launches": 10 * args.steps,
+        "clocks": clk,
+    }
+    if stages is not None:
+        alg = algorithmic_bytes(N, B, P, inst, vis, tiles)
+        kern = {k: {"ms": stages[k], "alg_bytes": alg.get(k), "gbs": (alg[k] / (stages[k] * 1e-3) / 1e9) if k in alg and stages[k] > 0 else None}
+                for k in stages}
+        dom = max((k for k in stages if k in alg), key=lambda k: stages[k])
+        line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peaks["hbm_gbs"],
+                            "unit": "GB/s", "frac": kern[dom]["gbs"] / peaks["hbm_gbs"], "traffic": None,
+                            "peak_source": which, "share_of_step": stages[dom] / sum(stages.values())}
+        line["kernels"] = kern
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_reference_run(1, frames[:1], start, H, W, quiet=True)
+    return line
+
+
+def cpu_reference_run(steps, frames, start, H, W, quiet=False, warmup=0):
+    """The reference's path on the host cores = the oracle port (no CPU implementation exists in the
+    reference; its rasterizer is CUDA-only and absent).  Bounded sample: ONE keyframe per step at the
+    full 200k-Gaussian 640x480 workload: forward, 4-term loss, backward, Adam."""
+    from oracle import host_ref as hr
+    torch.set_num_threads(os.cpu_count())
+    state = {k: v.clone() for k, v in start.items()}
+    fr = [{k: v for k, v in f.items()} for f in frames]
+    for _ in range(warmup):
+        hr.train_iterations({k: v.clone() for k, v in state.items()}, fr, [[0]], torch.zeros(4), (0.001, 10.0), (H, W))
+    t0 = time.time()
+    hr.train_iterations(state, fr, [[0]] * steps, torch.zeros(4), (0.001, 10.0), (H, W))
+    dt = time.time() - t0
+    return {"value": steps * H * W / dt / 1e6, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{steps} step(s) x 1 keyframe (of 8) at full N/resolution: fwd+loss+bwd+Adam, torch-CPU oracle",
+            "seconds": dt}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    box, H, W, N = syn.ROOMS[CONFIG_IDX]
+    state = syn.make_room_scene(N, box=box, seed=1000 + CONFIG_IDX)
+    ext, K = syn.make_cameras(1, box=box, H=H, W=W, seed=2000 + CONFIG_IDX)
+    # GT for the CPU arm: the oracle's own render of the generating scene (no GPU involved)
+    from oracle import host_ref as hr, rasterizer_ref as rr
+    attrs = hr.activate(state["means"], state["scales"], state["rotations"], state["opacities"], state["harmonics"],
+                        state["view_scores"], state["view_supports"], state["view_means"])
+    with torch.no_grad():
+        out = hr.render_view_all(rr.rasterize, ext, K, attrs, torch.zeros(4), (0.001, 10.0), (H, W))
+    frames = [dict(rgb=out[0][0].clamp(0, 1), depth=syn.noisy_depth(out[1][0], seed=4000), extrinsic=ext[0],
+                   intrinsic=K[0], depth_range=torch.tensor([0.0, 5.0]))]
+    start = syn.perturb_state(state, seed=3000 + CONFIG_IDX)
+    steps = max(1, min(args.steps, 3))
+    cb = cpu_reference_run(steps, frames, start, H, W, warmup=min(args.warmup, 1))
+    return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["seconds"] / steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE config[1] (bounded sample: 1 keyframe per step)", "gaussians": N, "H": H, "W": W},
+            "cpu_baseline": cb, "gpu_launches": 0,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        line = run_reference(args, rank, world)
+    else:
+        line = run_ours(args, rank, world, local_rank)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    if world > 1 and args.impl == "ours":
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

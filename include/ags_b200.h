@@ -113,6 +113,16 @@ int ags_render_forward(const AgsRenderArgs* args);
 /* must be called with the same AgsRenderArgs (same workspace contents) as the forward */
 int ags_render_backward(const AgsRenderArgs* args, const AgsRenderGradArgs* grads);
 
+/* Profiling hook (bench.py): run one stage of the forward/backward pipeline so that each kernel can
+ * be bracketed with CUDA events.  Stages must be issued in pipeline order. */
+#define AGS_STAGE_CLEAR 0
+#define AGS_STAGE_PROJECT_FWD 1
+#define AGS_STAGE_BINNING 2
+#define AGS_STAGE_COMPOSITE_FWD 3
+#define AGS_STAGE_COMPOSITE_BWD 4
+#define AGS_STAGE_PROJECT_BWD 5
+int ags_render_stage(const AgsRenderArgs* args, const AgsRenderGradArgs* grads, int stage);
+
 typedef struct AgsLossArgs {
     int32_t B, H, W;
     int32_t B_total;               /* frames in the whole (possibly multi-GPU) batch; loss means use it */
@@ -138,6 +148,12 @@ typedef struct AgsLossArgs {
 size_t ags_loss_scratch_bytes(int32_t B, int32_t H, int32_t W);
 int ags_loss_forward_backward(const AgsLossArgs* args);
 
+/* forward-only post-processing of B rendered views (utils/operations.py:714-718):
+ * normal_unit = normalize(normal)*(opacity>1e-2), d2n = depth2normal(depth, mask, fov). */
+int ags_postprocess(int32_t B, int32_t H, int32_t W, const float* normal, const float* depth,
+                    const float* opacity, const float* fov, float* normal_unit, float* d2n,
+                    void* stream);
+
 #define AGS_ADAM_GROUPS 5
 typedef struct AgsAdamArgs {
     int32_t num_groups;                    /* <= AGS_ADAM_GROUPS */
@@ -151,6 +167,9 @@ typedef struct AgsAdamArgs {
     int32_t step;                          /* 1-based step used when step_dev == NULL */
     int32_t* step_dev;                     /* optional device counter: the kernel uses *step_dev + 1
                                               and a trailing 1-thread kernel increments it (graph replay) */
+    const int32_t* skip_flag;              /* optional: if *skip_flag != 0 the step is a no-op (pass
+                                              stats + AGS_STAT_OVERFLOW so an overflowed forward never
+                                              reaches the parameters) */
     void* stream;
 } AgsAdamArgs;
 

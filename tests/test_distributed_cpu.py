@@ -1,0 +1,63 @@
+"""CPU, world_size 2, gloo: the frame-sharding host logic (active_gs_b200/distributed.py) and the
+sharded sampler agreement -- the N>1 path of the training loop without GPUs."""
+import os
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from active_gs_b200.distributed import FrameShard
+    from active_gs_b200.gaussian_map import WeightedSampler
+    from active_gs_b200.config import default_gaussian_map_config
+    sh = FrameShard()
+    assert sh.world == world and sh.rank == rank
+    # same numpy seed on every rank -> same draw, disjoint contiguous slices that cover the batch
+    cfg = default_gaussian_map_config().sampler
+    cfg.batch_size = 8
+    np.random.seed(77)
+    sampler = WeightedSampler(cfg, 16)
+    perf = torch.linspace(0.1, 1.6, 16)
+    ids = sampler.next_ids(perf)
+    mine = sh.my_frames(ids)
+    assert sh.local_batch(len(ids)) == 4 and len(mine) == 4
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (ids.tolist(), mine.tolist()))
+    assert all(g[0] == ids.tolist() for g in gathered)
+    assert sum((g[1] for g in gathered), []) == ids.tolist()
+    # gradient all-reduce over views of one flat buffer = a single collective, summed over ranks
+    flat = torch.arange(14 * 5, dtype=torch.float32) * (rank + 1)
+    views, off = [], 0
+    for n, shape in [(15, (5, 3)), (15, (5, 3)), (20, (5, 4)), (5, (5,)), (15, (5, 1, 3))]:
+        views.append(flat[off:off + n].view(shape)); off += n
+    sh.all_reduce_grads_(views)
+    assert torch.equal(flat, torch.arange(70, dtype=torch.float32) * 3)
+    assert torch.equal(views[2], (torch.arange(30, 50, dtype=torch.float32) * 3).view(5, 4))
+    # visibility-count all-reduce (quirk Q1 coupling) and per-frame performance gather
+    vis = torch.full((3, 4), rank + 1, dtype=torch.int32)
+    assert int(sh.all_reduce_sum_(vis)[0, 0]) == 3
+    pf = sh.gather_perf(torch.tensor([rank + 0.25, rank + 0.5]), None)
+    assert torch.allclose(pf, torch.tensor([0.25, 0.5, 1.25, 1.5]))
+    with pytest.raises(ValueError):
+        sh.local_batch(7)
+    dist.barrier()
+    dist.destroy_process_group()
+    ret[rank] = True
+
+
+def test_frame_shard_world2_gloo():
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert all(ret.get(r) for r in range(world))

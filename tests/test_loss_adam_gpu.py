@@ -40,8 +40,14 @@ def make_inputs(B, H, W, seed):
 
 
 def oracle_loss(rgb, normal, depth, opacity, rgb_gt, depth_gt, fovs):
-    """operations.py:714-718 post-processing + gaussian_map.py:106-124 via the restated host oracle."""
+    """operations.py:714-718 post-processing + gaussian_map.py:106-124 via the restated host oracle.
+    Evaluated in float64: where all four depth2normal difference vectors of a pixel vanish
+    (isolated border pixel) normalize() divides by its eps=1e-12 and the fp32 autograd of the
+    reference leaves 1e12-amplified terms that only cancel to ~1e-7 relative -- noise of order 1 in
+    d_depth at those pixels.  The kernel returns the exact (cancelled) value, so is fp64 here."""
     B = rgb.shape[0]
+    rgb, normal, depth, opacity, rgb_gt, depth_gt = [t.double() for t in
+                                                     (rgb, normal, depth, opacity, rgb_gt, depth_gt)]
     leaves = [t.clone().requires_grad_(True) for t in (rgb, normal, depth)]
     r, n, d = leaves
     nus, d2ns = [], []
