@@ -6,8 +6,10 @@
 //
 // One CTA = one 16x16 tile of one view (grid.z = view: all B views of an iteration in one launch).
 // The tile's depth-sorted splat records (4 x float4 = 64 B each) are staged through shared memory in
-// batches of 256 with 128-bit loads, every thread then walks the batch for its pixel (shared-memory
-// broadcast reads).  The backward walks the SAME front-to-back order (no 1/(1-alpha) recurrences:
+// batches of 256 with 128-bit loads; the staging thread also derives the splat's cutoff bounding box
+// (the pixels where alpha can reach 1/255).  Each WARP owns an 8x4 pixel block of the tile, tests 32
+// splats at a time against its block (one ballot) and walks only the overlapping ones in depth
+// order (shared-memory broadcast reads) -- the skipped (warp, splat) pairs cost no evaluation at all.  The backward walks the SAME front-to-back order (no 1/(1-alpha) recurrences:
 // the "remaining" sum is total - prefix, computed from the saved forward outputs), reduces the 15
 // per-Gaussian partial gradients across the warp with a multi-value butterfly (16 shuffles instead
 // of 75) and issues one 16-lane vector RED per (warp, Gaussian) into a 64 B gradient record.
@@ -32,17 +34,51 @@ __device__ __forceinline__ SplatEval eval_alpha(const float4 g0, const float4 g1
     return e;
 }
 
+// Cutoff bounding box of a splat: alpha = o*exp(-q/2) >= 1/255  <=>  q <= tau = 2 ln(255 o); the
+// extent of {q <= tau} along x is sqrt(tau * Sigma_xx), Sigma = conic^-1.  Returned as
+// (xmin, xmax, ymin, ymax) in pixel coordinates, padded by a rounding margin; empty if o < 1/255.
+__device__ __forceinline__ float4 splat_bbox(const float4 g0, const float4 g1) {
+    const float tau = 2.f * __logf(255.f * g1.y);
+    if (!(tau > 0.f)) return make_float4(1e30f, -1e30f, 1e30f, -1e30f);
+    const float det = g0.z * g1.x - g0.w * g0.w;
+    const float inv = 1.f / det;
+    const float hx = sqrtf(tau * g1.x * inv) * 1.0001f + 1e-3f;
+    const float hy = sqrtf(tau * g0.z * inv) * 1.0001f + 1e-3f;
+    return make_float4(g0.x - hx, g0.x + hx, g0.y - hy, g0.y + hy);
+}
+
+struct WarpBlock {       // the 8x4 pixel block a warp owns inside its 16x16 tile
+    int px, py;          // this lane's pixel
+    float x0, x1, y0, y1;  // block extent in pixel coordinates (inclusive)
+};
+
+__device__ __forceinline__ WarpBlock warp_block(int tile_x, int tile_y, int tid) {
+    const int w = tid >> 5, lane = tid & 31;
+    const int bx = tile_x * TILE + (w & 1) * 8, by = tile_y * TILE + (w >> 1) * 4;
+    WarpBlock b;
+    b.px = bx + (lane & 7);
+    b.py = by + (lane >> 3);
+    b.x0 = (float)bx; b.x1 = (float)(bx + 7); b.y0 = (float)by; b.y1 = (float)(by + 3);
+    return b;
+}
+
+__device__ __forceinline__ bool bbox_hits(const float4 bb, const WarpBlock& b) {
+    return (bb.x <= b.x1) && (bb.y >= b.x0) && (bb.z <= b.y1) && (bb.w >= b.y0);
+}
+
 // K4 ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
-    __shared__ float4 s_g0[BATCH], s_g1[BATCH], s_f0[BATCH], s_f1[BATCH];
+    __shared__ float4 s_g0[BATCH], s_g1[BATCH], s_f0[BATCH], s_f1[BATCH], s_bb[BATCH];
     __shared__ int s_id[BATCH];
     const int v = blockIdx.z;
     const int tiles_x = gridDim.x, tiles_y = gridDim.y;
     const int tile = blockIdx.y * tiles_x + blockIdx.x;
     const size_t gt = (size_t)v * tiles_x * tiles_y + tile;
-    const int tid = threadIdx.y * TILE + threadIdx.x;
-    const int px = blockIdx.x * TILE + threadIdx.x, py = blockIdx.y * TILE + threadIdx.y;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const WarpBlock wb = warp_block(blockIdx.x, blockIdx.y, tid);
+    const int px = wb.px, py = wb.py;
     const bool inside = (px < a.W) && (py < a.H);
     const float pxf = (float)px, pyf = (float)py;
     const bool overflow = w.counters[0] > a.inst_cap;
@@ -59,38 +95,49 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f, D = 0.f, Cf = 0.f;
     int last = 0;
     bool done = !inside;
+    bool warp_done = __all_sync(0xffffffffu, done);
     for (int base = 0; base < n; base += BATCH) {
-        if (__syncthreads_and(done)) break;
+        if (__syncthreads_and(warp_done)) break;
         const int j = base + tid;
         if (j < n) {
             const int id = w.inst_sorted[off + j];
             const size_t idx = vN + id;
+            const float4 g0 = ldg4(w.geom0 + idx), g1 = ldg4(w.geom1 + idx);
             s_id[tid] = id;
-            s_g0[tid] = ldg4(w.geom0 + idx);
-            s_g1[tid] = ldg4(w.geom1 + idx);
+            s_g0[tid] = g0;
+            s_g1[tid] = g1;
             s_f0[tid] = ldg4(w.feat0 + idx);
             s_f1[tid] = ldg4(w.feat1 + idx);
+            s_bb[tid] = splat_bbox(g0, g1);
         }
         __syncthreads();
         const int cnt = min(BATCH, n - base);
-        for (int k = 0; !done && k < cnt; ++k) {
-            const float4 g0 = s_g0[k], g1 = s_g1[k];
-            const SplatEval e = eval_alpha(g0, g1, pxf, pyf);
-            if (e.skip) continue;
-            const float test_T = T * (1.f - e.alpha);
-            if (test_T < AGS_T_EPS) { done = true; continue; }
-            const float wgt = e.alpha * T;
-            const float4 f0 = s_f0[k], f1 = s_f1[k];
-            C0 += wgt * f0.x; C1 += wgt * f0.y; C2 += wgt * f0.z;
-            D += wgt * (f0.w - g1.z * e.dx - g1.w * e.dy);
-            N0 += wgt * f1.x; N1 += wgt * f1.y; N2 += wgt * f1.z;
-            Cf += wgt * f1.w;
-            T = test_T;
-            last = base + k + 1;
-            if (imp_pix && wgt > a.weight_thres) {
-                atomicAdd(a.count + vN + s_id[k], 1);
-                atomicAdd(a.importance + vN + s_id[k], wgt);
+        for (int c = 0; c < cnt && !warp_done; c += 32) {
+            const int jj = c + lane;
+            unsigned mask = __ballot_sync(0xffffffffu, jj < cnt && bbox_hits(s_bb[jj], wb));
+            while (mask) {
+                const int k = c + __ffs(mask) - 1;
+                mask &= mask - 1;
+                if (done) continue;
+                const float4 g0 = s_g0[k], g1 = s_g1[k];
+                const SplatEval e = eval_alpha(g0, g1, pxf, pyf);
+                if (e.skip) continue;
+                const float test_T = T * (1.f - e.alpha);
+                if (test_T < AGS_T_EPS) { done = true; continue; }
+                const float wgt = e.alpha * T;
+                const float4 f0 = s_f0[k], f1 = s_f1[k];
+                C0 += wgt * f0.x; C1 += wgt * f0.y; C2 += wgt * f0.z;
+                D += wgt * (f0.w - g1.z * e.dx - g1.w * e.dy);
+                N0 += wgt * f1.x; N1 += wgt * f1.y; N2 += wgt * f1.z;
+                Cf += wgt * f1.w;
+                T = test_T;
+                last = base + k + 1;
+                if (imp_pix && wgt > a.weight_thres) {
+                    atomicAdd(a.count + vN + s_id[k], 1);
+                    atomicAdd(a.importance + vN + s_id[k], wgt);
+                }
             }
+            warp_done = __all_sync(0xffffffffu, done);
         }
     }
     if (inside) {
@@ -155,16 +202,17 @@ __device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
 
 __global__ void __launch_bounds__(256)
 composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
-    __shared__ float4 s_g0[BATCH], s_g1[BATCH], s_f0[BATCH], s_f1[BATCH];
+    __shared__ float4 s_g0[BATCH], s_g1[BATCH], s_f0[BATCH], s_f1[BATCH], s_bb[BATCH];
     __shared__ int s_id[BATCH];
     __shared__ int s_max_last;
     const int v = blockIdx.z;
     const int tiles_x = gridDim.x, tiles_y = gridDim.y;
     const int tile = blockIdx.y * tiles_x + blockIdx.x;
     const size_t gt = (size_t)v * tiles_x * tiles_y + tile;
-    const int tid = threadIdx.y * TILE + threadIdx.x;
+    const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int px = blockIdx.x * TILE + threadIdx.x, py = blockIdx.y * TILE + threadIdx.y;
+    const WarpBlock wb = warp_block(blockIdx.x, blockIdx.y, tid);
+    const int px = wb.px, py = wb.py;
     const bool inside = (px < a.W) && (py < a.H);
     const float pxf = (float)px, pyf = (float)py;
     if (w.counters[0] > a.inst_cap) return;
@@ -206,6 +254,7 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
     __syncthreads();
     const int n_eff = min(n, s_max_last);
 
+    const int warp_last = __reduce_max_sync(0xffffffffu, my_last);
     float T = 1.f;
     for (int base = 0; base < n_eff; base += BATCH) {
         __syncthreads();
@@ -213,51 +262,59 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
         if (j < n_eff) {
             const int id = w.inst_sorted[off + j];
             const size_t idx = vN + id;
+            const float4 g0 = ldg4(w.geom0 + idx), g1 = ldg4(w.geom1 + idx);
             s_id[tid] = id;
-            s_g0[tid] = ldg4(w.geom0 + idx);
-            s_g1[tid] = ldg4(w.geom1 + idx);
+            s_g0[tid] = g0;
+            s_g1[tid] = g1;
             s_f0[tid] = ldg4(w.feat0 + idx);
             s_f1[tid] = ldg4(w.feat1 + idx);
+            s_bb[tid] = splat_bbox(g0, g1);
         }
         __syncthreads();
-        const int cnt = min(BATCH, n_eff - base);
-        for (int k = 0; k < cnt; ++k) {
-            const float4 g0 = s_g0[k], g1 = s_g1[k];
-            const SplatEval e = eval_alpha(g0, g1, pxf, pyf);
-            const bool active = (base + k < my_last) && !e.skip;
-            if (__ballot_sync(0xffffffffu, active) == 0u) continue;
-            float val[16];
+        const int cnt = min(BATCH, min(n_eff, warp_last) - base);   // nothing beyond the warp's last contributor
+        for (int c = 0; c < cnt; c += 32) {
+            const int jj = c + lane;
+            unsigned mask = __ballot_sync(0xffffffffu, jj < cnt && bbox_hits(s_bb[jj], wb));
+            while (mask) {
+                const int k = c + __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float4 g0 = s_g0[k], g1 = s_g1[k];
+                const SplatEval e = eval_alpha(g0, g1, pxf, pyf);
+                const bool active = (base + k < my_last) && !e.skip;
+                if (__ballot_sync(0xffffffffu, active) == 0u) continue;
+                float val[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) val[q] = 0.f;
-            if (active) {
-                const float4 f0 = s_f0[k], f1 = s_f1[k];
-                const float wgt = e.alpha * T;
-                const float one_m = 1.f - e.alpha;
-                const float dpix = f0.w - g1.z * e.dx - g1.w * e.dy;
-                const float s = gC0 * f0.x + gC1 * f0.y + gC2 * f0.z + gN0 * f1.x + gN1 * f1.y + gN2 * f1.z
-                              + gD * dpix + gCf * f1.w;
-                rem -= wgt * s;
-                const float dalpha = T * s - rem / one_m;
-                T *= one_m;
-                // alpha = min(0.99, o*G): clamped -> no gradient
-                const float G = __expf(e.power);
-                const bool unclamped = (g1.y * G <= AGS_ALPHA_MAX);
-                const float dpower = unclamped ? e.alpha * dalpha : 0.f;
-                const float wgD = wgt * gD;
-                val[0] = dpower * (-g0.z * e.dx - g0.w * e.dy) - wgD * g1.z;    // d x
-                val[1] = dpower * (-g1.x * e.dy - g0.w * e.dx) - wgD * g1.w;    // d y
-                val[2] = -0.5f * e.dx * e.dx * dpower;                          // d conic a
-                val[3] = -e.dx * e.dy * dpower;                                 // d conic b
-                val[4] = -0.5f * e.dy * e.dy * dpower;                          // d conic c
-                val[5] = unclamped ? G * dalpha : 0.f;                          // d opacity
-                val[6] = wgt * gC0; val[7] = wgt * gC1; val[8] = wgt * gC2;     // d rgb
-                val[9] = wgt * gN0; val[10] = wgt * gN1; val[11] = wgt * gN2;   // d normal
-                val[12] = wgD;                                                  // d depth
-                val[13] = -wgD * e.dx;                                          // d slope x
-                val[14] = -wgD * e.dy;                                          // d slope y
+                for (int q = 0; q < 16; ++q) val[q] = 0.f;
+                if (active) {
+                    const float4 f0 = s_f0[k], f1 = s_f1[k];
+                    const float wgt = e.alpha * T;
+                    const float one_m = 1.f - e.alpha;
+                    const float dpix = f0.w - g1.z * e.dx - g1.w * e.dy;
+                    const float sdot = gC0 * f0.x + gC1 * f0.y + gC2 * f0.z + gN0 * f1.x + gN1 * f1.y + gN2 * f1.z
+                                     + gD * dpix + gCf * f1.w;
+                    rem -= wgt * sdot;
+                    const float dalpha = T * sdot - rem / one_m;
+                    T *= one_m;
+                    // alpha = min(0.99, o*G): clamped -> no gradient
+                    const float G = __expf(e.power);
+                    const bool unclamped = (g1.y * G <= AGS_ALPHA_MAX);
+                    const float dpower = unclamped ? e.alpha * dalpha : 0.f;
+                    const float wgD = wgt * gD;
+                    val[0] = dpower * (-g0.z * e.dx - g0.w * e.dy) - wgD * g1.z;    // d x
+                    val[1] = dpower * (-g1.x * e.dy - g0.w * e.dx) - wgD * g1.w;    // d y
+                    val[2] = -0.5f * e.dx * e.dx * dpower;                          // d conic a
+                    val[3] = -e.dx * e.dy * dpower;                                 // d conic b
+                    val[4] = -0.5f * e.dy * e.dy * dpower;                          // d conic c
+                    val[5] = unclamped ? G * dalpha : 0.f;                          // d opacity
+                    val[6] = wgt * gC0; val[7] = wgt * gC1; val[8] = wgt * gC2;     // d rgb
+                    val[9] = wgt * gN0; val[10] = wgt * gN1; val[11] = wgt * gN2;   // d normal
+                    val[12] = wgD;                                                  // d depth
+                    val[13] = -wgD * e.dx;                                          // d slope x
+                    val[14] = -wgD * e.dy;                                          // d slope y
+                }
+                const float r = butterfly16(val, lane);
+                if ((lane & 1) == 0 && lane < 30) atomicAdd(w.dsplat + (vN + s_id[k]) * 16 + (lane >> 1), r);
             }
-            const float r = butterfly16(val, lane);
-            if ((lane & 1) == 0 && lane < 30) atomicAdd(w.dsplat + (vN + s_id[k]) * 16 + (lane >> 1), r);
         }
     }
 }
@@ -266,7 +323,7 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
 
 int ags_launch_composite_fwd(const AgsRenderArgs& a, const AgsWorkspace& w) {
     dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE, a.B);
-    dim3 block(TILE, TILE);
+    dim3 block(TILE * TILE);
     composite_fwd_kernel<<<grid, block, 0, (cudaStream_t)a.stream>>>(a, w);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -274,7 +331,7 @@ int ags_launch_composite_fwd(const AgsRenderArgs& a, const AgsWorkspace& w) {
 
 int ags_launch_composite_bwd(const AgsRenderArgs& a, const AgsRenderGradArgs& g, const AgsWorkspace& w) {
     dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE, a.B);
-    dim3 block(TILE, TILE);
+    dim3 block(TILE * TILE);
     composite_bwd_kernel<<<grid, block, 0, (cudaStream_t)a.stream>>>(a, g, w);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;

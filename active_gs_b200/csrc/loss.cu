@@ -8,10 +8,12 @@
 //   /root/reference/mapping/gaussian_map.py:132-139  track_performance per-frame means
 // and the autograd backward of all of it down to d rgb / d depth / d normal(raw).
 //
-// Two stencil passes, one thread per pixel, looping over the B frames (needed anyway for Q1):
-//   pass A: unit normal, d2n, adjoint of the un-normalised d2n vector, rgb gradient, loss sums
-//   pass B: depth gradient (L1 + gather of the d2n adjoints over the 3x3 window), normal gradient
-//           (consistency + gather of the TV terms, then through normalize*mask), TV loss sum
+// Two stencil passes, one thread per (pixel, frame):
+//   pass A: unit normal, d2n, rgb gradient, loss sums, and the depth gradient -- the L1 term plus the
+//           adjoint of depth2normal, which touches the pixel and its 4 neighbours and is SCATTERED
+//           with 5 float atomics (the gather form re-derives 4 neighbour stencils per pixel: 3x slower)
+//   pass B: normal gradient (consistency + gather of the TV terms, then through normalize*mask),
+//           TV loss sum
 // HBM roofline: reads 15 planes + writes 13 planes of B*H*W floats (+3 scratch planes twice).
 #include "ags_common.cuh"
 
@@ -99,78 +101,92 @@ __device__ __forceinline__ void block_accumulate(float (&v)[K], float* const (&d
     __syncthreads();
 }
 
+__device__ __forceinline__ float vis_sum(const AgsLossArgs& a, size_t P, size_t p) {
+    if (a.vis_count) return (float)a.vis_count[p];
+    float m = 0.f;
+    for (int f = 0; f < a.B; ++f) m += (a.opacity[(size_t)f * P + p] > 1e-3f) ? 1.f : 0.f;
+    return m;
+}
+
+// pass A: one thread per (pixel, frame).  Writes normal_unit, d2n, d_rgb; scatters the depth
+// gradient (L1 term + adjoint of depth2normal, 6 atomics into the zero-initialised d_depth).
 __global__ void __launch_bounds__(256)
-loss_pass_a(AgsLossArgs a, float* g_nsum) {
+loss_pass_a(AgsLossArgs a) {
     const int H = a.H, W = a.W;
     const size_t P = (size_t)H * W;
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
     const bool in = p < P;
-    const int y = in ? (int)(p / W) : 0, x = in ? (int)(p % W) : 0;
     const float Bt = (float)a.B_total;
     const float inv_rgb = 1.f / (Bt * 3.f * (float)P);
     const float inv_d = 1.f / (Bt * (float)P);
     const float inv_cons = 1.f / (Bt * Bt * (float)P);
-    float msum = 0.f;
+    float fr_rgb = 0.f, fr_d = 0.f, acc_cons = 0.f;
     if (in) {
-        if (a.vis_count) msum = (float)a.vis_count[p];
-        else for (int f = 0; f < a.B; ++f) msum += (a.opacity[(size_t)f * P + p] > 1e-3f) ? 1.f : 0.f;
-    }
-    float acc_rgb = 0.f, acc_d = 0.f, acc_cons = 0.f;
-    for (int f = 0; f < a.B; ++f) {
-        float fr_rgb = 0.f, fr_d = 0.f;
-        if (in) {
-            const float* opac = a.opacity + (size_t)f * P;
-            const float* depth = a.depth + (size_t)f * P;
-            const float A = opac[p];
-            const float mvis = (A > 1e-3f) ? 1.f : 0.f;
-            const float m2 = (A > 1e-2f) ? 1.f : 0.f;
-            // ---- L1 rgb + gradient
-            const float* rp = a.rgb + (size_t)f * 3 * P + p;
-            const float* rg = a.rgb_gt + (size_t)f * 3 * P + p;
-            float* drgb = a.d_rgb + (size_t)f * 3 * P + p;
+        const int y = (int)(p / W), x = (int)(p % W);
+        const float msum = vis_sum(a, P, p);
+        const float* opac = a.opacity + (size_t)f * P;
+        const float* depth = a.depth + (size_t)f * P;
+        float* ddep = a.d_depth + (size_t)f * P;
+        const float A = opac[p];
+        const float mvis = (A > 1e-3f) ? 1.f : 0.f;
+        const float m2 = (A > 1e-2f) ? 1.f : 0.f;
+        // ---- L1 rgb + gradient
+        const float* rp = a.rgb + (size_t)f * 3 * P + p;
+        const float* rg = a.rgb_gt + (size_t)f * 3 * P + p;
+        float* drgb = a.d_rgb + (size_t)f * 3 * P + p;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float e = (rp[c * P] - rg[c * P]) * mvis;
-                fr_rgb += fabsf(e);
-                drgb[c * P] = (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f)) * mvis * inv_rgb;
-            }
-            // ---- L1 depth (gradient is finished in pass B)
-            const float dg = a.depth_gt[(size_t)f * P + p];
-            const float md = (dg > 0.f) ? 1.f : 0.f;
-            fr_d = fabsf((depth[p] - dg) * md);
-            // ---- unit normal
-            const float* np_ = a.normal + (size_t)f * 3 * P + p;
-            const F3 n = f3(np_[0], np_[P], np_[2 * P]);
-            const float nn = fmaxf(sqrtf(dot(n, n)), 1e-12f);
-            const F3 nu = n * (m2 / nn);
-            float* no = a.normal_unit + (size_t)f * 3 * P + p;
-            no[0] = nu.x; no[P] = nu.y; no[2 * P] = nu.z;
-            // ---- depth2normal
-            const FrameGeom g = frame_geom(a.fov, f, H, W);
-            const D2N v = d2n_vectors(depth, opac, g, H, W, y, x);
-            const F3 ns = cross(v.pu, v.pl) + cross(v.pr, v.pu) + cross(v.pb, v.pr) + cross(v.pl, v.pb);
-            const float nsn = fmaxf(sqrtf(dot(ns, ns)), 1e-12f);
-            const F3 u = ns * (1.f / nsn);
-            const F3 d2n = u * m2;
-            float* dn = a.d2n + (size_t)f * 3 * P + p;
-            dn[0] = d2n.x; dn[P] = d2n.y; dn[2 * P] = d2n.z;
-            // ---- consistency loss and the adjoint of the un-normalised d2n vector
-            acc_cons += (1.f - dot(nu, d2n)) * msum;
-            const float wc = -a.w_cons * msum * inv_cons;                // dL/d(nu . d2n)
-            const F3 gd = nu * (wc * m2);                                // dL/d u  (d2n = u*m2)
-            const F3 gns = (gd - u * dot(u, gd)) * (1.f / nsn);
-            float* gs = g_nsum + (size_t)f * 3 * P + p;
-            gs[0] = gns.x; gs[P] = gns.y; gs[2 * P] = gns.z;
+        for (int c = 0; c < 3; ++c) {
+            const float e = (rp[c * P] - rg[c * P]) * mvis;
+            fr_rgb += fabsf(e);
+            drgb[c * P] = (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f)) * mvis * inv_rgb;
         }
-        acc_rgb += fr_rgb;
-        acc_d += fr_d;
-        float v2[2] = {fr_rgb / (3.f * (float)P), fr_d / (float)P};
-        float* const d2[2] = {a.loss_terms + 4 + 2 * f, a.loss_terms + 4 + 2 * f + 1};
-        block_accumulate<2>(v2, d2);
+        // ---- L1 depth + gradient
+        const float dg = a.depth_gt[(size_t)f * P + p];
+        const float md = (dg > 0.f) ? 1.f : 0.f;
+        const float ed = (depth[p] - dg) * md;
+        fr_d = fabsf(ed);
+        float dd_self = a.w_depth * (ed > 0.f ? 1.f : (ed < 0.f ? -1.f : 0.f)) * md * inv_d;
+        // ---- unit normal
+        const float* np_ = a.normal + (size_t)f * 3 * P + p;
+        const F3 n = f3(np_[0], np_[P], np_[2 * P]);
+        const float nn = fmaxf(sqrtf(dot(n, n)), 1e-12f);
+        const F3 nu = n * (m2 / nn);
+        float* no = a.normal_unit + (size_t)f * 3 * P + p;
+        no[0] = nu.x; no[P] = nu.y; no[2 * P] = nu.z;
+        // ---- depth2normal
+        const FrameGeom g = frame_geom(a.fov, f, H, W);
+        const D2N v = d2n_vectors(depth, opac, g, H, W, y, x);
+        const F3 ns = cross(v.pu, v.pl) + cross(v.pr, v.pu) + cross(v.pb, v.pr) + cross(v.pl, v.pb);
+        const float nsn = fmaxf(sqrtf(dot(ns, ns)), 1e-12f);
+        const F3 u = ns * (1.f / nsn);
+        const F3 d2n = u * m2;
+        float* dn = a.d2n + (size_t)f * 3 * P + p;
+        dn[0] = d2n.x; dn[P] = d2n.y; dn[2 * P] = d2n.z;
+        // ---- consistency loss; adjoint of the un-normalised d2n vector, pushed to the five depths
+        acc_cons = (1.f - dot(nu, d2n)) * msum;
+        if (m2 > 0.f && msum > 0.f) {
+            const float wc = -a.w_cons * msum * inv_cons;                // dL/d(nu . d2n)
+            const F3 gd = nu * wc;                                       // dL/d u  (d2n = u*m2, m2 = 1)
+            const F3 gq = (gd - u * dot(u, gd)) * (1.f / nsn);
+            const F3 dpu = (cross(v.pl, gq) + cross(gq, v.pr)) * v.mu;
+            const F3 dpl = (cross(gq, v.pu) + cross(v.pb, gq)) * v.ml;
+            const F3 dpb = (cross(v.pr, gq) + cross(gq, v.pl)) * v.mb;
+            const F3 dpr = (cross(v.pu, gq) + cross(gq, v.pb)) * v.mr;
+            const F3 dpc = (dpu + dpl + dpb + dpr) * (-v.mc);
+            const float rx = (x - g.cx) * g.ik00, ry = (y - g.cy) * g.ik11;   // c = depth * (rx, ry, 1)
+            dd_self += dpc.x * rx + dpc.y * ry + dpc.z;
+            if (v.mu > 0.f) atomicAdd(ddep + p - W, dpu.x * rx + dpu.y * (ry - g.ik11) + dpu.z);
+            if (v.ml > 0.f) atomicAdd(ddep + p - 1, dpl.x * (rx - g.ik00) + dpl.y * ry + dpl.z);
+            if (v.mb > 0.f) atomicAdd(ddep + p + W, dpb.x * rx + dpb.y * (ry + g.ik11) + dpb.z);
+            if (v.mr > 0.f) atomicAdd(ddep + p + 1, dpr.x * (rx + g.ik00) + dpr.y * ry + dpr.z);
+        }
+        if (dd_self != 0.f) atomicAdd(ddep + p, dd_self);
     }
-    float v3[3] = {acc_rgb * inv_rgb, acc_d * inv_d, acc_cons * inv_cons};
-    float* const d3[3] = {a.loss_terms + 0, a.loss_terms + 1, a.loss_terms + 2};
-    block_accumulate<3>(v3, d3);
+    float v5[5] = {fr_rgb * inv_rgb, fr_d * inv_d, acc_cons * inv_cons, fr_rgb / (3.f * (float)P), fr_d / (float)P};
+    float* const d5[5] = {a.loss_terms + 0, a.loss_terms + 1, a.loss_terms + 2,
+                          a.loss_terms + 4 + 2 * f, a.loss_terms + 4 + 2 * f + 1};
+    block_accumulate<5>(v5, d5);
 }
 
 // TV helper: value and derivative factor of one one-sided difference
@@ -185,118 +201,60 @@ __device__ __forceinline__ void tv_term(F3 np_, F3 nq, float dp, float dq, float
     coef = gate * e * (1.f - nd * inv2s2);       // d val / d nd
 }
 
+// pass B: one thread per (pixel, frame): normal gradient (consistency + TV gather, through
+// normalize*mask) and the TV loss sum.
 __global__ void __launch_bounds__(256)
-loss_pass_b(AgsLossArgs a, const float* g_nsum) {
+loss_pass_b(AgsLossArgs a) {
     const int H = a.H, W = a.W;
     const size_t P = (size_t)H * W;
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
     const bool in = p < P;
-    const int y = in ? (int)(p / W) : 0, x = in ? (int)(p % W) : 0;
     const float Bt = (float)a.B_total;
-    const float inv_d = 1.f / (Bt * (float)P);
     const float inv_cons = 1.f / (Bt * Bt * (float)P);
     const float inv_tv = 1.f / (Bt * 4.f * (float)P);
     const float inv2s2 = 1.f / (2.f * 0.3f * 0.3f);
-    float msum = 0.f;
-    if (in) {
-        if (a.vis_count) msum = (float)a.vis_count[p];
-        else for (int f = 0; f < a.B; ++f) msum += (a.opacity[(size_t)f * P + p] > 1e-3f) ? 1.f : 0.f;
-    }
     float acc_tv = 0.f;
-    for (int f = 0; f < a.B && in; ++f) {
-        const float* opac = a.opacity + (size_t)f * P;
+    if (in) {
+        const int y = (int)(p / W), x = (int)(p % W);
+        const float msum = vis_sum(a, P, p);
         const float* depth = a.depth + (size_t)f * P;
         const float* dgt = a.depth_gt + (size_t)f * P;
         const float* nu_ = a.normal_unit + (size_t)f * 3 * P;
-        const float* gs_ = g_nsum + (size_t)f * 3 * P;
-        const FrameGeom g = frame_geom(a.fov, f, H, W);
-        auto NU = [&](int yy, int xx) { const size_t q = (size_t)yy * W + xx; return f3(nu_[q], nu_[P + q], nu_[2 * P + q]); };
-        auto GS = [&](int yy, int xx) { const size_t q = (size_t)yy * W + xx; return f3(gs_[q], gs_[P + q], gs_[2 * P + q]); };
+        auto NU = [&](size_t q) { return f3(nu_[q], nu_[P + q], nu_[2 * P + q]); };
         const float dp = depth[p];
         const float md_p = (dgt[p] > 0.f) ? 1.f : 0.f;
-        const float m2 = (opac[p] > 1e-2f) ? 1.f : 0.f;
-
-        // ---------------- depth gradient: L1 + d2n gather
-        const float e = (dp - dgt[p]) * md_p;
-        float ddepth = a.w_depth * (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f)) * md_p * inv_d;
-        {
-            F3 dc = f3(0.f, 0.f, 0.f);
-            // own pixel: p_c enters all four difference vectors with a minus sign
-            {
-                const D2N v = d2n_vectors(depth, opac, g, H, W, y, x);
-                const F3 gq = GS(y, x);
-                const F3 dpu = cross(v.pl, gq) + cross(gq, v.pr);
-                const F3 dpl = cross(gq, v.pu) + cross(v.pb, gq);
-                const F3 dpb = cross(v.pr, gq) + cross(gq, v.pl);
-                const F3 dpr = cross(v.pu, gq) + cross(gq, v.pb);
-                const F3 dpc = (dpu * v.mu + dpl * v.ml + dpb * v.mb + dpr * v.mr) * (-1.f);
-                dc = dc + dpc * v.mc;
-            }
-            // neighbours q for which this pixel is the up / left / bottom / right sample
-            if (y < H - 1) {   // q below: p is q's "up"
-                const D2N v = d2n_vectors(depth, opac, g, H, W, y + 1, x);
-                const F3 gq = GS(y + 1, x);
-                dc = dc + (cross(v.pl, gq) + cross(gq, v.pr)) * v.mu;
-            }
-            if (x < W - 1) {   // q right: p is q's "left"
-                const D2N v = d2n_vectors(depth, opac, g, H, W, y, x + 1);
-                const F3 gq = GS(y, x + 1);
-                dc = dc + (cross(gq, v.pu) + cross(v.pb, gq)) * v.ml;
-            }
-            if (y > 0) {       // q above: p is q's "bottom"
-                const D2N v = d2n_vectors(depth, opac, g, H, W, y - 1, x);
-                const F3 gq = GS(y - 1, x);
-                dc = dc + (cross(v.pr, gq) + cross(gq, v.pl)) * v.mb;
-            }
-            if (x > 0) {       // q left: p is q's "right"
-                const D2N v = d2n_vectors(depth, opac, g, H, W, y, x - 1);
-                const F3 gq = GS(y, x - 1);
-                dc = dc + (cross(v.pu, gq) + cross(gq, v.pb)) * v.mr;
-            }
-            ddepth += dc.x * (x - g.cx) * g.ik00 + dc.y * (y - g.cy) * g.ik11 + dc.z;
-        }
-        a.d_depth[(size_t)f * P + p] = ddepth;
-
-        // ---------------- normal gradient: consistency + TV gather, then through normalize*mask
-        const F3 nu = NU(y, x);
+        const float m2 = (a.opacity[(size_t)f * P + p] > 1e-2f) ? 1.f : 0.f;
+        const F3 nu = NU(p);
         const float* d2p = a.d2n + (size_t)f * 3 * P + p;
-        const F3 d2n = f3(d2p[0], d2p[P], d2p[2 * P]);
-        F3 gnu = d2n * (-a.w_cons * msum * inv_cons);
-        {
-            const float ctv = a.w_tv * inv_tv;
-            float val, coef;
-            // own four differences
-            if (x < W - 1) { const F3 nq = NU(y, x + 1); tv_term(nu, nq, dp, depth[p + 1], md_p, inv2s2, val, coef);
-                             acc_tv += val; gnu = gnu + (nu - nq) * (2.f * coef * ctv); }
-            if (x > 0)     { const F3 nq = NU(y, x - 1); tv_term(nu, nq, dp, depth[p - 1], md_p, inv2s2, val, coef);
-                             acc_tv += val; gnu = gnu + (nu - nq) * (2.f * coef * ctv); }
-            if (y < H - 1) { const F3 nq = NU(y + 1, x); tv_term(nu, nq, dp, depth[p + W], md_p, inv2s2, val, coef);
-                             acc_tv += val; gnu = gnu + (nu - nq) * (2.f * coef * ctv); }
-            if (y > 0)     { const F3 nq = NU(y - 1, x); tv_term(nu, nq, dp, depth[p - W], md_p, inv2s2, val, coef);
-                             acc_tv += val; gnu = gnu + (nu - nq) * (2.f * coef * ctv); }
-            // differences of the neighbours that reference this pixel (their mask, their centre)
-            if (x > 0)     { const F3 nq = NU(y, x - 1); const float mdq = (dgt[p - 1] > 0.f) ? 1.f : 0.f;
-                             tv_term(nq, nu, depth[p - 1], dp, mdq, inv2s2, val, coef);
-                             gnu = gnu - (nq - nu) * (2.f * coef * ctv); }
-            if (x < W - 1) { const F3 nq = NU(y, x + 1); const float mdq = (dgt[p + 1] > 0.f) ? 1.f : 0.f;
-                             tv_term(nq, nu, depth[p + 1], dp, mdq, inv2s2, val, coef);
-                             gnu = gnu - (nq - nu) * (2.f * coef * ctv); }
-            if (y > 0)     { const F3 nq = NU(y - 1, x); const float mdq = (dgt[p - W] > 0.f) ? 1.f : 0.f;
-                             tv_term(nq, nu, depth[p - W], dp, mdq, inv2s2, val, coef);
-                             gnu = gnu - (nq - nu) * (2.f * coef * ctv); }
-            if (y < H - 1) { const F3 nq = NU(y + 1, x); const float mdq = (dgt[p + W] > 0.f) ? 1.f : 0.f;
-                             tv_term(nq, nu, depth[p + W], dp, mdq, inv2s2, val, coef);
-                             gnu = gnu - (nq - nu) * (2.f * coef * ctv); }
+        F3 gnu = f3(d2p[0], d2p[P], d2p[2 * P]) * (-a.w_cons * msum * inv_cons);
+        const float ctv = a.w_tv * inv_tv;
+        float val, coef;
+        // each neighbour q contributes the own one-sided difference (mask of p) and the mirrored
+        // difference of q that references p (mask of q)
+#define AGS_TV_PAIR(cond, q)                                                                 \
+        if (cond) {                                                                          \
+            const F3 nq = NU(q);                                                             \
+            const float dq = depth[q];                                                       \
+            tv_term(nu, nq, dp, dq, md_p, inv2s2, val, coef);                                \
+            acc_tv += val;                                                                   \
+            gnu = gnu + (nu - nq) * (2.f * coef * ctv);                                      \
+            const float mdq = (dgt[q] > 0.f) ? 1.f : 0.f;                                    \
+            tv_term(nq, nu, dq, dp, mdq, inv2s2, val, coef);                                 \
+            gnu = gnu - (nq - nu) * (2.f * coef * ctv);                                      \
         }
-        {
-            const float* np_ = a.normal + (size_t)f * 3 * P + p;
-            const F3 n = f3(np_[0], np_[P], np_[2 * P]);
-            const float nn = fmaxf(sqrtf(dot(n, n)), 1e-12f);
-            const F3 uh = n * (1.f / nn);
-            const F3 gn = (gnu - uh * dot(uh, gnu)) * (m2 / nn);
-            float* dn = a.d_normal + (size_t)f * 3 * P + p;
-            dn[0] = gn.x; dn[P] = gn.y; dn[2 * P] = gn.z;
-        }
+        AGS_TV_PAIR(x < W - 1, p + 1)
+        AGS_TV_PAIR(x > 0, p - 1)
+        AGS_TV_PAIR(y < H - 1, p + W)
+        AGS_TV_PAIR(y > 0, p - W)
+#undef AGS_TV_PAIR
+        const float* np_ = a.normal + (size_t)f * 3 * P + p;
+        const F3 n = f3(np_[0], np_[P], np_[2 * P]);
+        const float nn = fmaxf(sqrtf(dot(n, n)), 1e-12f);
+        const F3 uh = n * (1.f / nn);
+        const F3 gn = (gnu - uh * dot(uh, gnu)) * (m2 / nn);
+        float* dn = a.d_normal + (size_t)f * 3 * P + p;
+        dn[0] = gn.x; dn[P] = gn.y; dn[2 * P] = gn.z;
     }
     float v1[1] = {acc_tv * inv_tv};
     float* const d1[1] = {a.loss_terms + 3};
@@ -346,7 +304,7 @@ extern "C" int ags_postprocess(int32_t B, int32_t H, int32_t W, const float* nor
 
 extern "C" size_t ags_loss_scratch_bytes(int32_t B, int32_t H, int32_t W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
-    return ags_align256((size_t)B * 3 * H * W * sizeof(float));
+    return 256;   // the two-pass scheme needs no scratch any more; kept for ABI stability
 }
 
 extern "C" int ags_loss_forward_backward(const AgsLossArgs* a) {
@@ -362,11 +320,11 @@ extern "C" int ags_loss_forward_backward(const AgsLossArgs* a) {
     cudaStream_t st = (cudaStream_t)a->stream;
     AGS_CHECK_CUDA(cudaMemsetAsync(a->loss_terms, 0, (4 + 2 * (size_t)a->B) * sizeof(float), st));
     const size_t P = (size_t)a->H * a->W;
-    const int blocks = (int)((P + 255) / 256);
-    float* g_nsum = (float*)a->workspace;
-    loss_pass_a<<<blocks, 256, 0, st>>>(*a, g_nsum);
+    AGS_CHECK_CUDA(cudaMemsetAsync(a->d_depth, 0, (size_t)a->B * P * sizeof(float), st));
+    dim3 grid((unsigned)((P + 255) / 256), a->B);
+    loss_pass_a<<<grid, 256, 0, st>>>(*a);
     AGS_CHECK_CUDA(cudaGetLastError());
-    loss_pass_b<<<blocks, 256, 0, st>>>(*a, g_nsum);
+    loss_pass_b<<<grid, 256, 0, st>>>(*a);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
