@@ -34,11 +34,10 @@ struct FrameGeom {       // per-frame constants of depth2normal (quirk Q2)
     float cx, cy;        // W/2, H/2
 };
 
-__device__ __forceinline__ FrameGeom frame_geom(const float* fov, int f, int H, int W) {
+__device__ __forceinline__ FrameGeom frame_geom(const float* tanfov, int f, int H, int W) {
     FrameGeom g;
-    const float f0 = __ldg(fov + 2 * f), f1 = __ldg(fov + 2 * f + 1);
-    g.ik00 = (2.f * tanf(0.5f * f0)) / (float)H;
-    g.ik11 = (2.f * tanf(0.5f * f1)) / (float)W;
+    g.ik00 = (2.f * __ldg(tanfov + 2 * f)) / (float)H;
+    g.ik11 = (2.f * __ldg(tanfov + 2 * f + 1)) / (float)W;
     g.cx = 0.5f * W;
     g.cy = 0.5f * H;
     return g;
@@ -155,7 +154,7 @@ loss_pass_a(AgsLossArgs a) {
         float* no = a.normal_unit + (size_t)f * 3 * P + p;
         no[0] = nu.x; no[P] = nu.y; no[2 * P] = nu.z;
         // ---- depth2normal
-        const FrameGeom g = frame_geom(a.fov, f, H, W);
+        const FrameGeom g = frame_geom(a.tanfov, f, H, W);
         const D2N v = d2n_vectors(depth, opac, g, H, W, y, x);
         const F3 ns = cross(v.pu, v.pl) + cross(v.pr, v.pu) + cross(v.pb, v.pr) + cross(v.pl, v.pb);
         const float nsn = fmaxf(sqrtf(dot(ns, ns)), 1e-12f);
@@ -311,7 +310,7 @@ extern "C" int ags_loss_forward_backward(const AgsLossArgs* a) {
     AGS_CHECK_ARG(a != nullptr, "args is NULL");
     AGS_CHECK_ARG(a->B > 0 && a->H > 0 && a->W > 0 && a->B_total >= a->B, "bad sizes B=%d H=%d W=%d B_total=%d",
                   a->B, a->H, a->W, a->B_total);
-    AGS_CHECK_ARG(a->rgb && a->normal && a->depth && a->opacity && a->rgb_gt && a->depth_gt && a->fov,
+    AGS_CHECK_ARG(a->rgb && a->normal && a->depth && a->opacity && a->rgb_gt && a->depth_gt && a->tanfov,
                   "NULL input");
     AGS_CHECK_ARG(a->normal_unit && a->d2n && a->d_rgb && a->d_normal && a->d_depth && a->loss_terms,
                   "NULL output");

@@ -75,10 +75,13 @@ class _TrainEngine:
         self.conf = gm.get_confidences.contiguous()
         self.rgb_gt = torch.empty(B, 3, H, W, **o)
         self.depth_gt = torch.empty(B, 1, H, W, **o)
-        self.view = torch.empty(B, 16, **o)
-        self.proj = torch.empty(B, 16, **o)
-        self.tanfov = torch.empty(B, 2, **o)
-        self.fov = torch.empty(B, 2, **o)
+        # camera blocks of the batch: one flat device buffer [B*16 view | B*16 proj | B*2 tanfov]
+        # refreshed by ONE small H2D copy per iteration from a pinned staging buffer
+        self.cam_flat = torch.empty(B * 34, **o)
+        self.view = self.cam_flat[:B * 16].view(B, 16)
+        self.proj = self.cam_flat[B * 16:B * 32].view(B, 16)
+        self.tanfov = self.cam_flat[B * 32:].view(B, 2)
+        self.cam_host = torch.empty(B * 34, dtype=torch.float32).pin_memory()
         self.bg = gm.background_color.to(dev).float().contiguous()
         cap = gm._inst_cap_hint(N, B)
         self.rb = RenderBatch(gm._means, gm._scales, gm._rotations, gm._opacities,
@@ -95,27 +98,34 @@ class _TrainEngine:
         self.host = torch.empty(2 * B + 4, dtype=torch.float32).pin_memory()
         self.host_stats = torch.empty(L.AGS_NUM_STATS, dtype=torch.int32).pin_memory()
         self.event = torch.cuda.Event()
+        self.fwd_args = self.rb._args()      # argument structs are built once: pointers never change
+        self.grad_args = None
+        self.adam_cache = {}
 
-    def set_batch(self, rgbs, depths, view, proj, tanfov, fov):
-        """Stage this iteration's keyframes (lists of (3,H,W)/(1,H,W) tensors) and camera blocks in
-        the fixed device buffers.  Pinned host sources make this the per-step H2D of the end-to-end
-        path; device sources are gathered with one stack kernel per tensor."""
+    def set_batch(self, rgbs, depths, views_h, projs_h, tanfovs_h, idx):
+        """Stage this iteration's keyframes (lists of (3,H,W)/(1,H,W) tensors) and camera blocks
+        (rows `idx` of the host camera tables) in the fixed device buffers.  Pinned host frames make
+        this the per-step H2D of the end-to-end path; device frames are gathered with one stack
+        kernel per tensor."""
+        B = self.B
         if rgbs[0].is_cuda:
             torch.stack(rgbs, out=self.rgb_gt)
             torch.stack(depths, out=self.depth_gt)
         else:
-            for k in range(self.B):
+            for k in range(B):
                 self.rgb_gt[k].copy_(rgbs[k], non_blocking=True)
                 self.depth_gt[k].copy_(depths[k], non_blocking=True)
-        self.view.copy_(view.reshape(self.B, 16), non_blocking=True)
-        self.proj.copy_(proj.reshape(self.B, 16), non_blocking=True)
-        self.tanfov.copy_(tanfov, non_blocking=True)
-        self.fov.copy_(fov, non_blocking=True)
+        h = self.cam_host
+        torch.index_select(views_h, 0, idx, out=h[:B * 16].view(B, 16))
+        torch.index_select(projs_h, 0, idx, out=h[B * 16:B * 32].view(B, 16))
+        torch.index_select(tanfovs_h, 0, idx, out=h[B * 32:].view(B, 2))
+        self.cam_flat.copy_(h, non_blocking=True)
 
     def grow(self, need):
         """re-plan the instance capacity after an overflow (nothing was rendered or updated)"""
         self.rb.inst_cap = int(need * 1.3) + 65536
         self.rb._alloc(L.load())
+        self.fwd_args = self.rb._args()
 
     def iterate(self):
         """Enqueue one optimisation step on the staged batch.  Order on the stream:
@@ -124,33 +134,37 @@ class _TrainEngine:
         with the host preparing the next batch.  Adam is gated on the device overflow flag."""
         lib = L.load()
         rb = self.rb
-        rb.forward(check_overflow=False)
+        st = L.current_stream(self.dev)
+        fa = self.fwd_args
+        fa.stream = st
+        L.check(lib.ags_render_forward(C.byref(fa)), "ags_render_forward")
         vis = None
         if self.dist is not None:
             torch.sum(rb.opacity[:, 0] > 1e-3, dim=0, dtype=torch.int32, out=self.vis_count)
             self.dist.all_reduce_sum_(self.vis_count)
             vis = self.vis_count
         self.loss_out = ops.loss_forward_backward(
-            rb.rgb, rb.normal, rb.depth, rb.opacity, self.rgb_gt, self.depth_gt, self.fov,
+            rb.rgb, rb.normal, rb.depth, rb.opacity, self.rgb_gt, self.depth_gt, self.tanfov,
             B_total=self.B_total, vis_count=vis, out=self.loss_out)
         lo = self.loss_out
-        B = self.B
         self.host.copy_(lo.terms, non_blocking=True)
         self.host_stats.copy_(rb.stats, non_blocking=True)
         self.event.record(torch.cuda.current_stream(self.dev))
-        g = L.RenderGradArgs()
-        g.d_rgb, g.d_normal, g.d_depth = L.ptr(lo.d_rgb), L.ptr(lo.d_normal), L.ptr(lo.d_depth)
-        g.d_opacity = g.d_confidence = None
-        (g.d_means3D, g.d_scales, g.d_rotations, g.d_opacities, g.d_colors) = [
-            L.ptr(t) for t in self.grads]
-        g.d_means2D = None
-        g.accumulate = 0
-        L.check(lib.ags_render_backward(C.byref(rb._args()), C.byref(g)), "ags_render_backward")
+        if self.grad_args is None:
+            g = L.RenderGradArgs()
+            g.d_rgb, g.d_normal, g.d_depth = L.ptr(lo.d_rgb), L.ptr(lo.d_normal), L.ptr(lo.d_depth)
+            g.d_opacity = g.d_confidence = None
+            (g.d_means3D, g.d_scales, g.d_rotations, g.d_opacities, g.d_colors) = [
+                L.ptr(t) for t in self.grads]
+            g.d_means2D = None
+            g.accumulate = 0
+            self.grad_args = g
+        L.check(lib.ags_render_backward(C.byref(fa), C.byref(self.grad_args)), "ags_render_backward")
         if self.dist is not None:
             self.dist.all_reduce_grads_(self.grads)
         self.step += 1
         ops.adam_step(self.params, self.grads, self.m, self.v, self.lrs, step=self.step,
-                      skip_flag_ptr=rb.stats.data_ptr() + 4 * L.STAT_OVERFLOW)
+                      skip_flag_ptr=rb.stats.data_ptr() + 4 * L.STAT_OVERFLOW, cache=self.adam_cache)
 
     def fetch(self):
         """Wait for the loss terms / per-frame performance / instance statistics of the step that
@@ -220,11 +234,10 @@ class GaussianMap:
         sampler = WeightedSampler(self.cfg.sampler, T)
         B = sampler.v if self.dist is None else self.dist.local_batch(sampler.v)
         _, H, W = self.training_data[0]["rgb"].shape
-        fovs, views, projs, tanfovs = self._camera_table()
-        place = (lambda t: t.pin_memory()) if self.frames_on_host else (lambda t: t.to(self.device))
+        fovs, views, projs, tanfovs = self._camera_table()           # host tensors (T, .)
         return SimpleNamespace(
-            sampler=sampler, B=B, H=H, W=W, fovs=place(fovs), views=place(views), projs=place(projs),
-            tanfovs=place(tanfovs), eng=_TrainEngine(self, B, H, W, self.dist),
+            sampler=sampler, B=B, H=H, W=W, views=views.contiguous(), projs=projs.contiguous(),
+            tanfovs=tanfovs.contiguous(), eng=_TrainEngine(self, B, H, W, self.dist),
             perf_host=self.training_performance.detach().float().cpu().clone(), log=[])
 
     def train_step(self, ctx, ids=None):
@@ -236,7 +249,7 @@ class GaussianMap:
         idx = torch.as_tensor(my, dtype=torch.long)
         eng.set_batch([self.training_data[i]["rgb"] for i in my],
                       [self.training_data[i]["depth"] for i in my],
-                      ctx.views[idx], ctx.projs[idx], ctx.tanfovs[idx], ctx.fovs[idx])
+                      ctx.views, ctx.projs, ctx.tanfovs, idx)
         while True:
             eng.iterate()
             terms, perf, stats = eng.fetch()

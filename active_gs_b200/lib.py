@@ -46,7 +46,7 @@ class LossArgs(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("B_total", C.c_int32),
         ("rgb", _f), ("normal", _f), ("depth", _f), ("opacity", _f),
-        ("rgb_gt", _f), ("depth_gt", _f), ("fov", _f), ("vis_count", _f),
+        ("rgb_gt", _f), ("depth_gt", _f), ("tanfov", _f), ("vis_count", _f),
         ("normal_unit", _f), ("d2n", _f), ("d_rgb", _f), ("d_normal", _f), ("d_depth", _f),
         ("loss_terms", _f),
         ("w_depth", C.c_float), ("w_cons", C.c_float), ("w_tv", C.c_float),

@@ -132,7 +132,8 @@ def depth2normal(depth, mask, fov):
     dev = depth.device
     H, W = depth.shape[1:]
     opac = mask.to(torch.float32).reshape(1, 1, H, W).contiguous()
-    fv = torch.tensor([[float(fov[0]), float(fov[1])]], dtype=torch.float32, device=dev)
+    fv = torch.tensor([[math.tan(0.5 * float(fov[0])), math.tan(0.5 * float(fov[1]))]],
+                      dtype=torch.float32, device=dev)
     _, d2n = ops.postprocess(torch.zeros(1, 3, H, W, device=dev), depth.reshape(1, 1, H, W).contiguous(),
                              opac, fv)
     return d2n[0]
@@ -230,7 +231,7 @@ class GaussianRenderer:
                 rb.forward(check_overflow=True)
                 rgb, normal, depth, opacity, conf = rb.rgb, rb.normal, rb.depth, rb.opacity, rb.confidence
                 imp, cnt, radii = rb.importance, rb.count, rb.radii
-                normal_u, d2n = ops.postprocess(normal, depth, opacity, fovs.contiguous())
+                normal_u, d2n = ops.postprocess(normal, depth, opacity, tanfov.contiguous())
         return rgb, depth, normal_u, opacity, d2n, conf, imp, cnt, radii
 
     def render_view(self, i=0, require_grad=False, require_importance=False, front_only=False):

@@ -131,7 +131,8 @@ typedef struct AgsLossArgs {
     /* ground truth */
     const float* rgb_gt;           /* (B,3,H,W) */
     const float* depth_gt;         /* (B,1,H,W) */
-    const float* fov;              /* (B,2) radians (fov_x, fov_y) -- quirk Q2 pairing kept */
+    const float* tanfov;           /* (B,2) tan(fov_x/2), tan(fov_y/2): the same tensor the rasterizer takes.
+                                      depth2normal pairs fov_x with H and fov_y with W (quirk Q2 kept) */
     const int32_t* vis_count;      /* (H,W) sum over ALL frames of (opacity>1e-3) (quirk Q1), or NULL:
                                       computed from this call's B frames */
     /* outputs */
@@ -151,7 +152,7 @@ int ags_loss_forward_backward(const AgsLossArgs* args);
 /* forward-only post-processing of B rendered views (utils/operations.py:714-718):
  * normal_unit = normalize(normal)*(opacity>1e-2), d2n = depth2normal(depth, mask, fov). */
 int ags_postprocess(int32_t B, int32_t H, int32_t W, const float* normal, const float* depth,
-                    const float* opacity, const float* fov, float* normal_unit, float* d2n,
+                    const float* opacity, const float* tanfov, float* normal_unit, float* d2n,
                     void* stream);
 
 #define AGS_ADAM_GROUPS 5

@@ -68,7 +68,7 @@ def test_fused_loss_matches_oracle(B, H, W):
     ins = make_inputs(B, H, W, seed=B * 100 + H)
     fovs = torch.tensor([[1.0472, 0.8170]]).repeat(B, 1) + 0.01 * torch.arange(B)[:, None]
     total, perf, nu, d2n, g_rgb, g_n, g_d = oracle_loss(*ins, fovs)
-    res = ops.loss_forward_backward(*[t.to(dev).contiguous() for t in ins], fovs.to(dev))
+    res = ops.loss_forward_backward(*[t.to(dev).contiguous() for t in ins], (0.5 * fovs).tan().to(dev))
     torch.cuda.synchronize()
     checks = [("total", res.total().reshape(1), total.reshape(1)), ("perf", res.frame_perf(), perf),
               ("normal_unit", res.normal_unit, nu), ("d2n", res.d2n, d2n), ("d_rgb", res.d_rgb, g_rgb),
@@ -88,7 +88,7 @@ def test_fused_loss_vis_count_override_and_btotal():
     from active_gs_b200 import ops
     B, H, W = 4, 20, 28
     ins = [t.to(dev).contiguous() for t in make_inputs(B, H, W, seed=5)]
-    fovs = torch.tensor([[1.0, 0.8]]).repeat(B, 1).to(dev)
+    fovs = (0.5 * torch.tensor([[1.0, 0.8]])).tan().repeat(B, 1).to(dev)
     full = ops.loss_forward_backward(*ins, fovs)
     vis = (ins[3] > 1e-3).sum(0)[0].to(torch.int32).contiguous()
     parts = [ops.loss_forward_backward(*[t[s].contiguous() for t in ins], fovs[s].contiguous(),
