@@ -50,6 +50,13 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.rows, self.proc, self.idx = [], None, gpu_index
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def run(self):
         try:
@@ -57,7 +64,7 @@ class ClockSampler(threading.Thread):
                 ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                  "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
         except Exception:
             pass
 
@@ -65,7 +72,8 @@ class ClockSampler(threading.Thread):
         if self.proc is not None:
             self.proc.terminate()
         sm, reasons, mx = [], set(), None
-        for r in self.rows:
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 - 0.05 <= t <= (self.t1 or t) + 0.12]
+        for r in (inside or [r for _, r in self.rows[-3:]]):
             try:
                 sm.append(float(r[0])); mx = float(r[1])
                 for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
@@ -74,7 +82,7 @@ class ClockSampler(threading.Thread):
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(inside)}
 
 
 def build_workload(dev, rank, world, seed_base=1000 + CONFIG_IDX):
@@ -174,6 +182,9 @@ def run_ours(args, rank, world, local_rank):
         from active_gs_b200.distributed import FrameShard
         dist.init_process_group("nccl", device_id=dev)
         shard = FrameShard()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()                      # nvidia-smi takes a moment to start: launch it early
     state, start, frames, cfg, (H, W, N, T) = build_workload(dev, rank, world)
     B = B_PER_GPU
     P = H * W
@@ -191,15 +202,14 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.warmup):
         gm.train_step(ctx)
     barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
+    clocks.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         gm.train_step(ctx)
     e1.record()
     barrier()
+    clocks.mark_end()
     ms = e0.elapsed_time(e1)
     inst = int(np.mean([l[2] for l in ctx.log[-args.steps:]]))
     vis = int(np.mean([l[3] for l in ctx.log[-args.steps:]]))
@@ -310,7 +320,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
