@@ -52,6 +52,10 @@ static int render_forward_impl(const AgsRenderArgs* a, bool for_backward) {
     const size_t zero_bytes = (char*)w.inst_key - (char*)w.tile_count;
     AGS_CHECK_CUDA(cudaMemsetAsync(w.tile_count, 0, zero_bytes, st));
     AGS_CHECK_CUDA(cudaMemsetAsync(a->stats, 0, AGS_NUM_STATS * sizeof(int32_t), st));
+    if (a->N > 0) {   // importance / count are all-zero unless config[3]; optional outputs
+        if (a->importance) AGS_CHECK_CUDA(cudaMemsetAsync(a->importance, 0, (size_t)a->B * a->N * 4, st));
+        if (a->count) AGS_CHECK_CUDA(cudaMemsetAsync(a->count, 0, (size_t)a->B * a->N * 4, st));
+    }
     if ((rc = ags_launch_project_fwd(*a, w, for_backward))) return rc;
     if ((rc = ags_launch_binning(*a, w))) return rc;
     if ((rc = ags_launch_composite_fwd(*a, w))) return rc;
@@ -71,6 +75,10 @@ extern "C" int ags_render_stage(const AgsRenderArgs* a, const AgsRenderGradArgs*
             const size_t zero_bytes = (char*)w.inst_key - (char*)w.tile_count;
             AGS_CHECK_CUDA(cudaMemsetAsync(w.tile_count, 0, zero_bytes, st));
             AGS_CHECK_CUDA(cudaMemsetAsync(a->stats, 0, AGS_NUM_STATS * sizeof(int32_t), st));
+            if (a->N > 0) {
+                if (a->importance) AGS_CHECK_CUDA(cudaMemsetAsync(a->importance, 0, (size_t)a->B * a->N * 4, st));
+                if (a->count) AGS_CHECK_CUDA(cudaMemsetAsync(a->count, 0, (size_t)a->B * a->N * 4, st));
+            }
             return 0;
         }
         case AGS_STAGE_PROJECT_FWD: return ags_launch_project_fwd(*a, w, true);

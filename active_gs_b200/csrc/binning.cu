@@ -55,28 +55,30 @@ alloc_kernel(AgsWorkspace w, int n_tiles_total, int inst_cap, int32_t* stats) {
 
 __global__ void __launch_bounds__(256)
 scatter_kernel(AgsRenderArgs a, AgsWorkspace w) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int v = blockIdx.y;
     const int total = w.counters[0];
     if (total > a.inst_cap) {
-        if (i == 0 && v == 0) a.stats[AGS_STAT_OVERFLOW] = 1;
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.stats[AGS_STAT_OVERFLOW] = 1;
         return;
     }
-    if (i >= a.N) return;
-    const size_t idx = (size_t)v * a.N + i;
-    const uint2 r = w.rect[idx];
-    const int minx = r.x & 0xffff, maxx = r.x >> 16, miny = r.y & 0xffff, maxy = r.y >> 16;
-    if (maxx <= minx || maxy <= miny) return;
+    const int nvis = w.counters[1];
     const int tiles_x = (a.W + TILE - 1) / TILE, tiles_y = (a.H + TILE - 1) / TILE;
-    const size_t tbase = (size_t)v * tiles_x * tiles_y;
-    const float depth = w.feat0[idx].w;
-    const uint64_t key = ((uint64_t)__float_as_uint(depth) << 32) | (uint32_t)i;
-    for (int ty = miny; ty < maxy; ++ty)
-        for (int tx = minx; tx < maxx; ++tx) {
-            const size_t t = tbase + (size_t)ty * tiles_x + tx;
-            const int slot = w.tile_offset[t] + atomicAdd(w.tile_fill + t, 1);
-            w.inst_key[slot] = key;
-        }
+    const int stride = gridDim.x * blockDim.x;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nvis; e += stride) {
+        const size_t idx = (size_t)w.vis_list[e];
+        const int v = (int)(idx / a.N);
+        const uint32_t i = (uint32_t)(idx - (size_t)v * a.N);
+        const uint2 r = w.rect[idx];
+        const int minx = r.x & 0xffff, maxx = r.x >> 16, miny = r.y & 0xffff, maxy = r.y >> 16;
+        const size_t tbase = (size_t)v * tiles_x * tiles_y;
+        const float depth = w.feat0[idx].w;
+        const uint64_t key = ((uint64_t)__float_as_uint(depth) << 32) | i;
+        for (int ty = miny; ty < maxy; ++ty)
+            for (int tx = minx; tx < maxx; ++tx) {
+                const size_t t = tbase + (size_t)ty * tiles_x + tx;
+                const int slot = w.tile_offset[t] + atomicAdd(w.tile_fill + t, 1);
+                w.inst_key[slot] = key;
+            }
+    }
 }
 
 __device__ __forceinline__ void bitonic_smem(uint64_t* s, int m) {
@@ -159,8 +161,9 @@ int ags_launch_binning(const AgsRenderArgs& a, const AgsWorkspace& w) {
     alloc_kernel<<<(nt + 255) / 256, 256, 0, st>>>(w, nt, a.inst_cap, a.stats);
     AGS_CHECK_CUDA(cudaGetLastError());
     if (a.N > 0) {
-        dim3 grid((a.N + 255) / 256, a.B);
-        scatter_kernel<<<grid, 256, 0, st>>>(a, w);
+        long long blocks = ((long long)a.N * a.B + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        scatter_kernel<<<(int)blocks, 256, 0, st>>>(a, w);
         AGS_CHECK_CUDA(cudaGetLastError());
     }
     tile_sort_kernel<<<nt, SORT_THREADS, 0, st>>>(w, a.inst_cap);

@@ -11,13 +11,19 @@
 // splats at a time against its block (one ballot) and walks only the overlapping ones in depth
 // order (shared-memory broadcast reads) -- the skipped (warp, splat) pairs cost no evaluation at all.  The backward walks the SAME front-to-back order (no 1/(1-alpha) recurrences:
 // the "remaining" sum is total - prefix, computed from the saved forward outputs), reduces the 15
-// per-Gaussian partial gradients across the warp with a multi-value butterfly (16 shuffles instead
-// of 75) and issues one 16-lane vector RED per (warp, Gaussian) into a 64 B gradient record.
+// per-Gaussian partial gradients across the warp through a shared-memory transposition (36
+// instructions instead of 150 for a plain shuffle tree) and issues one 15-lane vector RED per
+// (warp, Gaussian) into a 64 B gradient record.
 #include "ags_common.cuh"
 
 namespace {
 
 constexpr int BATCH = 256;
+
+// one staged splat in shared memory: 80 B, read with 128-bit broadcast loads at immediate offsets
+struct __align__(16) SplatRec {
+    float4 g0, g1, f0, f1, bb;
+};
 
 struct SplatEval {
     float dx, dy, power, alpha;
@@ -69,7 +75,7 @@ __device__ __forceinline__ bool bbox_hits(const float4 bb, const WarpBlock& b) {
 // K4 ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
-    __shared__ float4 s_g0[BATCH], s_g1[BATCH], s_f0[BATCH], s_f1[BATCH], s_bb[BATCH];
+    __shared__ SplatRec s_rec[BATCH];
     __shared__ int s_id[BATCH];
     const int v = blockIdx.z;
     const int tiles_x = gridDim.x, tiles_y = gridDim.y;
@@ -104,28 +110,30 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
             const size_t idx = vN + id;
             const float4 g0 = ldg4(w.geom0 + idx), g1 = ldg4(w.geom1 + idx);
             s_id[tid] = id;
-            s_g0[tid] = g0;
-            s_g1[tid] = g1;
-            s_f0[tid] = ldg4(w.feat0 + idx);
-            s_f1[tid] = ldg4(w.feat1 + idx);
-            s_bb[tid] = splat_bbox(g0, g1);
+            SplatRec& r = s_rec[tid];
+            r.g0 = g0;
+            r.g1 = g1;
+            r.f0 = ldg4(w.feat0 + idx);
+            r.f1 = ldg4(w.feat1 + idx);
+            r.bb = splat_bbox(g0, g1);
         }
         __syncthreads();
         const int cnt = min(BATCH, n - base);
         for (int c = 0; c < cnt && !warp_done; c += 32) {
             const int jj = c + lane;
-            unsigned mask = __ballot_sync(0xffffffffu, jj < cnt && bbox_hits(s_bb[jj], wb));
+            unsigned mask = __ballot_sync(0xffffffffu, jj < cnt && bbox_hits(s_rec[jj].bb, wb));
             while (mask) {
                 const int k = c + __ffs(mask) - 1;
                 mask &= mask - 1;
                 if (done) continue;
-                const float4 g0 = s_g0[k], g1 = s_g1[k];
+                const SplatRec& rec = s_rec[k];
+                const float4 g0 = rec.g0, g1 = rec.g1;
                 const SplatEval e = eval_alpha(g0, g1, pxf, pyf);
                 if (e.skip) continue;
                 const float test_T = T * (1.f - e.alpha);
                 if (test_T < AGS_T_EPS) { done = true; continue; }
                 const float wgt = e.alpha * T;
-                const float4 f0 = s_f0[k], f1 = s_f1[k];
+                const float4 f0 = rec.f0, f1 = rec.f1;
                 C0 += wgt * f0.x; C1 += wgt * f0.y; C2 += wgt * f0.z;
                 D += wgt * (f0.w - g1.z * e.dx - g1.w * e.dy);
                 N0 += wgt * f1.x; N1 += wgt * f1.y; N2 += wgt * f1.z;
@@ -156,55 +164,36 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
 }
 
 // K5 ---------------------------------------------------------------------------------------------
-// multi-value butterfly: v[0..15] per lane -> lane L holds sum over the warp of v[L>>1]
-__device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
-    const unsigned full = 0xffffffffu;
-    float a8[8];
-    {
-        const bool up = (lane & 16) != 0;
+// Warp reduction of 15 values per lane: lane L ends up with the warp-wide sum of value L>>1.
+// Transposition through a per-warp shared buffer: every lane stores its 15 partials (conflict-free,
+// row = value, column = lane), lane L then loads the 16 partials of value L>>1 that belong to the
+// half-warp (L&1) with four 128-bit loads and one shuffle joins the halves.  36 instructions per
+// (warp, splat) instead of 63 for the register butterfly (31 FSEL + 16 SHFL + 16 FADD).
+// Row stride 36 floats keeps the 128-bit loads of a quarter-warp on distinct banks.
+constexpr int RED_STRIDE = 36;
+
+__device__ __forceinline__ float warp_reduce15(const float (&v)[15], float* buf, int lane) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float send = up ? v[k] : v[k + 8];
-            const float keep = up ? v[k + 8] : v[k];
-            a8[k] = keep + __shfl_xor_sync(full, send, 16);
-        }
+    for (int q = 0; q < 15; ++q) buf[q * RED_STRIDE + lane] = v[q];
+    __syncwarp();
+    float r = 0.f;
+    if (lane < 30) {
+        const float4* src = reinterpret_cast<const float4*>(buf + (lane >> 1) * RED_STRIDE + (lane & 1) * 16);
+        const float4 x0 = src[0], x1 = src[1], x2 = src[2], x3 = src[3];
+        r = ((x0.x + x0.y) + (x0.z + x0.w)) + ((x1.x + x1.y) + (x1.z + x1.w))
+          + ((x2.x + x2.y) + (x2.z + x2.w)) + ((x3.x + x3.y) + (x3.z + x3.w));
     }
-    float a4[4];
-    {
-        const bool up = (lane & 8) != 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float send = up ? a8[k] : a8[k + 4];
-            const float keep = up ? a8[k + 4] : a8[k];
-            a4[k] = keep + __shfl_xor_sync(full, send, 8);
-        }
-    }
-    float a2[2];
-    {
-        const bool up = (lane & 4) != 0;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const float send = up ? a4[k] : a4[k + 2];
-            const float keep = up ? a4[k + 2] : a4[k];
-            a2[k] = keep + __shfl_xor_sync(full, send, 4);
-        }
-    }
-    float a1;
-    {
-        const bool up = (lane & 2) != 0;
-        const float send = up ? a2[0] : a2[1];
-        const float keep = up ? a2[1] : a2[0];
-        a1 = keep + __shfl_xor_sync(full, send, 2);
-    }
-    a1 += __shfl_xor_sync(full, a1, 1);
-    return a1;
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    __syncwarp();
+    return r;
 }
 
 __global__ void __launch_bounds__(256)
 composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
-    __shared__ float4 s_g0[BATCH], s_g1[BATCH], s_f0[BATCH], s_f1[BATCH], s_bb[BATCH];
+    __shared__ SplatRec s_rec[BATCH];
     __shared__ int s_id[BATCH];
     __shared__ int s_max_last;
+    __shared__ __align__(16) float s_red[8][15 * RED_STRIDE];   // per-warp transposition buffer
     const int v = blockIdx.z;
     const int tiles_x = gridDim.x, tiles_y = gridDim.y;
     const int tile = blockIdx.y * tiles_x + blockIdx.x;
@@ -264,36 +253,38 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
             const size_t idx = vN + id;
             const float4 g0 = ldg4(w.geom0 + idx), g1 = ldg4(w.geom1 + idx);
             s_id[tid] = id;
-            s_g0[tid] = g0;
-            s_g1[tid] = g1;
-            s_f0[tid] = ldg4(w.feat0 + idx);
-            s_f1[tid] = ldg4(w.feat1 + idx);
-            s_bb[tid] = splat_bbox(g0, g1);
+            SplatRec& r = s_rec[tid];
+            r.g0 = g0;
+            r.g1 = g1;
+            r.f0 = ldg4(w.feat0 + idx);
+            r.f1 = ldg4(w.feat1 + idx);
+            r.bb = splat_bbox(g0, g1);
         }
         __syncthreads();
         const int cnt = min(BATCH, min(n_eff, warp_last) - base);   // nothing beyond the warp's last contributor
         for (int c = 0; c < cnt; c += 32) {
             const int jj = c + lane;
-            unsigned mask = __ballot_sync(0xffffffffu, jj < cnt && bbox_hits(s_bb[jj], wb));
+            unsigned mask = __ballot_sync(0xffffffffu, jj < cnt && bbox_hits(s_rec[jj].bb, wb));
             while (mask) {
                 const int k = c + __ffs(mask) - 1;
                 mask &= mask - 1;
-                const float4 g0 = s_g0[k], g1 = s_g1[k];
+                const SplatRec& rec = s_rec[k];
+                const float4 g0 = rec.g0, g1 = rec.g1;
                 const SplatEval e = eval_alpha(g0, g1, pxf, pyf);
                 const bool active = (base + k < my_last) && !e.skip;
                 if (__ballot_sync(0xffffffffu, active) == 0u) continue;
-                float val[16];
+                float val[15];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) val[q] = 0.f;
+                for (int q = 0; q < 15; ++q) val[q] = 0.f;
                 if (active) {
-                    const float4 f0 = s_f0[k], f1 = s_f1[k];
+                    const float4 f0 = rec.f0, f1 = rec.f1;
                     const float wgt = e.alpha * T;
                     const float one_m = 1.f - e.alpha;
                     const float dpix = f0.w - g1.z * e.dx - g1.w * e.dy;
                     const float sdot = gC0 * f0.x + gC1 * f0.y + gC2 * f0.z + gN0 * f1.x + gN1 * f1.y + gN2 * f1.z
                                      + gD * dpix + gCf * f1.w;
                     rem -= wgt * sdot;
-                    const float dalpha = T * sdot - rem / one_m;
+                    const float dalpha = T * sdot - __fdividef(rem, one_m);   // one_m >= 0.01
                     T *= one_m;
                     // alpha = min(0.99, o*G): clamped -> no gradient
                     const float G = __expf(e.power);
@@ -312,7 +303,7 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
                     val[13] = -wgD * e.dx;                                          // d slope x
                     val[14] = -wgD * e.dy;                                          // d slope y
                 }
-                const float r = butterfly16(val, lane);
+                const float r = warp_reduce15(val, s_red[tid >> 5], lane);
                 if ((lane & 1) == 0 && lane < 30) atomicAdd(w.dsplat + (vN + s_id[k]) * 16 + (lane >> 1), r);
             }
         }

@@ -84,23 +84,24 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <int K>
 __device__ __forceinline__ void block_accumulate(float (&v)[K], float* const (&dst)[K]) {
     __shared__ float sm[K][8];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const float s = warp_sum(v[k]);
         if (lane == 0) sm[k][wid] = s;
     }
     __syncthreads();
-    if (threadIdx.x < K) {
+    if (tid < K) {
         float s = 0.f;
-        const int nw = (blockDim.x + 31) >> 5;
-        for (int w = 0; w < nw; ++w) s += sm[threadIdx.x][w];
-        if (s != 0.f) atomicAdd(dst[threadIdx.x], s);
+        const int nw = (blockDim.x * blockDim.y + 31) >> 5;
+        for (int w = 0; w < nw; ++w) s += sm[tid][w];
+        if (s != 0.f) atomicAdd(dst[tid], s);
     }
     __syncthreads();
 }
 
-__device__ __forceinline__ float vis_sum(const AgsLossArgs& a, size_t P, size_t p) {
+__device__ __forceinline__ float vis_sum(const AgsLossArgs& a, size_t P, int p) {
     if (a.vis_count) return (float)a.vis_count[p];
     float m = 0.f;
     for (int f = 0; f < a.B; ++f) m += (a.opacity[(size_t)f * P + p] > 1e-3f) ? 1.f : 0.f;
@@ -113,16 +114,16 @@ __global__ void __launch_bounds__(256)
 loss_pass_a(AgsLossArgs a) {
     const int H = a.H, W = a.W;
     const size_t P = (size_t)H * W;
-    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int f = blockIdx.y;
-    const bool in = p < P;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    const int f = blockIdx.z;
+    const bool in = (x < W) && (y < H);
+    const int p = y * W + x;                 // 32-bit pixel index (P < 2^31)
     const float Bt = (float)a.B_total;
     const float inv_rgb = 1.f / (Bt * 3.f * (float)P);
     const float inv_d = 1.f / (Bt * (float)P);
     const float inv_cons = 1.f / (Bt * Bt * (float)P);
     float fr_rgb = 0.f, fr_d = 0.f, acc_cons = 0.f;
     if (in) {
-        const int y = (int)(p / W), x = (int)(p % W);
         const float msum = vis_sum(a, P, p);
         const float* opac = a.opacity + (size_t)f * P;
         const float* depth = a.depth + (size_t)f * P;
@@ -206,21 +207,21 @@ __global__ void __launch_bounds__(256)
 loss_pass_b(AgsLossArgs a) {
     const int H = a.H, W = a.W;
     const size_t P = (size_t)H * W;
-    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int f = blockIdx.y;
-    const bool in = p < P;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    const int f = blockIdx.z;
+    const bool in = (x < W) && (y < H);
+    const int p = y * W + x;                 // 32-bit pixel index (P < 2^31)
     const float Bt = (float)a.B_total;
     const float inv_cons = 1.f / (Bt * Bt * (float)P);
     const float inv_tv = 1.f / (Bt * 4.f * (float)P);
     const float inv2s2 = 1.f / (2.f * 0.3f * 0.3f);
     float acc_tv = 0.f;
     if (in) {
-        const int y = (int)(p / W), x = (int)(p % W);
         const float msum = vis_sum(a, P, p);
         const float* depth = a.depth + (size_t)f * P;
         const float* dgt = a.depth_gt + (size_t)f * P;
         const float* nu_ = a.normal_unit + (size_t)f * 3 * P;
-        auto NU = [&](size_t q) { return f3(nu_[q], nu_[P + q], nu_[2 * P + q]); };
+        auto NU = [&](int q) { return f3(nu_[q], nu_[P + q], nu_[2 * P + q]); };
         const float dp = depth[p];
         const float md_p = (dgt[p] > 0.f) ? 1.f : 0.f;
         const float m2 = (a.opacity[(size_t)f * P + p] > 1e-2f) ? 1.f : 0.f;
@@ -320,10 +321,10 @@ extern "C" int ags_loss_forward_backward(const AgsLossArgs* a) {
     AGS_CHECK_CUDA(cudaMemsetAsync(a->loss_terms, 0, (4 + 2 * (size_t)a->B) * sizeof(float), st));
     const size_t P = (size_t)a->H * a->W;
     AGS_CHECK_CUDA(cudaMemsetAsync(a->d_depth, 0, (size_t)a->B * P * sizeof(float), st));
-    dim3 grid((unsigned)((P + 255) / 256), a->B);
-    loss_pass_a<<<grid, 256, 0, st>>>(*a);
+    dim3 grid((a->W + 31) / 32, (a->H + 7) / 8, a->B), block(32, 8);
+    loss_pass_a<<<grid, block, 0, st>>>(*a);
     AGS_CHECK_CUDA(cudaGetLastError());
-    loss_pass_b<<<grid, 256, 0, st>>>(*a);
+    loss_pass_b<<<grid, block, 0, st>>>(*a);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

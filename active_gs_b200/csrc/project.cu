@@ -3,8 +3,8 @@
 // Replaces the per-Gaussian stage of the native extension behind
 // /root/reference/utils/operations.py:701-713 and, in RAW mode, the activations of
 // /root/reference/mapping/gaussian_map.py:529-545 (fused here and in the backward).
-// One thread owns one Gaussian and loops over the B views of the batch: the rotation matrix and the
-// 3D covariance are view independent and are built once.
+// K1 runs one thread per (Gaussian, view) pair with a conservative early cull; K6 one thread per
+// visible pair (compact list).
 //
 // HBM roofline: K1 reads 60 B/Gaussian and writes 72+8 B per (view, Gaussian); K6 reads 64 B grad
 // record + 56 B params per visible (view, Gaussian) and writes 56 B/Gaussian. Pure streaming.
@@ -172,72 +172,121 @@ __device__ __forceinline__ void project_view(ViewProj& o, const GaussAct& g, con
 }
 
 // K1 ---------------------------------------------------------------------------------------------
+// One thread per (Gaussian, view) pair.  Most pairs are outside the frustum (C2: ~89 %), so the pair
+// is first tested against a CONSERVATIVE screen-space radius bound that needs only the mean and the
+// scales:  a,c <= s_max^2 (f/t_z)^2 (1 + lim^2) + 0.3,  lambda_1 <= a + c + sqrt(0.1)  =>  R_b.  A pair
+// whose tile rect is empty even with R_b cannot be visible; everything else takes the exact path.
+// Visible pairs are appended to a compact list that drives the scatter and K6.
 __global__ void __launch_bounds__(128)
 project_fwd_kernel(AgsRenderArgs a, AgsWorkspace w, int for_backward) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.N) return;
-    GaussAct g;
-    activate(g, a, i);
-    const float cr = __ldg(a.colors + 3 * i), cg = __ldg(a.colors + 3 * i + 1), cb = __ldg(a.colors + 3 * i + 2);
-    const float conf = a.confidences ? __ldg(a.confidences + i) : 0.f;
+    const int v = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    bool valid = false;
+    const size_t idx = (size_t)v * a.N + (i < a.N ? i : 0);
     const int tiles_x = (a.W + TILE - 1) / TILE, tiles_y = (a.H + TILE - 1) / TILE;
-    const int tiles = tiles_x * tiles_y;
-    int nvis = 0;
-    for (int v = 0; v < a.B; ++v) {
+    ViewProj p;
+    if (i < a.N) {
         Cam cam;
         load_cam(cam, a.viewmatrix, a.projmatrix, a.tanfov, v);
-        ViewProj p;
-        project_view(p, g, cam, a.H, a.W, a.front_only != 0);
-        const size_t idx = (size_t)v * a.N + i;
-        a.radii[idx] = p.radius;
-        if (a.importance) a.importance[idx] = 0.f;
-        if (a.count) a.count[idx] = 0;
-        if (!p.valid) {
-            w.rect[idx] = make_uint2(0u, 0u);
-            continue;
+        const float mx = __ldg(a.means3D + 3 * i), my = __ldg(a.means3D + 3 * i + 1), mz = __ldg(a.means3D + 3 * i + 2);
+        const float* V = cam.V;
+        const float* M = cam.M;
+        const float tz = mx * V[2] + my * V[6] + mz * V[10] + V[14];
+        bool maybe = tz > AGS_NEAR_CULL;
+        if (maybe) {
+            float smax;
+            if (a.param_mode == AGS_PARAMS_RAW) {
+                smax = a.scale_max * a.scale_modifier;
+            } else {
+                smax = fmaxf(fmaxf(fabsf(__ldg(a.scales + 3 * i)), fabsf(__ldg(a.scales + 3 * i + 1))),
+                             fabsf(__ldg(a.scales + 3 * i + 2))) * a.scale_modifier;
+            }
+            const float homx = mx * M[0] + my * M[4] + mz * M[8] + M[12];
+            const float homy = mx * M[1] + my * M[5] + mz * M[9] + M[13];
+            const float homw = mx * M[3] + my * M[7] + mz * M[11] + M[15];
+            const float iw = 1.f / (homw + 1e-7f);
+            const float xg = ((homx * iw + 1.f) * a.W - 1.f) * 0.5f, yg = ((homy * iw + 1.f) * a.H - 1.f) * 0.5f;
+            const float fx = a.W / (2.f * cam.tanx), fy = a.H / (2.f * cam.tany);
+            const float lx = 1.3f * cam.tanx, ly = 1.3f * cam.tany;
+            const float sz = smax / tz;
+            const float ab = sz * sz * fx * fx * (1.f + lx * lx) + AGS_LOWPASS;
+            const float cb = sz * sz * fy * fy * (1.f + ly * ly) + AGS_LOWPASS;
+            const float Rb = ceilf(3.f * sqrtf(ab + cb + 0.3163f)) * 1.001f + 2.f;
+            if (xg == xg && yg == yg && fabsf(xg) < 1e9f && fabsf(yg) < 1e9f && Rb < 1e9f) {
+                const int minx = min(tiles_x, max(0, (int)((xg - Rb) / TILE)));
+                const int miny = min(tiles_y, max(0, (int)((yg - Rb) / TILE)));
+                const int maxx = min(tiles_x, max(0, (int)((xg + Rb + TILE - 1) / TILE)));
+                const int maxy = min(tiles_y, max(0, (int)((yg + Rb + TILE - 1) / TILE)));
+                maybe = (maxx - minx) * (maxy - miny) > 0;
+            }
         }
-        ++nvis;
-        w.geom0[idx] = make_float4(p.xg, p.yg, p.ca, p.cb);
-        w.geom1[idx] = make_float4(p.cc, g.o, p.sx, p.sy);
-        w.feat0[idx] = make_float4(cr, cg, cb, p.t[2]);
-        w.feat1[idx] = make_float4(p.nv[0], p.nv[1], p.nv[2], conf);
-        w.rect[idx] = make_uint2((unsigned)p.minx | ((unsigned)p.maxx << 16),
-                                 (unsigned)p.miny | ((unsigned)p.maxy << 16));
-        if (for_backward) {
-            float4* d = reinterpret_cast<float4*>(w.dsplat + idx * 16);
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            d[0] = z; d[1] = z; d[2] = z; d[3] = z;
+        if (maybe) {
+            GaussAct g;
+            activate(g, a, i);
+            project_view(p, g, cam, a.H, a.W, a.front_only != 0);
+            valid = p.valid;
+            if (valid) {
+                const float conf = a.confidences ? __ldg(a.confidences + i) : 0.f;
+                w.geom0[idx] = make_float4(p.xg, p.yg, p.ca, p.cb);
+                w.geom1[idx] = make_float4(p.cc, g.o, p.sx, p.sy);
+                w.feat0[idx] = make_float4(__ldg(a.colors + 3 * i), __ldg(a.colors + 3 * i + 1),
+                                           __ldg(a.colors + 3 * i + 2), p.t[2]);
+                w.feat1[idx] = make_float4(p.nv[0], p.nv[1], p.nv[2], conf);
+                w.rect[idx] = make_uint2((unsigned)p.minx | ((unsigned)p.maxx << 16),
+                                         (unsigned)p.miny | ((unsigned)p.maxy << 16));
+                if (for_backward) {
+                    float4* d = reinterpret_cast<float4*>(w.dsplat + idx * 16);
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    d[0] = z; d[1] = z; d[2] = z; d[3] = z;
+                }
+                int32_t* tc = w.tile_count + (size_t)v * tiles_x * tiles_y;
+                for (int ty = p.miny; ty < p.maxy; ++ty)
+                    for (int tx = p.minx; tx < p.maxx; ++tx) atomicAdd(tc + ty * tiles_x + tx, 1);
+            }
         }
-        int32_t* tc = w.tile_count + (size_t)v * tiles;
-        for (int ty = p.miny; ty < p.maxy; ++ty)
-            for (int tx = p.minx; tx < p.maxx; ++tx) atomicAdd(tc + ty * tiles_x + tx, 1);
+        a.radii[idx] = valid ? p.radius : 0;
     }
-    // visible-count statistic, one atomic per warp
-    unsigned m = __activemask();
-    for (int off = 16; off > 0; off >>= 1) nvis += __shfl_down_sync(m, nvis, off);
-    if ((threadIdx.x & 31) == 0 && nvis) atomicAdd(a.stats + AGS_STAT_VISIBLE, nvis);
+    // append visible pairs to the compact list (one atomic per warp)
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    if (m) {
+        int base = 0;
+        const int leader = __ffs(m) - 1;
+        if (lane == leader) base = atomicAdd(w.counters + 1, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (valid) w.vis_list[base + __popc(m & ((1u << lane) - 1u))] = (int)idx;
+        if (lane == leader) atomicAdd(a.stats + AGS_STAT_VISIBLE, __popc(m));
+    }
 }
 
 // K6 ---------------------------------------------------------------------------------------------
+// One thread per VISIBLE (view, Gaussian) pair (compact list from K1).  The whole chain down to the
+// raw parameters is linear in the incoming gradient record, so every pair finishes its own
+// contribution and adds 14 floats to the (pre-zeroed) parameter gradients with atomics; a Gaussian
+// is visible in about one of the B views, so collisions are rare.
+__global__ void __launch_bounds__(128)
+zero_grads_kernel(AgsRenderGradArgs gr, int N, int B) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)N * 4; e += stride) {
+        if (e < (size_t)N * 3) { gr.d_means3D[e] = 0.f; gr.d_scales[e] = 0.f; gr.d_colors[e] = 0.f; }
+        gr.d_rotations[e] = 0.f;
+        if (e < (size_t)N) gr.d_opacities[e] = 0.f;
+    }
+    if (gr.d_means2D)
+        for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)B * N * 3; e += stride)
+            gr.d_means2D[e] = 0.f;
+}
+
 __global__ void __launch_bounds__(128)
 project_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.N) return;
-    GaussAct g;
-    activate(g, a, i);
-    float dp[3] = {0.f, 0.f, 0.f};
-    float Gs[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // symmetric (G + G^T) of dL/dSigma: xx xy xz yy yz zz
-    float dnw[3] = {0.f, 0.f, 0.f};
-    float d_o = 0.f, dcol[3] = {0.f, 0.f, 0.f};
-    for (int v = 0; v < a.B; ++v) {
-        const size_t idx = (size_t)v * a.N + i;
-        const bool vis = a.radii[idx] > 0;
-        if (gr.d_means2D) {
-            float gx = 0.f, gy = 0.f;
-            if (vis) { gx = w.dsplat[idx * 16 + 0]; gy = w.dsplat[idx * 16 + 1]; }
-            gr.d_means2D[idx * 3 + 0] = gx; gr.d_means2D[idx * 3 + 1] = gy; gr.d_means2D[idx * 3 + 2] = 0.f;
-        }
-        if (!vis) continue;
+    const int nvis = w.counters[1];
+    const int stride = gridDim.x * blockDim.x;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nvis; e += stride) {
+        const size_t idx = (size_t)w.vis_list[e];
+        const int v = (int)(idx / a.N);
+        const int i = (int)(idx - (size_t)v * a.N);
+        GaussAct g;
+        activate(g, a, i);
         Cam cam;
         load_cam(cam, a.viewmatrix, a.projmatrix, a.tanfov, v);
         ViewProj p;
@@ -246,22 +295,23 @@ project_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
         const float4 d0 = dr[0], d1 = dr[1], d2 = dr[2], d3 = dr[3];
         const float dxg = d0.x, dyg = d0.y, dca = d0.z, dcb = d0.w;
         const float dcc = d1.x;
-        d_o += d1.y;
-        dcol[0] += d1.z; dcol[1] += d1.w; dcol[2] += d2.x;
+        const float d_o = d1.y;
+        const float dcol[3] = {d1.z, d1.w, d2.x};
         float dnv[3] = {d2.y, d2.z, d2.w};
         const float dz = d3.x, dsx = d3.y, dsy = d3.z;
+        if (gr.d_means2D) { gr.d_means2D[idx * 3 + 0] = dxg; gr.d_means2D[idx * 3 + 1] = dyg; }
         const float* V = cam.V;
         const float* M = cam.M;
         const float tz = p.t[2];
-        float dt[3] = {0.f, 0.f, 0.f};
+        float dp[3], dt[3] = {0.f, 0.f, 0.f};
         // ---- screen position -> mean
         {
             const float dndcx = dxg * 0.5f * a.W, dndcy = dyg * 0.5f * a.H;
             const float dhx = dndcx * p.inv_w, dhy = dndcy * p.inv_w;
             const float dhw = -(p.ndcx * dndcx + p.ndcy * dndcy) * p.inv_w;
-            dp[0] += M[0] * dhx + M[1] * dhy + M[3] * dhw;
-            dp[1] += M[4] * dhx + M[5] * dhy + M[7] * dhw;
-            dp[2] += M[8] * dhx + M[9] * dhy + M[11] * dhw;
+            dp[0] = M[0] * dhx + M[1] * dhy + M[3] * dhw;
+            dp[1] = M[4] * dhx + M[5] * dhy + M[7] * dhw;
+            dp[2] = M[8] * dhx + M[9] * dhy + M[11] * dhw;
         }
         // ---- conic -> cov2
         float da, db, dc;
@@ -271,15 +321,16 @@ project_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
             db = (2.f * p.b * p.c * dca - (p.a * p.c + p.b * p.b) * dcb + 2.f * p.a * p.b * dcc) * id2;
             dc = (-p.b * p.b * dca + p.a * p.b * dcb - p.a * p.a * dcc) * id2;
         }
-        // ---- cov2 = T Sigma T^T
+        // ---- cov2 = T Sigma T^T ; Gs = symmetric (G + G^T) of dL/dSigma: xx xy xz yy yz zz
+        float Gs[6];
         {
             const float* T0 = p.T0; const float* T1 = p.T1;
-            Gs[0] += 2.f * da * T0[0] * T0[0] + 2.f * db * T0[0] * T1[0] + 2.f * dc * T1[0] * T1[0];
-            Gs[1] += 2.f * da * T0[0] * T0[1] + db * (T0[0] * T1[1] + T0[1] * T1[0]) + 2.f * dc * T1[0] * T1[1];
-            Gs[2] += 2.f * da * T0[0] * T0[2] + db * (T0[0] * T1[2] + T0[2] * T1[0]) + 2.f * dc * T1[0] * T1[2];
-            Gs[3] += 2.f * da * T0[1] * T0[1] + 2.f * db * T0[1] * T1[1] + 2.f * dc * T1[1] * T1[1];
-            Gs[4] += 2.f * da * T0[1] * T0[2] + db * (T0[1] * T1[2] + T0[2] * T1[1]) + 2.f * dc * T1[1] * T1[2];
-            Gs[5] += 2.f * da * T0[2] * T0[2] + 2.f * db * T0[2] * T1[2] + 2.f * dc * T1[2] * T1[2];
+            Gs[0] = 2.f * da * T0[0] * T0[0] + 2.f * db * T0[0] * T1[0] + 2.f * dc * T1[0] * T1[0];
+            Gs[1] = 2.f * da * T0[0] * T0[1] + db * (T0[0] * T1[1] + T0[1] * T1[0]) + 2.f * dc * T1[0] * T1[1];
+            Gs[2] = 2.f * da * T0[0] * T0[2] + db * (T0[0] * T1[2] + T0[2] * T1[0]) + 2.f * dc * T1[0] * T1[2];
+            Gs[3] = 2.f * da * T0[1] * T0[1] + 2.f * db * T0[1] * T1[1] + 2.f * dc * T1[1] * T1[1];
+            Gs[4] = 2.f * da * T0[1] * T0[2] + db * (T0[1] * T1[2] + T0[2] * T1[1]) + 2.f * dc * T1[1] * T1[2];
+            Gs[5] = 2.f * da * T0[2] * T0[2] + 2.f * db * T0[2] * T1[2] + 2.f * dc * T1[2] * T1[2];
             float dT0[3], dT1[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -304,6 +355,7 @@ project_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
             if (p.uy_free) { dt[1] += duy * itz; dt[2] += -duy * p.t[1] * itz2; }
         }
         // ---- depth + plane slopes + normal
+        float dnw[3];
         {
             dt[2] += dz;
             // sx = -tz*nv.x/(Dc*fx)
@@ -320,82 +372,67 @@ project_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
             // nv = sigma * Wr nw  -> dnw_k = sigma * sum_j V[4k+j] dnv_j
 #pragma unroll
             for (int k = 0; k < 3; ++k)
-                dnw[k] += p.sigma_n * (V[4 * k] * dnv[0] + V[4 * k + 1] * dnv[1] + V[4 * k + 2] * dnv[2]);
+                dnw[k] = p.sigma_n * (V[4 * k] * dnv[0] + V[4 * k + 1] * dnv[1] + V[4 * k + 2] * dnv[2]);
         }
         // ---- t = Wr p + tr
 #pragma unroll
         for (int k = 0; k < 3; ++k) dp[k] += V[4 * k] * dt[0] + V[4 * k + 1] * dt[1] + V[4 * k + 2] * dt[2];
-    }
-    // ---- Sigma = M3 M3^T, M3 = R diag(s):  dM3 = Gs * M3
-    const float* R = g.R;
-    float dR[9], ds[3];
-    {
-        float M3[9];
+        // ---- Sigma = M3 M3^T, M3 = R diag(s):  dM3 = Gs * M3
+        const float* R = g.R;
+        float dR[9], ds[3];
+        {
+            float M3[9];
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) M3[3 * r + k] = R[3 * r + k] * g.s[k];
-        float dM3[9];
+                for (int k = 0; k < 3; ++k) M3[3 * r + k] = R[3 * r + k] * g.s[k];
+            float dM3[9];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            float col[3] = {M3[k], M3[3 + k], M3[6 + k]}, o3[3];
-            sym_mul(Gs, col, o3);
-            dM3[k] = o3[0]; dM3[3 + k] = o3[1]; dM3[6 + k] = o3[2];
+            for (int k = 0; k < 3; ++k) {
+                float col[3] = {M3[k], M3[3 + k], M3[6 + k]}, o3[3];
+                sym_mul(Gs, col, o3);
+                dM3[k] = o3[0]; dM3[3 + k] = o3[1]; dM3[6 + k] = o3[2];
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                ds[k] = dM3[k] * R[k] + dM3[3 + k] * R[3 + k] + dM3[6 + k] * R[6 + k];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) dR[3 * r + k] = dM3[3 * r + k] * g.s[k];
+            }
+            dR[2] += dnw[0]; dR[5] += dnw[1]; dR[8] += dnw[2];
+        }
+        float dq[4];
+        {
+            const float r = g.q[0], x = g.q[1], y = g.q[2], z = g.q[3];
+            dq[0] = 2.f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]);
+            dq[1] = 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.f * x * dR[8]);
+            dq[2] = 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.f * y * dR[8]);
+            dq[3] = 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]);
+        }
+        float dsr[3], dqr[4], dor;
+        if (a.param_mode == AGS_PARAMS_RAW) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dsr[k] = g.s_pass[k] ? ds[k] * g.s[k] : 0.f;   // d/draw of clamp(sf*exp)
+            const float qd = g.q[0] * dq[0] + g.q[1] * dq[1] + g.q[2] * dq[2] + g.q[3] * dq[3];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dqr[k] = (dq[k] - g.q[k] * qd) / g.qn;
+            dor = d_o * g.o * (1.f - g.o);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dsr[k] = ds[k] * a.scale_modifier;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dqr[k] = dq[k];
+            dor = d_o;
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            ds[k] = dM3[k] * R[k] + dM3[3 + k] * R[3 + k] + dM3[6 + k] * R[6 + k];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) dR[3 * r + k] = dM3[3 * r + k] * g.s[k];
-        }
-        dR[2] += dnw[0]; dR[5] += dnw[1]; dR[8] += dnw[2];
-    }
-    float dq[4];
-    {
-        const float r = g.q[0], x = g.q[1], y = g.q[2], z = g.q[3];
-        dq[0] = 2.f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]);
-        dq[1] = 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.f * x * dR[8]);
-        dq[2] = 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.f * y * dR[8]);
-        dq[3] = 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]);
-    }
-    float dsr[3], dqr[4], dor;
-    if (a.param_mode == AGS_PARAMS_RAW) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            // s = clamp(sf*exp(raw)) * modifier ; d/draw = s (when the clamp passes)
-            dsr[k] = g.s_pass[k] ? ds[k] * g.s[k] : 0.f;
-        }
-        const float qd = g.q[0] * dq[0] + g.q[1] * dq[1] + g.q[2] * dq[2] + g.q[3] * dq[3];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) dqr[k] = (dq[k] - g.q[k] * qd) / g.qn;
-        dor = d_o * g.o * (1.f - g.o);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) dsr[k] = ds[k] * a.scale_modifier;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) dqr[k] = dq[k];
-        dor = d_o;
-    }
-    if (gr.accumulate) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            gr.d_means3D[3 * i + k] += dp[k];
-            gr.d_scales[3 * i + k] += dsr[k];
-            gr.d_colors[3 * i + k] += dcol[k];
+            atomicAdd(gr.d_means3D + 3 * i + k, dp[k]);
+            if (dsr[k] != 0.f) atomicAdd(gr.d_scales + 3 * i + k, dsr[k]);
+            atomicAdd(gr.d_colors + 3 * i + k, dcol[k]);
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) gr.d_rotations[4 * i + k] += dqr[k];
-        gr.d_opacities[i] += dor;
-    } else {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            gr.d_means3D[3 * i + k] = dp[k];
-            gr.d_scales[3 * i + k] = dsr[k];
-            gr.d_colors[3 * i + k] = dcol[k];
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) gr.d_rotations[4 * i + k] = dqr[k];
-        gr.d_opacities[i] = dor;
+        for (int k = 0; k < 4; ++k) atomicAdd(gr.d_rotations + 4 * i + k, dqr[k]);
+        atomicAdd(gr.d_opacities + i, dor);
     }
 }
 
@@ -404,8 +441,8 @@ project_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
 int ags_launch_project_fwd(const AgsRenderArgs& a, const AgsWorkspace& w, bool for_backward) {
     if (a.N == 0) return 0;
     const int threads = 128;
-    project_fwd_kernel<<<(a.N + threads - 1) / threads, threads, 0, (cudaStream_t)a.stream>>>(
-        a, w, for_backward ? 1 : 0);
+    dim3 grid((a.N + threads - 1) / threads, a.B);
+    project_fwd_kernel<<<grid, threads, 0, (cudaStream_t)a.stream>>>(a, w, for_backward ? 1 : 0);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -413,7 +450,12 @@ int ags_launch_project_fwd(const AgsRenderArgs& a, const AgsWorkspace& w, bool f
 int ags_launch_project_bwd(const AgsRenderArgs& a, const AgsRenderGradArgs& g, const AgsWorkspace& w) {
     if (a.N == 0) return 0;
     const int threads = 128;
-    project_bwd_kernel<<<(a.N + threads - 1) / threads, threads, 0, (cudaStream_t)a.stream>>>(a, g, w);
+    cudaStream_t st = (cudaStream_t)a.stream;
+    if (!g.accumulate) {
+        zero_grads_kernel<<<148 * 4, threads, 0, st>>>(g, a.N, a.B);
+        AGS_CHECK_CUDA(cudaGetLastError());
+    }
+    project_bwd_kernel<<<148 * 8, threads, 0, st>>>(a, g, w);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -45,6 +45,11 @@ class FrameShard:
             for g in grads:
                 dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
 
+    def all_gather_into_(self, out, local):
+        """out (world*n,) <- concatenation over ranks of local (n,), on the current stream"""
+        dist.all_gather_into_tensor(out, local, group=self.group)
+        return out
+
     def gather_perf(self, perf_local, ids):
         """per-frame performance of the whole batch, ordered like `ids` (host tensors)"""
         out = [torch.empty_like(perf_local) for _ in range(self.world)]

@@ -87,7 +87,7 @@ class _TrainEngine:
         self.rb = RenderBatch(gm._means, gm._scales, gm._rotations, gm._opacities,
                               gm._harmonics.reshape(N, 3), self.conf, self.view, self.proj, self.tanfov,
                               self.bg, H, W, param_mode=L.PARAMS_RAW, scale_factor=gm.scale_factor,
-                              scale_max=0.05, inst_cap=cap)
+                              scale_max=0.05, inst_cap=cap, with_importance=False)
         # RenderBatch copies nothing for contiguous fp32 inputs, but make the aliasing explicit
         self.rb.inputs = [gm._means, gm._scales, gm._rotations, gm._opacities,
                           gm._harmonics.reshape(N, 3), self.conf]
@@ -95,7 +95,9 @@ class _TrainEngine:
         self.loss = None
         self.loss_out = None
         self.vis_count = torch.empty(H, W, device=dev, dtype=torch.int32) if dist_ctx else None
-        self.host = torch.empty(2 * B + 4, dtype=torch.float32).pin_memory()
+        W_ = dist_ctx.world if dist_ctx else 1
+        self.host = torch.empty(W_ * (2 * B + 4), dtype=torch.float32).pin_memory()
+        self.terms_all = torch.empty(W_ * (2 * B + 4), **o) if dist_ctx else None
         self.host_stats = torch.empty(L.AGS_NUM_STATS, dtype=torch.int32).pin_memory()
         self.event = torch.cuda.Event()
         self.fwd_args = self.rb._args()      # argument structs are built once: pointers never change
@@ -147,7 +149,13 @@ class _TrainEngine:
             rb.rgb, rb.normal, rb.depth, rb.opacity, self.rgb_gt, self.depth_gt, self.tanfov,
             B_total=self.B_total, vis_count=vis, out=self.loss_out)
         lo = self.loss_out
-        self.host.copy_(lo.terms, non_blocking=True)
+        if self.dist is not None:
+            # loss terms + per-frame performance of every rank, gathered on the stream before the
+            # backward is enqueued: the host waits for this small copy only
+            self.dist.all_gather_into_(self.terms_all, lo.terms)
+            self.host.copy_(self.terms_all, non_blocking=True)
+        else:
+            self.host.copy_(lo.terms, non_blocking=True)
         self.host_stats.copy_(rb.stats, non_blocking=True)
         self.event.record(torch.cuda.current_stream(self.dev))
         if self.grad_args is None:
@@ -171,9 +179,9 @@ class _TrainEngine:
         was just enqueued (the sampler needs them, mapping/utils.py:206-218)."""
         B = self.B
         self.event.synchronize()
-        h = self.host.clone()
-        terms = h[:4]
-        perf = h[4:4 + 2 * B:2] + h[5:4 + 2 * B:2]
+        h = self.host.clone().view(-1, 2 * B + 4)           # one row per rank
+        terms = h[:, :4].sum(0)                             # every rank's terms are already / B_total
+        perf = (h[:, 4::2] + h[:, 5::2]).reshape(-1)        # ordered like the sampled ids
         return terms, perf, self.host_stats.to(torch.int64)
 
 
@@ -261,8 +269,6 @@ class GaussianMap:
             eng.grow(int(stats[L.STAT_INSTANCES]))
         need = float(stats[L.STAT_INSTANCES]) / max(1, eng.N * ctx.B)
         self._cap_per_gaussian = max(self._cap_per_gaussian, 1.5 * need)
-        if self.dist is not None:
-            perf = self.dist.gather_perf(perf, ids)
         ctx.perf_host[torch.as_tensor(ids, dtype=torch.long)] = perf
         loss = float(terms[0] + 0.8 * terms[1] + 0.1 * terms[2] + 0.1 * terms[3])
         ctx.log.append((loss, perf.clone(), int(stats[L.STAT_INSTANCES]), int(stats[L.STAT_VISIBLE])))

@@ -44,7 +44,8 @@ class RenderBatch:
     def __init__(self, means3D, scales, rotations, opacities, colors, confidences, viewmatrix,
                  projmatrix, tanfov, bg, H, W, *, render_mask=None, scale_modifier=1.0,
                  weight_thres=0.03, require_importance=False, front_only=False,
-                 param_mode=L.PARAMS_ACTIVATED, scale_factor=0.01, scale_max=0.05, inst_cap=None):
+                 param_mode=L.PARAMS_ACTIVATED, scale_factor=0.01, scale_max=0.05, inst_cap=None,
+                 with_importance=True):
         lib = L.load()
         dev = means3D.device
         if dev.type != "cuda":
@@ -69,8 +70,10 @@ class RenderBatch:
         self.depth = torch.empty(B, 1, H, W, **o)
         self.opacity = torch.empty(B, 1, H, W, **o)
         self.confidence = torch.empty(B, 1, H, W, **o)
-        self.importance = torch.empty(B, N, **o)
-        self.count = torch.empty(B, N, device=dev, dtype=torch.int32)
+        # optional outputs (all-zero unless require_importance): the training engine skips them
+        with_importance = with_importance or require_importance
+        self.importance = torch.empty(B, N, **o) if with_importance else None
+        self.count = torch.empty(B, N, device=dev, dtype=torch.int32) if with_importance else None
         self.radii = torch.empty(B, N, device=dev, dtype=torch.int32)
         self.stats = torch.empty(L.AGS_NUM_STATS, device=dev, dtype=torch.int32)
         self.cfg = dict(param_mode=param_mode, require_importance=int(require_importance),

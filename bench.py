@@ -180,6 +180,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         from active_gs_b200.distributed import FrameShard
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout
         dist.init_process_group("nccl", device_id=dev)
         shard = FrameShard()
     clocks = ClockSampler(local_rank)

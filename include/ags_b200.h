@@ -81,8 +81,8 @@ typedef struct AgsRenderArgs {
     float* out_depth;              /* (B,1,H,W) opacity-normalised per-pixel plane depth */
     float* out_opacity;            /* (B,1,H,W) */
     float* out_confidence;         /* (B,1,H,W) */
-    float* importance;             /* (B,N) f32, zero unless require_importance */
-    int32_t* count;                /* (B,N) i32, zero unless require_importance */
+    float* importance;             /* (B,N) f32, zero unless require_importance; may be NULL if not required */
+    int32_t* count;                /* (B,N) i32, zero unless require_importance; may be NULL if not required */
     int32_t* radii;                /* (B,N) i32, 0 = culled */
     int32_t* stats;                /* (AGS_NUM_STATS) i32 */
     /* workspace (also carries everything the backward needs) */
