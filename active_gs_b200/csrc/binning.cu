@@ -19,6 +19,7 @@ namespace {
 
 constexpr int SORT_CHUNK = 4096;
 constexpr int SORT_THREADS = 256;
+constexpr int SORT_SMALL = 256;          // tiles up to this size are sorted by ONE warp
 
 __global__ void __launch_bounds__(256)
 alloc_kernel(AgsWorkspace w, int n_tiles_total, int inst_cap, int32_t* stats) {
@@ -61,6 +62,7 @@ scatter_kernel(AgsRenderArgs a, AgsWorkspace w) {
         return;
     }
     const int nvis = w.counters[1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.stats[AGS_STAT_VISIBLE] = nvis;
     const int tiles_x = (a.W + TILE - 1) / TILE, tiles_y = (a.H + TILE - 1) / TILE;
     const int stride = gridDim.x * blockDim.x;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nvis; e += stride) {
@@ -96,20 +98,50 @@ __device__ __forceinline__ void bitonic_smem(uint64_t* s, int m) {
     }
 }
 
+// Small tiles (the common case: ~80 instances): one WARP per tile, 8 tiles per CTA, bitonic network
+// in the warp's private slice of shared memory with __syncwarp only -- no CTA barriers.
+__global__ void __launch_bounds__(256)
+tile_sort_small_kernel(AgsWorkspace w, int n_tiles_total, int inst_cap) {
+    __shared__ uint64_t s_all[8][SORT_SMALL];
+    if (w.counters[0] > inst_cap) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int t = blockIdx.x * 8 + wid;
+    if (t >= n_tiles_total) return;
+    const int n = w.tile_count[t];
+    if (n == 0 || n > SORT_SMALL) return;
+    const int off = w.tile_offset[t];
+    const uint64_t* keys = w.inst_key + off;
+    int32_t* out = w.inst_sorted + off;
+    uint64_t* s = s_all[wid];
+    int m = 2;
+    while (m < n) m <<= 1;
+    for (int k = lane; k < m; k += 32) s[k] = (k < n) ? keys[k] : ~0ull;
+    __syncwarp();
+    for (int k = 2; k <= m; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int q = lane; q < (m >> 1); q += 32) {
+                const int lo = ((q & ~(j - 1)) << 1) | (q & (j - 1));
+                const int hi = lo | j;
+                const bool asc = ((lo & k) == 0);
+                const uint64_t x = s[lo], y = s[hi];
+                if ((x > y) == asc) { s[lo] = y; s[hi] = x; }
+            }
+            __syncwarp();
+        }
+    }
+    for (int k = lane; k < n; k += 32) out[k] = (int32_t)(s[k] & 0xffffffffu);
+}
+
 __global__ void __launch_bounds__(SORT_THREADS)
 tile_sort_kernel(AgsWorkspace w, int inst_cap) {
     __shared__ uint64_t s[SORT_CHUNK];
     if (w.counters[0] > inst_cap) return;
     const int t = blockIdx.x;
     const int n = w.tile_count[t];
-    if (n == 0) return;
+    if (n <= SORT_SMALL) return;             // handled by tile_sort_small_kernel
     const int off = w.tile_offset[t];
     uint64_t* keys = w.inst_key + off;
     int32_t* out = w.inst_sorted + off;
-    if (n == 1) {
-        if (threadIdx.x == 0) out[0] = (int32_t)(keys[0] & 0xffffffffu);
-        return;
-    }
     // phase 1: sort chunks of SORT_CHUNK in shared memory
     for (int cbase = 0; cbase < n; cbase += SORT_CHUNK) {
         const int cn = min(SORT_CHUNK, n - cbase);
@@ -166,6 +198,8 @@ int ags_launch_binning(const AgsRenderArgs& a, const AgsWorkspace& w) {
         scatter_kernel<<<(int)blocks, 256, 0, st>>>(a, w);
         AGS_CHECK_CUDA(cudaGetLastError());
     }
+    tile_sort_small_kernel<<<(nt + 7) / 8, 256, 0, st>>>(w, nt, a.inst_cap);
+    AGS_CHECK_CUDA(cudaGetLastError());
     tile_sort_kernel<<<nt, SORT_THREADS, 0, st>>>(w, a.inst_cap);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -9,11 +9,11 @@
 // and the autograd backward of all of it down to d rgb / d depth / d normal(raw).
 //
 // Two stencil passes, one thread per (pixel, frame):
-//   pass A: unit normal, d2n, rgb gradient, loss sums, and the depth gradient -- the L1 term plus the
-//           adjoint of depth2normal, which touches the pixel and its 4 neighbours and is SCATTERED
-//           with 5 float atomics (the gather form re-derives 4 neighbour stencils per pixel: 3x slower)
-//   pass B: normal gradient (consistency + gather of the TV terms, then through normalize*mask),
-//           TV loss sum
+//   pass A: unit normal, d2n, rgb gradient, loss sums, the pixel's own depth gradient (L1 term +
+//           its share of the depth2normal adjoint) and, as four planes, what it contributes to the
+//           depth gradients of its 4 neighbours
+//   pass B: depth gradient += gather of the neighbours' planes; normal gradient (consistency +
+//           gather of the TV terms, then through normalize*mask); TV loss sum
 // HBM roofline: reads 15 planes + writes 13 planes of B*H*W floats (+3 scratch planes twice).
 #include "ags_common.cuh"
 
@@ -108,10 +108,12 @@ __device__ __forceinline__ float vis_sum(const AgsLossArgs& a, size_t P, int p) 
     return m;
 }
 
-// pass A: one thread per (pixel, frame).  Writes normal_unit, d2n, d_rgb; scatters the depth
-// gradient (L1 term + adjoint of depth2normal, 6 atomics into the zero-initialised d_depth).
+// pass A: one thread per (pixel, frame).  Writes normal_unit, d2n, d_rgb, the pixel's own depth
+// gradient (L1 term + its share of the depth2normal adjoint) and the four contributions it makes
+// to its neighbours' depth gradients as four planes (up, left, bottom, right) that pass B gathers:
+// no atomics, deterministic.
 __global__ void __launch_bounds__(256)
-loss_pass_a(AgsLossArgs a) {
+loss_pass_a(AgsLossArgs a, float* __restrict__ nb, float* __restrict__ msum_plane) {
     const int H = a.H, W = a.W;
     const size_t P = (size_t)H * W;
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
@@ -125,9 +127,12 @@ loss_pass_a(AgsLossArgs a) {
     float fr_rgb = 0.f, fr_d = 0.f, acc_cons = 0.f;
     if (in) {
         const float msum = vis_sum(a, P, p);
+        if (f == 0) msum_plane[p] = msum;
         const float* opac = a.opacity + (size_t)f * P;
         const float* depth = a.depth + (size_t)f * P;
         float* ddep = a.d_depth + (size_t)f * P;
+        float* nbf = nb + (size_t)f * 4 * P + p;
+        float c_up = 0.f, c_left = 0.f, c_bottom = 0.f, c_right = 0.f;
         const float A = opac[p];
         const float mvis = (A > 1e-3f) ? 1.f : 0.f;
         const float m2 = (A > 1e-2f) ? 1.f : 0.f;
@@ -176,12 +181,13 @@ loss_pass_a(AgsLossArgs a) {
             const F3 dpc = (dpu + dpl + dpb + dpr) * (-v.mc);
             const float rx = (x - g.cx) * g.ik00, ry = (y - g.cy) * g.ik11;   // c = depth * (rx, ry, 1)
             dd_self += dpc.x * rx + dpc.y * ry + dpc.z;
-            if (v.mu > 0.f) atomicAdd(ddep + p - W, dpu.x * rx + dpu.y * (ry - g.ik11) + dpu.z);
-            if (v.ml > 0.f) atomicAdd(ddep + p - 1, dpl.x * (rx - g.ik00) + dpl.y * ry + dpl.z);
-            if (v.mb > 0.f) atomicAdd(ddep + p + W, dpb.x * rx + dpb.y * (ry + g.ik11) + dpb.z);
-            if (v.mr > 0.f) atomicAdd(ddep + p + 1, dpr.x * (rx + g.ik00) + dpr.y * ry + dpr.z);
+            c_up = dpu.x * rx + dpu.y * (ry - g.ik11) + dpu.z;          // zero when v.mu == 0
+            c_left = dpl.x * (rx - g.ik00) + dpl.y * ry + dpl.z;
+            c_bottom = dpb.x * rx + dpb.y * (ry + g.ik11) + dpb.z;
+            c_right = dpr.x * (rx + g.ik00) + dpr.y * ry + dpr.z;
         }
-        if (dd_self != 0.f) atomicAdd(ddep + p, dd_self);
+        ddep[p] = dd_self;
+        nbf[0] = c_up; nbf[P] = c_left; nbf[2 * P] = c_bottom; nbf[3 * P] = c_right;
     }
     float v5[5] = {fr_rgb * inv_rgb, fr_d * inv_d, acc_cons * inv_cons, fr_rgb / (3.f * (float)P), fr_d / (float)P};
     float* const d5[5] = {a.loss_terms + 0, a.loss_terms + 1, a.loss_terms + 2,
@@ -204,7 +210,7 @@ __device__ __forceinline__ void tv_term(F3 np_, F3 nq, float dp, float dq, float
 // pass B: one thread per (pixel, frame): normal gradient (consistency + TV gather, through
 // normalize*mask) and the TV loss sum.
 __global__ void __launch_bounds__(256)
-loss_pass_b(AgsLossArgs a) {
+loss_pass_b(AgsLossArgs a, const float* __restrict__ nb, const float* __restrict__ msum_plane) {
     const int H = a.H, W = a.W;
     const size_t P = (size_t)H * W;
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
@@ -217,7 +223,16 @@ loss_pass_b(AgsLossArgs a) {
     const float inv2s2 = 1.f / (2.f * 0.3f * 0.3f);
     float acc_tv = 0.f;
     if (in) {
-        const float msum = vis_sum(a, P, p);
+        const float msum = msum_plane[p];
+        {   // depth gradient: own term (pass A) + what the four neighbours push to this pixel
+            const float* nbf = nb + (size_t)f * 4 * P;
+            float dd = 0.f;
+            if (y < H - 1) dd += nbf[p + W];              // "up" plane of the pixel below
+            if (x < W - 1) dd += nbf[P + p + 1];          // "left" plane of the pixel to the right
+            if (y > 0) dd += nbf[2 * P + p - W];          // "bottom" plane of the pixel above
+            if (x > 0) dd += nbf[3 * P + p - 1];          // "right" plane of the pixel to the left
+            a.d_depth[(size_t)f * P + p] += dd;
+        }
         const float* depth = a.depth + (size_t)f * P;
         const float* dgt = a.depth_gt + (size_t)f * P;
         const float* nu_ = a.normal_unit + (size_t)f * 3 * P;
@@ -304,7 +319,7 @@ extern "C" int ags_postprocess(int32_t B, int32_t H, int32_t W, const float* nor
 
 extern "C" size_t ags_loss_scratch_bytes(int32_t B, int32_t H, int32_t W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
-    return 256;   // the two-pass scheme needs no scratch any more; kept for ABI stability
+    return ags_align256(((size_t)B * 4 + 1) * H * W * sizeof(float));
 }
 
 extern "C" int ags_loss_forward_backward(const AgsLossArgs* a) {
@@ -320,11 +335,12 @@ extern "C" int ags_loss_forward_backward(const AgsLossArgs* a) {
     cudaStream_t st = (cudaStream_t)a->stream;
     AGS_CHECK_CUDA(cudaMemsetAsync(a->loss_terms, 0, (4 + 2 * (size_t)a->B) * sizeof(float), st));
     const size_t P = (size_t)a->H * a->W;
-    AGS_CHECK_CUDA(cudaMemsetAsync(a->d_depth, 0, (size_t)a->B * P * sizeof(float), st));
+    float* nb = (float*)a->workspace;                     // (B,4,H,W) neighbour contributions
+    float* msum_plane = nb + (size_t)a->B * 4 * P;        // (H,W) visibility count (quirk Q1)
     dim3 grid((a->W + 31) / 32, (a->H + 7) / 8, a->B), block(32, 8);
-    loss_pass_a<<<grid, block, 0, st>>>(*a);
+    loss_pass_a<<<grid, block, 0, st>>>(*a, nb, msum_plane);
     AGS_CHECK_CUDA(cudaGetLastError());
-    loss_pass_b<<<grid, block, 0, st>>>(*a);
+    loss_pass_b<<<grid, block, 0, st>>>(*a, nb, msum_plane);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -179,16 +179,23 @@ __device__ __forceinline__ void project_view(ViewProj& o, const GaussAct& g, con
 // Visible pairs are appended to a compact list that drives the scatter and K6.
 __global__ void __launch_bounds__(128)
 project_fwd_kernel(AgsRenderArgs a, AgsWorkspace w, int for_backward) {
+    __shared__ Cam s_cam;                 // the view is uniform per block (blockIdx.y)
+    __shared__ int s_warp_cnt[4], s_base;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x < 16) {
+        s_cam.V[threadIdx.x] = __ldg(a.viewmatrix + v * 16 + threadIdx.x);
+        s_cam.M[threadIdx.x] = __ldg(a.projmatrix + v * 16 + threadIdx.x);
+    }
+    if (threadIdx.x == 32) { s_cam.tanx = __ldg(a.tanfov + v * 2); s_cam.tany = __ldg(a.tanfov + v * 2 + 1); }
+    __syncthreads();
     bool valid = false;
     const size_t idx = (size_t)v * a.N + (i < a.N ? i : 0);
     const int tiles_x = (a.W + TILE - 1) / TILE, tiles_y = (a.H + TILE - 1) / TILE;
     ViewProj p;
     if (i < a.N) {
-        Cam cam;
-        load_cam(cam, a.viewmatrix, a.projmatrix, a.tanfov, v);
+        const Cam& cam = s_cam;
         const float mx = __ldg(a.means3D + 3 * i), my = __ldg(a.means3D + 3 * i + 1), mz = __ldg(a.means3D + 3 * i + 2);
         const float* V = cam.V;
         const float* M = cam.M;
@@ -247,15 +254,19 @@ project_fwd_kernel(AgsRenderArgs a, AgsWorkspace w, int for_backward) {
         }
         a.radii[idx] = valid ? p.radius : 0;
     }
-    // append visible pairs to the compact list (one atomic per warp)
+    // append visible pairs to the compact list: ballot per warp, ONE atomic per block
     const unsigned m = __ballot_sync(0xffffffffu, valid);
-    if (m) {
-        int base = 0;
-        const int leader = __ffs(m) - 1;
-        if (lane == leader) base = atomicAdd(w.counters + 1, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (valid) w.vis_list[base + __popc(m & ((1u << lane) - 1u))] = (int)idx;
-        if (lane == leader) atomicAdd(a.stats + AGS_STAT_VISIBLE, __popc(m));
+    if (lane == 0) s_warp_cnt[wid] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int tot = s_warp_cnt[0] + s_warp_cnt[1] + s_warp_cnt[2] + s_warp_cnt[3];
+        s_base = tot ? atomicAdd(w.counters + 1, tot) : 0;
+    }
+    __syncthreads();
+    if (valid) {
+        int pre = 0;
+        for (int k = 0; k < wid; ++k) pre += s_warp_cnt[k];
+        w.vis_list[s_base + pre + __popc(m & ((1u << lane) - 1u))] = (int)idx;
     }
 }
 
