@@ -43,16 +43,19 @@ __device__ __forceinline__ FrameGeom frame_geom(const float* tanfov, int f, int 
     return g;
 }
 
-// camera-space point of pixel (y,x) and its d2n mask (opacity > 1e-2)
+// camera-space point of pixel (y,x) and its d2n mask (opacity > 1e-2); read-only path so the
+// loads can be issued ahead of the kernel's stores
 __device__ __forceinline__ F3 cam_point(const float* depth, const float* opac, const FrameGeom& g, int W,
                                         int y, int x, float& m) {
-    const float d = depth[(size_t)y * W + x];
-    m = (opac[(size_t)y * W + x] > 1e-2f) ? 1.f : 0.f;
+    const float d = __ldg(depth + y * W + x);
+    m = (__ldg(opac + y * W + x) > 1e-2f) ? 1.f : 0.f;
     return f3((x - g.cx) * d * g.ik00, (y - g.cy) * d * g.ik11, d);
 }
 
 // the four masked difference vectors of depth2normal at pixel (y,x); replicate padding makes the
-// out-of-image neighbour equal to the pixel itself, whose difference is exactly zero for a 0/1 mask
+// out-of-image neighbour equal to the pixel itself, whose difference is exactly zero for a 0/1 mask.
+// Branch-free: neighbours are fetched at clamped coordinates and the border is folded into the mask,
+// so all ten loads are independent and issue back to back.
 struct D2N {
     F3 pu, pl, pb, pr;
     float mu, ml, mb, mr, mc;
@@ -61,16 +64,22 @@ struct D2N {
 __device__ __forceinline__ D2N d2n_vectors(const float* depth, const float* opac, const FrameGeom& g,
                                            int H, int W, int y, int x) {
     D2N r;
+    const int yu = max(y - 1, 0), yb = min(y + 1, H - 1), xl = max(x - 1, 0), xr = min(x + 1, W - 1);
+    float mu, ml, mb, mr;
     const F3 c = cam_point(depth, opac, g, W, y, x, r.mc);
+    const F3 qu = cam_point(depth, opac, g, W, yu, x, mu);
+    const F3 ql = cam_point(depth, opac, g, W, y, xl, ml);
+    const F3 qb = cam_point(depth, opac, g, W, yb, x, mb);
+    const F3 qr = cam_point(depth, opac, g, W, y, xr, mr);
+    r.mu = (y > 0) ? mu : 0.f;
+    r.ml = (x > 0) ? ml : 0.f;
+    r.mb = (y < H - 1) ? mb : 0.f;
+    r.mr = (x < W - 1) ? mr : 0.f;
     const F3 pc = c * r.mc;
-    const F3 zero = f3(0.f, 0.f, 0.f);
-    r.mu = r.ml = r.mb = r.mr = 0.f;
-    r.pu = r.pl = r.pb = r.pr = zero;
-    float m;
-    if (y > 0)     { F3 q = cam_point(depth, opac, g, W, y - 1, x, m); r.mu = m; r.pu = (q - pc) * m; }
-    if (x > 0)     { F3 q = cam_point(depth, opac, g, W, y, x - 1, m); r.ml = m; r.pl = (q - pc) * m; }
-    if (y < H - 1) { F3 q = cam_point(depth, opac, g, W, y + 1, x, m); r.mb = m; r.pb = (q - pc) * m; }
-    if (x < W - 1) { F3 q = cam_point(depth, opac, g, W, y, x + 1, m); r.mr = m; r.pr = (q - pc) * m; }
+    r.pu = (qu - pc) * r.mu;
+    r.pl = (ql - pc) * r.ml;
+    r.pb = (qb - pc) * r.mb;
+    r.pr = (qr - pc) * r.mr;
     return r;
 }
 
@@ -102,9 +111,9 @@ __device__ __forceinline__ void block_accumulate(float (&v)[K], float* const (&d
 }
 
 __device__ __forceinline__ float vis_sum(const AgsLossArgs& a, size_t P, int p) {
-    if (a.vis_count) return (float)a.vis_count[p];
+    if (a.vis_count) return (float)__ldg(a.vis_count + p);
     float m = 0.f;
-    for (int f = 0; f < a.B; ++f) m += (a.opacity[(size_t)f * P + p] > 1e-3f) ? 1.f : 0.f;
+    for (int f = 0; f < a.B; ++f) m += (__ldg(a.opacity + (size_t)f * P + p) > 1e-3f) ? 1.f : 0.f;
     return m;
 }
 
@@ -133,7 +142,7 @@ loss_pass_a(AgsLossArgs a, float* __restrict__ nb, float* __restrict__ msum_plan
         float* ddep = a.d_depth + (size_t)f * P;
         float* nbf = nb + (size_t)f * 4 * P + p;
         float c_up = 0.f, c_left = 0.f, c_bottom = 0.f, c_right = 0.f;
-        const float A = opac[p];
+        const float A = __ldg(opac + p);
         const float mvis = (A > 1e-3f) ? 1.f : 0.f;
         const float m2 = (A > 1e-2f) ? 1.f : 0.f;
         // ---- L1 rgb + gradient
@@ -142,19 +151,19 @@ loss_pass_a(AgsLossArgs a, float* __restrict__ nb, float* __restrict__ msum_plan
         float* drgb = a.d_rgb + (size_t)f * 3 * P + p;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float e = (rp[c * P] - rg[c * P]) * mvis;
+            const float e = (__ldg(rp + c * P) - __ldg(rg + c * P)) * mvis;
             fr_rgb += fabsf(e);
             drgb[c * P] = (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f)) * mvis * inv_rgb;
         }
         // ---- L1 depth + gradient
-        const float dg = a.depth_gt[(size_t)f * P + p];
+        const float dg = __ldg(a.depth_gt + (size_t)f * P + p);
         const float md = (dg > 0.f) ? 1.f : 0.f;
-        const float ed = (depth[p] - dg) * md;
+        const float ed = (__ldg(depth + p) - dg) * md;
         fr_d = fabsf(ed);
         float dd_self = a.w_depth * (ed > 0.f ? 1.f : (ed < 0.f ? -1.f : 0.f)) * md * inv_d;
         // ---- unit normal
         const float* np_ = a.normal + (size_t)f * 3 * P + p;
-        const F3 n = f3(np_[0], np_[P], np_[2 * P]);
+        const F3 n = f3(__ldg(np_), __ldg(np_ + P), __ldg(np_ + 2 * P));
         const float nn = fmaxf(sqrtf(dot(n, n)), 1e-12f);
         const F3 nu = n * (m2 / nn);
         float* no = a.normal_unit + (size_t)f * 3 * P + p;
@@ -223,48 +232,52 @@ loss_pass_b(AgsLossArgs a, const float* __restrict__ nb, const float* __restrict
     const float inv2s2 = 1.f / (2.f * 0.3f * 0.3f);
     float acc_tv = 0.f;
     if (in) {
-        const float msum = msum_plane[p];
+        const float msum = __ldg(msum_plane + p);
         {   // depth gradient: own term (pass A) + what the four neighbours push to this pixel
             const float* nbf = nb + (size_t)f * 4 * P;
             float dd = 0.f;
-            if (y < H - 1) dd += nbf[p + W];              // "up" plane of the pixel below
-            if (x < W - 1) dd += nbf[P + p + 1];          // "left" plane of the pixel to the right
-            if (y > 0) dd += nbf[2 * P + p - W];          // "bottom" plane of the pixel above
-            if (x > 0) dd += nbf[3 * P + p - 1];          // "right" plane of the pixel to the left
+            if (y < H - 1) dd += __ldg(nbf + p + W);          // "up" plane of the pixel below
+            if (x < W - 1) dd += __ldg(nbf + P + p + 1);      // "left" plane of the pixel to the right
+            if (y > 0) dd += __ldg(nbf + 2 * P + p - W);      // "bottom" plane of the pixel above
+            if (x > 0) dd += __ldg(nbf + 3 * P + p - 1);      // "right" plane of the pixel to the left
             a.d_depth[(size_t)f * P + p] += dd;
         }
         const float* depth = a.depth + (size_t)f * P;
         const float* dgt = a.depth_gt + (size_t)f * P;
         const float* nu_ = a.normal_unit + (size_t)f * 3 * P;
-        auto NU = [&](int q) { return f3(nu_[q], nu_[P + q], nu_[2 * P + q]); };
-        const float dp = depth[p];
-        const float md_p = (dgt[p] > 0.f) ? 1.f : 0.f;
-        const float m2 = (a.opacity[(size_t)f * P + p] > 1e-2f) ? 1.f : 0.f;
+        auto NU = [&](int q) { return f3(__ldg(nu_ + q), __ldg(nu_ + P + q), __ldg(nu_ + 2 * P + q)); };
+        // all loads of the 5-point stencil up front (clamped coordinates, validity folded into flags)
+        const int qs[4] = {y * W + min(x + 1, W - 1), y * W + max(x - 1, 0),
+                           min(y + 1, H - 1) * W + x, max(y - 1, 0) * W + x};
+        const float ok[4] = {x < W - 1 ? 1.f : 0.f, x > 0 ? 1.f : 0.f, y < H - 1 ? 1.f : 0.f, y > 0 ? 1.f : 0.f};
         const F3 nu = NU(p);
+        F3 nq[4];
+        float dq[4], mdq[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            nq[k] = NU(qs[k]);
+            dq[k] = __ldg(depth + qs[k]);
+            mdq[k] = (__ldg(dgt + qs[k]) > 0.f) ? ok[k] : 0.f;
+        }
+        const float dp = __ldg(depth + p);
+        const float md_p = (__ldg(dgt + p) > 0.f) ? 1.f : 0.f;
+        const float m2 = (__ldg(a.opacity + (size_t)f * P + p) > 1e-2f) ? 1.f : 0.f;
         const float* d2p = a.d2n + (size_t)f * 3 * P + p;
-        F3 gnu = f3(d2p[0], d2p[P], d2p[2 * P]) * (-a.w_cons * msum * inv_cons);
+        F3 gnu = f3(__ldg(d2p), __ldg(d2p + P), __ldg(d2p + 2 * P)) * (-a.w_cons * msum * inv_cons);
+        const float* np_ = a.normal + (size_t)f * 3 * P + p;
+        const F3 n = f3(__ldg(np_), __ldg(np_ + P), __ldg(np_ + 2 * P));
         const float ctv = a.w_tv * inv_tv;
-        float val, coef;
         // each neighbour q contributes the own one-sided difference (mask of p) and the mirrored
         // difference of q that references p (mask of q)
-#define AGS_TV_PAIR(cond, q)                                                                 \
-        if (cond) {                                                                          \
-            const F3 nq = NU(q);                                                             \
-            const float dq = depth[q];                                                       \
-            tv_term(nu, nq, dp, dq, md_p, inv2s2, val, coef);                                \
-            acc_tv += val;                                                                   \
-            gnu = gnu + (nu - nq) * (2.f * coef * ctv);                                      \
-            const float mdq = (dgt[q] > 0.f) ? 1.f : 0.f;                                    \
-            tv_term(nq, nu, dq, dp, mdq, inv2s2, val, coef);                                 \
-            gnu = gnu - (nq - nu) * (2.f * coef * ctv);                                      \
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float val, coef;
+            tv_term(nu, nq[k], dp, dq[k], md_p * ok[k], inv2s2, val, coef);
+            acc_tv += val;
+            gnu = gnu + (nu - nq[k]) * (2.f * coef * ctv);
+            tv_term(nq[k], nu, dq[k], dp, mdq[k], inv2s2, val, coef);
+            gnu = gnu - (nq[k] - nu) * (2.f * coef * ctv);
         }
-        AGS_TV_PAIR(x < W - 1, p + 1)
-        AGS_TV_PAIR(x > 0, p - 1)
-        AGS_TV_PAIR(y < H - 1, p + W)
-        AGS_TV_PAIR(y > 0, p - W)
-#undef AGS_TV_PAIR
-        const float* np_ = a.normal + (size_t)f * 3 * P + p;
-        const F3 n = f3(np_[0], np_[P], np_[2 * P]);
         const float nn = fmaxf(sqrtf(dot(n, n)), 1e-12f);
         const F3 uh = n * (1.f / nn);
         const F3 gn = (gnu - uh * dot(uh, gnu)) * (m2 / nn);

@@ -172,33 +172,46 @@ __device__ __forceinline__ void project_view(ViewProj& o, const GaussAct& g, con
 }
 
 // K1 ---------------------------------------------------------------------------------------------
-// One thread per (Gaussian, view) pair.  Most pairs are outside the frustum (C2: ~89 %), so the pair
-// is first tested against a CONSERVATIVE screen-space radius bound that needs only the mean and the
-// scales:  a,c <= s_max^2 (f/t_z)^2 (1 + lim^2) + 0.3,  lambda_1 <= a + c + sqrt(0.1)  =>  R_b.  A pair
-// whose tile rect is empty even with R_b cannot be visible; everything else takes the exact path.
-// Visible pairs are appended to a compact list that drives the scatter and K6.
-__global__ void __launch_bounds__(128)
+// One CTA handles 1024 consecutive Gaussians of one view in three phases:
+//   1. every (Gaussian, view) pair is tested against a CONSERVATIVE screen-space radius bound that
+//      needs only the mean (and, in ACTIVATED mode, the scales):
+//      a,c <= s_max^2 (f/t_z)^2 (1 + lim^2) + 0.3,  lambda_1 <= a + c + sqrt(0.1)  =>  R_b.
+//      A pair whose tile rect is empty even with R_b cannot be visible (C2: ~85 % of the pairs);
+//      the survivors are compacted into a shared-memory candidate list,
+//   2. the exact projection runs on the compacted candidates only, so the warps that execute the
+//      heavy path are dense even when the visible Gaussians are scattered over the index range,
+//   3. the visible pairs of the CTA are appended to the global compact list (one atomic per CTA)
+//      that drives the scatter and K6.
+constexpr int K1_THREADS = 256;
+constexpr int K1_PER_THREAD = 4;
+constexpr int K1_PAIRS = K1_THREADS * K1_PER_THREAD;
+
+__global__ void __launch_bounds__(K1_THREADS)
 project_fwd_kernel(AgsRenderArgs a, AgsWorkspace w, int for_backward) {
     __shared__ Cam s_cam;                 // the view is uniform per block (blockIdx.y)
-    __shared__ int s_warp_cnt[4], s_base;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int s_cand[K1_PAIRS], s_vis[K1_PAIRS];
+    __shared__ int s_ncand, s_nvis, s_base;
     const int v = blockIdx.y;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x < 16) {
-        s_cam.V[threadIdx.x] = __ldg(a.viewmatrix + v * 16 + threadIdx.x);
-        s_cam.M[threadIdx.x] = __ldg(a.projmatrix + v * 16 + threadIdx.x);
+    const int tid = threadIdx.x;
+    if (tid < 16) {
+        s_cam.V[tid] = __ldg(a.viewmatrix + v * 16 + tid);
+        s_cam.M[tid] = __ldg(a.projmatrix + v * 16 + tid);
     }
-    if (threadIdx.x == 32) { s_cam.tanx = __ldg(a.tanfov + v * 2); s_cam.tany = __ldg(a.tanfov + v * 2 + 1); }
+    if (tid == 32) { s_cam.tanx = __ldg(a.tanfov + v * 2); s_cam.tany = __ldg(a.tanfov + v * 2 + 1); }
+    if (tid == 64) { s_ncand = 0; s_nvis = 0; }
     __syncthreads();
-    bool valid = false;
-    const size_t idx = (size_t)v * a.N + (i < a.N ? i : 0);
+    const Cam& cam = s_cam;
+    const float* V = cam.V;
+    const float* M = cam.M;
     const int tiles_x = (a.W + TILE - 1) / TILE, tiles_y = (a.H + TILE - 1) / TILE;
-    ViewProj p;
-    if (i < a.N) {
-        const Cam& cam = s_cam;
+    const size_t vN = (size_t)v * a.N;
+    const float fx = a.W / (2.f * cam.tanx), fy = a.H / (2.f * cam.tany);
+    const float kx = fx * fx * (1.f + 1.69f * cam.tanx * cam.tanx), ky = fy * fy * (1.f + 1.69f * cam.tany * cam.tany);
+    // ---- phase 1: conservative cull, compaction of the candidates
+    for (int r = 0; r < K1_PER_THREAD; ++r) {
+        const int i = blockIdx.x * K1_PAIRS + r * K1_THREADS + tid;
+        if (i >= a.N) break;
         const float mx = __ldg(a.means3D + 3 * i), my = __ldg(a.means3D + 3 * i + 1), mz = __ldg(a.means3D + 3 * i + 2);
-        const float* V = cam.V;
-        const float* M = cam.M;
         const float tz = mx * V[2] + my * V[6] + mz * V[10] + V[14];
         bool maybe = tz > AGS_NEAR_CULL;
         if (maybe) {
@@ -214,12 +227,8 @@ project_fwd_kernel(AgsRenderArgs a, AgsWorkspace w, int for_backward) {
             const float homw = mx * M[3] + my * M[7] + mz * M[11] + M[15];
             const float iw = 1.f / (homw + 1e-7f);
             const float xg = ((homx * iw + 1.f) * a.W - 1.f) * 0.5f, yg = ((homy * iw + 1.f) * a.H - 1.f) * 0.5f;
-            const float fx = a.W / (2.f * cam.tanx), fy = a.H / (2.f * cam.tany);
-            const float lx = 1.3f * cam.tanx, ly = 1.3f * cam.tany;
             const float sz = smax / tz;
-            const float ab = sz * sz * fx * fx * (1.f + lx * lx) + AGS_LOWPASS;
-            const float cb = sz * sz * fy * fy * (1.f + ly * ly) + AGS_LOWPASS;
-            const float Rb = ceilf(3.f * sqrtf(ab + cb + 0.3163f)) * 1.001f + 2.f;
+            const float Rb = ceilf(3.f * sqrtf(sz * sz * (kx + ky) + 2.f * AGS_LOWPASS + 0.3163f)) * 1.001f + 2.f;
             if (xg == xg && yg == yg && fabsf(xg) < 1e9f && fabsf(yg) < 1e9f && Rb < 1e9f) {
                 const int minx = min(tiles_x, max(0, (int)((xg - Rb) / TILE)));
                 const int miny = min(tiles_y, max(0, (int)((yg - Rb) / TILE)));
@@ -228,46 +237,45 @@ project_fwd_kernel(AgsRenderArgs a, AgsWorkspace w, int for_backward) {
                 maybe = (maxx - minx) * (maxy - miny) > 0;
             }
         }
-        if (maybe) {
-            GaussAct g;
-            activate(g, a, i);
-            project_view(p, g, cam, a.H, a.W, a.front_only != 0);
-            valid = p.valid;
-            if (valid) {
-                const float conf = a.confidences ? __ldg(a.confidences + i) : 0.f;
-                w.geom0[idx] = make_float4(p.xg, p.yg, p.ca, p.cb);
-                w.geom1[idx] = make_float4(p.cc, g.o, p.sx, p.sy);
-                w.feat0[idx] = make_float4(__ldg(a.colors + 3 * i), __ldg(a.colors + 3 * i + 1),
-                                           __ldg(a.colors + 3 * i + 2), p.t[2]);
-                w.feat1[idx] = make_float4(p.nv[0], p.nv[1], p.nv[2], conf);
-                w.rect[idx] = make_uint2((unsigned)p.minx | ((unsigned)p.maxx << 16),
-                                         (unsigned)p.miny | ((unsigned)p.maxy << 16));
-                if (for_backward) {
-                    float4* d = reinterpret_cast<float4*>(w.dsplat + idx * 16);
-                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    d[0] = z; d[1] = z; d[2] = z; d[3] = z;
-                }
-                int32_t* tc = w.tile_count + (size_t)v * tiles_x * tiles_y;
-                for (int ty = p.miny; ty < p.maxy; ++ty)
-                    for (int tx = p.minx; tx < p.maxx; ++tx) atomicAdd(tc + ty * tiles_x + tx, 1);
-            }
+        if (maybe) s_cand[atomicAdd(&s_ncand, 1)] = i;
+        else a.radii[vN + i] = 0;
+    }
+    __syncthreads();
+    // ---- phase 2: exact projection of the candidates
+    const int ncand = s_ncand;
+    for (int c = tid; c < ncand; c += K1_THREADS) {
+        const int i = s_cand[c];
+        const size_t idx = vN + i;
+        GaussAct g;
+        activate(g, a, i);
+        ViewProj p;
+        project_view(p, g, cam, a.H, a.W, a.front_only != 0);
+        a.radii[idx] = p.valid ? p.radius : 0;
+        if (!p.valid) continue;
+        const float conf = a.confidences ? __ldg(a.confidences + i) : 0.f;
+        w.geom0[idx] = make_float4(p.xg, p.yg, p.ca, p.cb);
+        w.geom1[idx] = make_float4(p.cc, g.o, p.sx, p.sy);
+        w.feat0[idx] = make_float4(__ldg(a.colors + 3 * i), __ldg(a.colors + 3 * i + 1),
+                                   __ldg(a.colors + 3 * i + 2), p.t[2]);
+        w.feat1[idx] = make_float4(p.nv[0], p.nv[1], p.nv[2], conf);
+        w.rect[idx] = make_uint2((unsigned)p.minx | ((unsigned)p.maxx << 16),
+                                 (unsigned)p.miny | ((unsigned)p.maxy << 16));
+        if (for_backward) {
+            float4* d = reinterpret_cast<float4*>(w.dsplat + idx * 16);
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            d[0] = z; d[1] = z; d[2] = z; d[3] = z;
         }
-        a.radii[idx] = valid ? p.radius : 0;
-    }
-    // append visible pairs to the compact list: ballot per warp, ONE atomic per block
-    const unsigned m = __ballot_sync(0xffffffffu, valid);
-    if (lane == 0) s_warp_cnt[wid] = __popc(m);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int tot = s_warp_cnt[0] + s_warp_cnt[1] + s_warp_cnt[2] + s_warp_cnt[3];
-        s_base = tot ? atomicAdd(w.counters + 1, tot) : 0;
+        int32_t* tc = w.tile_count + (size_t)v * tiles_x * tiles_y;
+        for (int ty = p.miny; ty < p.maxy; ++ty)
+            for (int tx = p.minx; tx < p.maxx; ++tx) atomicAdd(tc + ty * tiles_x + tx, 1);
+        s_vis[atomicAdd(&s_nvis, 1)] = (int)idx;
     }
     __syncthreads();
-    if (valid) {
-        int pre = 0;
-        for (int k = 0; k < wid; ++k) pre += s_warp_cnt[k];
-        w.vis_list[s_base + pre + __popc(m & ((1u << lane) - 1u))] = (int)idx;
-    }
+    // ---- phase 3: append to the global visible list
+    const int nvis = s_nvis;
+    if (tid == 0) s_base = nvis ? atomicAdd(w.counters + 1, nvis) : 0;
+    __syncthreads();
+    for (int c = tid; c < nvis; c += K1_THREADS) w.vis_list[s_base + c] = s_vis[c];
 }
 
 // K6 ---------------------------------------------------------------------------------------------
@@ -451,9 +459,8 @@ project_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
 
 int ags_launch_project_fwd(const AgsRenderArgs& a, const AgsWorkspace& w, bool for_backward) {
     if (a.N == 0) return 0;
-    const int threads = 128;
-    dim3 grid((a.N + threads - 1) / threads, a.B);
-    project_fwd_kernel<<<grid, threads, 0, (cudaStream_t)a.stream>>>(a, w, for_backward ? 1 : 0);
+    dim3 grid((a.N + K1_PAIRS - 1) / K1_PAIRS, a.B);
+    project_fwd_kernel<<<grid, K1_THREADS, 0, (cudaStream_t)a.stream>>>(a, w, for_backward ? 1 : 0);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
