@@ -25,8 +25,24 @@ struct __align__(16) SplatRec {
     float4 g0, g1, f0, f1, bb;
 };
 
+#define AGS_LOG2E 1.4426950408889634f
+
+__device__ __forceinline__ float ex2_approx(float x) {      // MUFU.EX2, flush-to-zero, no range fix-up
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {      // MUFU.RCP
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// The staged record carries the conic pre-multiplied by log2(e), so the exponent feeds MUFU.EX2
+// directly: G = exp(power) = 2^(power2), power2 = -0.5 (a' dx^2 + c' dy^2) - b' dx dy.
+// `power` below is power2 (same sign as the natural exponent); `G` is the un-clamped Gaussian.
 struct SplatEval {
-    float dx, dy, power, alpha;
+    float dx, dy, power, G, alpha;
     bool skip;
 };
 
@@ -35,7 +51,8 @@ __device__ __forceinline__ SplatEval eval_alpha(const float4 g0, const float4 g1
     e.dx = g0.x - pxf;
     e.dy = g0.y - pyf;
     e.power = -0.5f * (g0.z * e.dx * e.dx + g1.x * e.dy * e.dy) - g0.w * e.dx * e.dy;
-    e.alpha = fminf(AGS_ALPHA_MAX, g1.y * __expf(e.power));
+    e.G = ex2_approx(e.power);
+    e.alpha = fminf(AGS_ALPHA_MAX, g1.y * e.G);
     e.skip = (e.power > 0.f) || (e.alpha < AGS_ALPHA_MIN);
     return e;
 }
@@ -111,8 +128,8 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
             const float4 g0 = ldg4(w.geom0 + idx), g1 = ldg4(w.geom1 + idx);
             s_id[tid] = id;
             SplatRec& r = s_rec[tid];
-            r.g0 = g0;
-            r.g1 = g1;
+            r.g0 = make_float4(g0.x, g0.y, g0.z * AGS_LOG2E, g0.w * AGS_LOG2E);   // conic * log2(e)
+            r.g1 = make_float4(g1.x * AGS_LOG2E, g1.y, g1.z, g1.w);
             r.f0 = ldg4(w.feat0 + idx);
             r.f1 = ldg4(w.feat1 + idx);
             r.bb = splat_bbox(g0, g1);
@@ -172,14 +189,20 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
 // Row stride 36 floats keeps the 128-bit loads of a quarter-warp on distinct banks.
 constexpr int RED_STRIDE = 36;
 
-__device__ __forceinline__ float warp_reduce15(const float (&v)[15], float* buf, int lane) {
-#pragma unroll
-    for (int q = 0; q < 15; ++q) buf[q * RED_STRIDE + lane] = v[q];
+__device__ __forceinline__ float warp_reduce15(const float (&v)[15], unsigned st_addr, unsigned ld_addr, int lane) {
+#define AGS_RED_ST(q) asm volatile("st.shared.f32 [%0+%1], %2;" :: "r"(st_addr), "n"((q) * RED_STRIDE * 4), "f"(v[q]) : "memory")
+    AGS_RED_ST(0); AGS_RED_ST(1); AGS_RED_ST(2); AGS_RED_ST(3); AGS_RED_ST(4);
+    AGS_RED_ST(5); AGS_RED_ST(6); AGS_RED_ST(7); AGS_RED_ST(8); AGS_RED_ST(9);
+    AGS_RED_ST(10); AGS_RED_ST(11); AGS_RED_ST(12); AGS_RED_ST(13); AGS_RED_ST(14);
+#undef AGS_RED_ST
     __syncwarp();
     float r = 0.f;
     if (lane < 30) {
-        const float4* src = reinterpret_cast<const float4*>(buf + (lane >> 1) * RED_STRIDE + (lane & 1) * 16);
-        const float4 x0 = src[0], x1 = src[1], x2 = src[2], x3 = src[3];
+        float4 x0, x1, x2, x3;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x0.x), "=f"(x0.y), "=f"(x0.z), "=f"(x0.w) : "r"(ld_addr) : "memory");
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(x1.x), "=f"(x1.y), "=f"(x1.z), "=f"(x1.w) : "r"(ld_addr) : "memory");
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+32];" : "=f"(x2.x), "=f"(x2.y), "=f"(x2.z), "=f"(x2.w) : "r"(ld_addr) : "memory");
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+48];" : "=f"(x3.x), "=f"(x3.y), "=f"(x3.z), "=f"(x3.w) : "r"(ld_addr) : "memory");
         r = ((x0.x + x0.y) + (x0.z + x0.w)) + ((x1.x + x1.y) + (x1.z + x1.w))
           + ((x2.x + x2.y) + (x2.z + x2.w)) + ((x3.x + x3.y) + (x3.z + x3.w));
     }
@@ -244,6 +267,11 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
     const int n_eff = min(n, s_max_last);
 
     const int warp_last = __reduce_max_sync(0xffffffffu, my_last);
+    // loop-invariant shared-space addresses of this lane's slots in the warp's transposition buffer
+    const unsigned red_st = (unsigned)__cvta_generic_to_shared(&s_red[tid >> 5][lane]);
+    const unsigned red_ld = (unsigned)__cvta_generic_to_shared(
+        &s_red[tid >> 5][(lane >> 1) * RED_STRIDE + (lane & 1) * 16]);
+    float* const dsplat_lane = w.dsplat + vN * 16 + (lane >> 1);
     float T = 1.f;
     for (int base = 0; base < n_eff; base += BATCH) {
         __syncthreads();
@@ -254,8 +282,8 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
             const float4 g0 = ldg4(w.geom0 + idx), g1 = ldg4(w.geom1 + idx);
             s_id[tid] = id;
             SplatRec& r = s_rec[tid];
-            r.g0 = g0;
-            r.g1 = g1;
+            r.g0 = make_float4(g0.x, g0.y, g0.z * AGS_LOG2E, g0.w * AGS_LOG2E);   // conic * log2(e)
+            r.g1 = make_float4(g1.x * AGS_LOG2E, g1.y, g1.z, g1.w);
             r.f0 = ldg4(w.feat0 + idx);
             r.f1 = ldg4(w.feat1 + idx);
             r.bb = splat_bbox(g0, g1);
@@ -273,38 +301,39 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
                 const SplatEval e = eval_alpha(g0, g1, pxf, pyf);
                 const bool active = (base + k < my_last) && !e.skip;
                 if (__ballot_sync(0xffffffffu, active) == 0u) continue;
+                // branch-free: an inactive lane runs the same arithmetic with alpha = G = 0, which
+                // leaves its T / rem untouched and makes all fifteen partials exactly zero
+                const float4 f0 = rec.f0, f1 = rec.f1;
+                const float alpha = active ? e.alpha : 0.f;
+                const float G = active ? e.G : 0.f;
+                const float wgt = alpha * T;
+                const float one_m = 1.f - alpha;
+                const float dpix = f0.w - g1.z * e.dx - g1.w * e.dy;
+                const float sdot = gC0 * f0.x + gC1 * f0.y + gC2 * f0.z + gN0 * f1.x + gN1 * f1.y + gN2 * f1.z
+                                 + gD * dpix + gCf * f1.w;
+                rem -= wgt * sdot;
+                const float dalpha = T * sdot - rem * rcp_approx(one_m);       // one_m >= 0.01
+                T *= one_m;
+                // alpha = min(0.99, o*G): clamped -> no gradient.  dpower is w.r.t. the NATURAL exponent;
+                // the staged conic is scaled by log2(e), hence the 1/log2(e) on the position terms.
+                const bool unclamped = (g1.y * G <= AGS_ALPHA_MAX);
+                const float dpower = unclamped ? alpha * dalpha : 0.f;
+                const float dps = dpower * (1.f / AGS_LOG2E);
+                const float wgD = wgt * gD;
                 float val[15];
-#pragma unroll
-                for (int q = 0; q < 15; ++q) val[q] = 0.f;
-                if (active) {
-                    const float4 f0 = rec.f0, f1 = rec.f1;
-                    const float wgt = e.alpha * T;
-                    const float one_m = 1.f - e.alpha;
-                    const float dpix = f0.w - g1.z * e.dx - g1.w * e.dy;
-                    const float sdot = gC0 * f0.x + gC1 * f0.y + gC2 * f0.z + gN0 * f1.x + gN1 * f1.y + gN2 * f1.z
-                                     + gD * dpix + gCf * f1.w;
-                    rem -= wgt * sdot;
-                    const float dalpha = T * sdot - __fdividef(rem, one_m);   // one_m >= 0.01
-                    T *= one_m;
-                    // alpha = min(0.99, o*G): clamped -> no gradient
-                    const float G = __expf(e.power);
-                    const bool unclamped = (g1.y * G <= AGS_ALPHA_MAX);
-                    const float dpower = unclamped ? e.alpha * dalpha : 0.f;
-                    const float wgD = wgt * gD;
-                    val[0] = dpower * (-g0.z * e.dx - g0.w * e.dy) - wgD * g1.z;    // d x
-                    val[1] = dpower * (-g1.x * e.dy - g0.w * e.dx) - wgD * g1.w;    // d y
-                    val[2] = -0.5f * e.dx * e.dx * dpower;                          // d conic a
-                    val[3] = -e.dx * e.dy * dpower;                                 // d conic b
-                    val[4] = -0.5f * e.dy * e.dy * dpower;                          // d conic c
-                    val[5] = unclamped ? G * dalpha : 0.f;                          // d opacity
-                    val[6] = wgt * gC0; val[7] = wgt * gC1; val[8] = wgt * gC2;     // d rgb
-                    val[9] = wgt * gN0; val[10] = wgt * gN1; val[11] = wgt * gN2;   // d normal
-                    val[12] = wgD;                                                  // d depth
-                    val[13] = -wgD * e.dx;                                          // d slope x
-                    val[14] = -wgD * e.dy;                                          // d slope y
-                }
-                const float r = warp_reduce15(val, s_red[tid >> 5], lane);
-                if ((lane & 1) == 0 && lane < 30) atomicAdd(w.dsplat + (vN + s_id[k]) * 16 + (lane >> 1), r);
+                val[0] = dps * (-g0.z * e.dx - g0.w * e.dy) - wgD * g1.z;       // d x
+                val[1] = dps * (-g1.x * e.dy - g0.w * e.dx) - wgD * g1.w;       // d y
+                val[2] = -0.5f * e.dx * e.dx * dpower;                          // d conic a
+                val[3] = -e.dx * e.dy * dpower;                                 // d conic b
+                val[4] = -0.5f * e.dy * e.dy * dpower;                          // d conic c
+                val[5] = unclamped ? G * dalpha : 0.f;                          // d opacity
+                val[6] = wgt * gC0; val[7] = wgt * gC1; val[8] = wgt * gC2;     // d rgb
+                val[9] = wgt * gN0; val[10] = wgt * gN1; val[11] = wgt * gN2;   // d normal
+                val[12] = wgD;                                                  // d depth
+                val[13] = -wgD * e.dx;                                          // d slope x
+                val[14] = -wgD * e.dy;                                          // d slope y
+                const float r = warp_reduce15(val, red_st, red_ld, lane);
+                if ((lane & 1) == 0 && lane < 30) atomicAdd(dsplat_lane + (size_t)s_id[k] * 16, r);
             }
         }
     }
