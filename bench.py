@@ -280,7 +280,10 @@ def cpu_reference_run(steps, frames, start, H, W, quiet=False, warmup=0):
     reference; its rasterizer is CUDA-only and absent).  Bounded sample: ONE keyframe per step at the
     full 200k-Gaussian 640x480 workload: forward, 4-term loss, backward, Adam."""
     from oracle import host_ref as hr
-    torch.set_num_threads(os.cpu_count())
+    # the oracle works tile by tile on small tensors: more than ~16 intra-op threads only adds
+    # synchronisation cost (measured: 128 threads are 13x slower than 8), so the thread count is capped
+    threads = min(os.cpu_count(), 16)
+    torch.set_num_threads(threads)
     state = {k: v.clone() for k, v in start.items()}
     fr = [{k: v for k, v in f.items()} for f in frames]
     for _ in range(warmup):
@@ -288,7 +291,7 @@ def cpu_reference_run(steps, frames, start, H, W, quiet=False, warmup=0):
     t0 = time.time()
     hr.train_iterations(state, fr, [[0]] * steps, torch.zeros(4), (0.001, 10.0), (H, W))
     dt = time.time() - t0
-    return {"value": steps * H * W / dt / 1e6, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+    return {"value": steps * H * W / dt / 1e6, "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(), "kind": "port",
             "sample": f"{steps} step(s) x 1 keyframe (of 8) at full N/resolution: fwd+loss+bwd+Adam, torch-CPU oracle",
             "seconds": dt}
 

@@ -77,7 +77,8 @@ def compare_states(ours, ref, iters):
         fin = torch.isfinite(b)
         d = torch.where(fin, d, torch.zeros_like(d))
         lr = LRS.get(k, 0.0)
-        scale = max(b[fin].abs().max().item(), 1e-12) if fin.any() else 1.0
+        live = fin & (b.abs() < 1e9)          # the inert third scale (-1e10) is not a scale reference
+        scale = max(b[live].abs().max().item(), 1e-12) if live.any() else 1.0
         tight = (d > 1e-4 * scale + 0.02 * lr).double().mean().item()
         worst = d.max().item()
         budget = max(2.0 * lr * iters, 2e-4 * scale)
