@@ -310,8 +310,12 @@ project_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
         load_cam(cam, a.viewmatrix, a.projmatrix, a.tanfov, v);
         ViewProj p;
         project_view(p, g, cam, a.H, a.W, false);
-        const float4* dr = reinterpret_cast<const float4*>(w.dsplat + idx * 16);
+        float4* dr = reinterpret_cast<float4*>(w.dsplat + idx * 16);
         const float4 d0 = dr[0], d1 = dr[1], d2 = dr[2], d3 = dr[3];
+        {   // consume-and-clear: a second backward on the same forward starts from zero again
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            dr[0] = z; dr[1] = z; dr[2] = z; dr[3] = z;
+        }
         const float dxg = d0.x, dyg = d0.y, dca = d0.z, dcb = d0.w;
         const float dcc = d1.x;
         const float d_o = d1.y;
