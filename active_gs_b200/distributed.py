@@ -10,16 +10,60 @@ sampled keyframe batch.  Exchanges per iteration:
 The sampler draw uses numpy's global RNG with the same seed on every rank, so the ids agree without
 a broadcast.  Loss normalisers use the global batch size (AgsLossArgs.B_total).
 """
+import ctypes as C
 import numpy as np
 import torch
 import torch.distributed as dist
 
 
+class SymmetricFlat:
+    """Symmetric (peer-mapped) flat buffers for the fused exchange: parameters, gradients, both of
+    `numel_padded` floats at the same offset on every GPU of the group, plus their NVLS multicast
+    addresses when the fabric supports it."""
+
+    def __init__(self, group, numel, device):
+        import torch.distributed._symmetric_memory as symm
+        world = dist.get_world_size(group)
+        q = 4 * world
+        self.numel = numel
+        self.numel_padded = (numel + q - 1) // q * q
+        self.param = symm.empty(self.numel_padded, dtype=torch.float32, device=device)
+        self.grad = symm.empty(self.numel_padded, dtype=torch.float32, device=device)
+        self.param.zero_(); self.grad.zero_()
+        g = group if group is not None else dist.group.WORLD
+        self.h_param = symm.rendezvous(self.param, g)
+        self.h_grad = symm.rendezvous(self.grad, g)
+        self.param_ptrs = [int(p) for p in self.h_param.buffer_ptrs]
+        self.grad_ptrs = [int(p) for p in self.h_grad.buffer_ptrs]
+        mc = bool(self.h_param.has_multicast_support) if hasattr(self.h_param, "has_multicast_support") else False
+        self.param_mc = int(self.h_param.multicast_ptr) if mc else 0
+        self.grad_mc = int(self.h_grad.multicast_ptr) if mc else 0
+
+    def barrier(self):
+        """cross-GPU barrier on the current stream (device side, no host sync)"""
+        self.h_grad.barrier()
+
+
 class FrameShard:
-    def __init__(self, group=None):
+    def __init__(self, group=None, fused=False):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        # fused = reduce-scatter -> Adam -> all-gather in ONE kernel over NVLink peer memory
+        # (csrc/dist_adam.cu) instead of NCCL all-reduce + replicated Adam
+        self.fused = fused
+        self.use_multicast = True
+        self._flat = None
+
+    def flat_buffers(self, numel, device):
+        """symmetric buffers with head-room, re-allocated (collective!) only when the map outgrows them"""
+        if self._flat is None or self._flat.numel_padded < numel:
+            self._flat = SymmetricFlat(self.group, int(numel * 1.25) + 1024, device)
+        return self._flat
+
+    def all_reduce_max_(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
 
     def local_batch(self, B_global):
         if B_global % self.world != 0:

@@ -60,15 +60,34 @@ class _TrainEngine:
         self.params = [gm._means, gm._scales, gm._rotations, gm._opacities, gm._harmonics]
         for p in self.params:
             assert p.is_contiguous() and p.dtype == torch.float32
-        # gradients are views of ONE flat buffer (14 floats per Gaussian): a single all-reduce
-        # in the frame-sharded multi-GPU path, a single memset if ever needed
-        self.grad_flat = torch.empty(sum(p.numel() for p in self.params), **o)
+        total = sum(p.numel() for p in self.params)
+        self.fused = dist_ctx is not None and dist_ctx.fused
+        self.flat = None
+        if self.fused:
+            # parameters and gradients live in symmetric (peer-mapped) flat buffers; the GaussianMap
+            # tensors become views of the parameter buffer for the duration of train()
+            self.flat = dist_ctx.flat_buffers(total, dev)
+            off, views = 0, []
+            for p in self.params:
+                dst = self.flat.param[off:off + p.numel()].view(p.shape)
+                dst.copy_(p)
+                views.append(dst)
+                off += p.numel()
+            gm._means, gm._scales, gm._rotations, gm._opacities, gm._harmonics = views
+            self.params = views
+            self.grad_flat = self.flat.grad
+            self.m_flat = torch.zeros(self.flat.numel_padded, **o)
+            self.v_flat = torch.zeros(self.flat.numel_padded, **o)
+        else:
+            # gradients are views of ONE flat buffer (14 floats per Gaussian): a single all-reduce
+            # in the frame-sharded multi-GPU path
+            self.grad_flat = torch.empty(total, **o)
         self.grads, off = [], 0
         for p in self.params:
             self.grads.append(self.grad_flat[off:off + p.numel()].view(p.shape))
             off += p.numel()
-        self.m = [torch.zeros_like(p) for p in self.params]
-        self.v = [torch.zeros_like(p) for p in self.params]
+        self.m = [torch.zeros_like(p) for p in self.params] if not self.fused else None
+        self.v = [torch.zeros_like(p) for p in self.params] if not self.fused else None
         self.lrs = [gm.cfg.optimizer.mean_lr, gm.cfg.optimizer.scale_lr, gm.cfg.optimizer.rotation_lr,
                     gm.cfg.optimizer.opacity_lr, gm.cfg.optimizer.harmonic_lr]
         self.step = 0
@@ -103,6 +122,7 @@ class _TrainEngine:
         self.fwd_args = self.rb._args()      # argument structs are built once: pointers never change
         self.grad_args = None
         self.adam_cache = {}
+        self.dist_args = None
 
     def set_batch(self, rgbs, depths, views_h, projs_h, tanfovs_h, idx):
         """Stage this iteration's keyframes (lists of (3,H,W)/(1,H,W) tensors) and camera blocks
@@ -142,6 +162,8 @@ class _TrainEngine:
         L.check(lib.ags_render_forward(C.byref(fa)), "ags_render_forward")
         vis = None
         if self.dist is not None:
+            # every rank must take the same overflow decision: stats[0:2] = (instances, overflow) -> MAX
+            self.dist.all_reduce_max_(rb.stats[:2])
             torch.sum(rb.opacity[:, 0] > 1e-3, dim=0, dtype=torch.int32, out=self.vis_count)
             self.dist.all_reduce_sum_(self.vis_count)
             vis = self.vis_count
@@ -168,11 +190,42 @@ class _TrainEngine:
             g.accumulate = 0
             self.grad_args = g
         L.check(lib.ags_render_backward(C.byref(fa), C.byref(self.grad_args)), "ags_render_backward")
+        self.step += 1
+        if self.fused:
+            self._fused_exchange_and_adam(lib, st)
+            return
         if self.dist is not None:
             self.dist.all_reduce_grads_(self.grads)
-        self.step += 1
         ops.adam_step(self.params, self.grads, self.m, self.v, self.lrs, step=self.step,
                       skip_flag_ptr=rb.stats.data_ptr() + 4 * L.STAT_OVERFLOW, cache=self.adam_cache)
+
+    def _fused_exchange_and_adam(self, lib, st):
+        """reduce-scatter(grads) -> Adam(shard) -> all-gather(params) in one kernel, between two
+        device-side cross-GPU barriers on this stream (csrc/dist_adam.cu)"""
+        f, d = self.flat, self.dist
+        a = self.dist_args
+        if a is None:
+            a = L.DistAdamArgs()
+            a.world, a.rank, a.num_groups = d.world, d.rank, len(self.params)
+            for p in range(d.world):
+                a.grad_peers[p], a.param_peers[p] = f.grad_ptrs[p], f.param_ptrs[p]
+                a.skip_peers[p] = None
+            a.skip_peers[d.rank] = self.rb.stats.data_ptr() + 4 * L.STAT_OVERFLOW   # already the global MAX
+            use_mc = d.use_multicast and f.grad_mc != 0 and f.param_mc != 0
+            a.grad_multicast = f.grad_mc if use_mc else None
+            a.param_multicast = f.param_mc if use_mc else None
+            a.exp_avg, a.exp_avg_sq = L.ptr(self.m_flat), L.ptr(self.v_flat)
+            for k, p in enumerate(self.params):
+                a.numel[k] = p.numel()
+                a.lr[k] = self.lrs[k]
+            a.numel_padded = f.numel_padded
+            a.beta1, a.beta2, a.eps = 0.9, 0.999, 1e-15
+            self.dist_args = a
+        a.step = self.step
+        a.stream = st
+        f.barrier()                                  # every rank's gradients are complete
+        L.check(lib.ags_dist_adam_step(C.byref(a)), "ags_dist_adam_step")
+        f.barrier()                                  # every rank's parameters are updated
 
     def fetch(self):
         """Wait for the loss terms / per-frame performance / instance statistics of the step that

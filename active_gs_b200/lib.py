@@ -65,10 +65,24 @@ class AdamArgs(C.Structure):
     ]
 
 
+MAX_PEERS = 8
+
+
+class DistAdamArgs(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32), ("rank", C.c_int32), ("num_groups", C.c_int32), ("step", C.c_int32),
+        ("grad_peers", _f * MAX_PEERS), ("param_peers", _f * MAX_PEERS), ("skip_peers", _f * MAX_PEERS),
+        ("grad_multicast", _f), ("param_multicast", _f), ("exp_avg", _f), ("exp_avg_sq", _f),
+        ("numel", C.c_int64 * ADAM_GROUPS), ("numel_padded", C.c_int64), ("lr", C.c_float * ADAM_GROUPS),
+        ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("stream", _f),
+    ]
+
+
 _lib = None
 
 EXPORTS = ["ags_scratch_bytes", "ags_render_forward", "ags_render_backward", "ags_render_stage",
            "ags_loss_scratch_bytes", "ags_loss_forward_backward", "ags_postprocess", "ags_adam_step",
+           "ags_dist_adam_step",
            "ags_last_error", "ags_version"]
 
 
@@ -92,6 +106,8 @@ def load():
     lib.ags_render_stage.restype = C.c_int
     lib.ags_loss_forward_backward.argtypes = [C.POINTER(LossArgs)]
     lib.ags_adam_step.argtypes = [C.POINTER(AdamArgs)]
+    lib.ags_dist_adam_step.argtypes = [C.POINTER(DistAdamArgs)]
+    lib.ags_dist_adam_step.restype = C.c_int
     lib.ags_postprocess.argtypes = [C.c_int32] * 3 + [C.c_void_p] * 7
     lib.ags_postprocess.restype = C.c_int
     lib.ags_last_error.restype = C.c_char_p

@@ -182,7 +182,9 @@ def run_ours(args, rank, world, local_rank):
         from active_gs_b200.distributed import FrameShard
         os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout
         dist.init_process_group("nccl", device_id=dev)
-        shard = FrameShard()
+        # fused NVLink reduce-scatter -> Adam -> all-gather kernel by default; AGS_DIST=nccl selects the
+        # NCCL all-reduce + replicated Adam baseline path
+        shard = FrameShard(fused=os.environ.get("AGS_DIST", "fused") != "nccl")
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()                      # nvidia-smi takes a moment to start: launch it early
@@ -251,7 +253,8 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": "BASELINE config[1]: office0-shaped room, 200k Gaussian surfels, 640x480, "
                                "train-loop iteration (render 8 keyframes fwd+bwd, 4-term loss, Adam)",
                    "gaussians": N, "H": H, "W": W, "keyframes_per_gpu": B, "global_batch": Bg,
-                   "parallelism": f"frame-shard x{world}", "instances_per_step": inst, "visible_per_step": vis,
+                   "parallelism": f"frame-shard x{world}" + ("" if world == 1 else
+                                   (" fused NVLink RS+Adam+AG" if shard.fused else " NCCL all-reduce")), "instances_per_step": inst, "visible_per_step": vis,
                    "l2": "inputs+outputs per step (~%.0f MB) exceed the 126 MB L2; no explicit flush"
                          % ((88 * B * P + 136 * inst + 500 * N) / 1e6),
                    "loss_first": loss_first, "loss_last": loss_last},

@@ -176,6 +176,32 @@ typedef struct AgsAdamArgs {
 
 int ags_adam_step(const AgsAdamArgs* args);
 
+/* K9: fused reduce-scatter(gradients) -> Adam(on the owned shard) -> all-gather(parameters) over
+ * NVLink peer memory (new: the reference is single-GPU).  All ranks launch it between two cross-GPU
+ * barriers on the same stream.  grad / param / skip buffers are symmetric allocations; pass the peer
+ * pointers of all ranks (index = rank), optionally the NVLS multicast addresses (NULL = peer loop).
+ * The flat vector holds the AGS_ADAM_GROUPS parameter tensors back to back (numel[], lr[]), padded to
+ * numel_padded (multiple of 4*world); rank r updates [r*C, (r+1)*C), C = numel_padded/world. */
+#define AGS_MAX_PEERS 8
+typedef struct AgsDistAdamArgs {
+    int32_t world, rank;
+    int32_t num_groups;
+    int32_t step;                               /* 1-based */
+    const float* grad_peers[AGS_MAX_PEERS];
+    float* param_peers[AGS_MAX_PEERS];
+    const int32_t* skip_peers[AGS_MAX_PEERS];   /* per-rank overflow flags (may be NULL) */
+    const float* grad_multicast;                /* NVLS multicast address of the gradient buffer or NULL */
+    float* param_multicast;                     /* NVLS multicast address of the parameter buffer or NULL */
+    float* exp_avg;                             /* local, numel_padded */
+    float* exp_avg_sq;                          /* local, numel_padded */
+    int64_t numel[AGS_ADAM_GROUPS];
+    int64_t numel_padded;
+    float lr[AGS_ADAM_GROUPS];
+    float beta1, beta2, eps;
+    void* stream;
+} AgsDistAdamArgs;
+int ags_dist_adam_step(const AgsDistAdamArgs* args);
+
 const char* ags_last_error(void);
 int ags_version(void);
 
