@@ -29,12 +29,15 @@ class SymmetricFlat:
         self.numel_padded = (numel + q - 1) // q * q
         self.param = symm.empty(self.numel_padded, dtype=torch.float32, device=device)
         self.grad = symm.empty(self.numel_padded, dtype=torch.float32, device=device)
-        self.param.zero_(); self.grad.zero_()
+        self.stats = symm.empty(8, dtype=torch.int32, device=device)      # AgsRenderArgs.stats, peer readable
+        self.param.zero_(); self.grad.zero_(); self.stats.zero_()
         g = group if group is not None else dist.group.WORLD
         self.h_param = symm.rendezvous(self.param, g)
         self.h_grad = symm.rendezvous(self.grad, g)
+        self.h_stats = symm.rendezvous(self.stats, g)
         self.param_ptrs = [int(p) for p in self.h_param.buffer_ptrs]
         self.grad_ptrs = [int(p) for p in self.h_grad.buffer_ptrs]
+        self.stats_ptrs = [int(p) for p in self.h_stats.buffer_ptrs]
         mc = bool(self.h_param.has_multicast_support) if hasattr(self.h_param, "has_multicast_support") else False
         self.param_mc = int(self.h_param.multicast_ptr) if mc else 0
         self.grad_mc = int(self.h_grad.multicast_ptr) if mc else 0

@@ -111,12 +111,16 @@ class _TrainEngine:
         self.rb.inputs = [gm._means, gm._scales, gm._rotations, gm._opacities,
                           gm._harmonics.reshape(N, 3), self.conf]
         self.rb.view = [self.view, self.proj, self.tanfov, self.bg]
+        if self.fused:
+            self.rb.stats = self.flat.stats          # peers read the overflow flag through NVLink
         self.loss = None
         self.loss_out = None
         self.vis_count = torch.empty(H, W, device=dev, dtype=torch.int32) if dist_ctx else None
         W_ = dist_ctx.world if dist_ctx else 1
-        self.host = torch.empty(W_ * (2 * B + 4), dtype=torch.float32).pin_memory()
-        self.terms_all = torch.empty(W_ * (2 * B + 4), **o) if dist_ctx else None
+        self.nterm = 2 * B + 4 + 2                    # loss terms, per-frame perf, (instances, overflow)
+        self.host = torch.empty(W_ * self.nterm, dtype=torch.float32).pin_memory()
+        self.terms_all = torch.empty(W_ * self.nterm, **o) if dist_ctx else None
+        self.terms_loc = torch.empty(self.nterm, **o) if dist_ctx else None
         self.host_stats = torch.empty(L.AGS_NUM_STATS, dtype=torch.int32).pin_memory()
         self.event = torch.cuda.Event()
         self.fwd_args = self.rb._args()      # argument structs are built once: pointers never change
@@ -162,8 +166,10 @@ class _TrainEngine:
         L.check(lib.ags_render_forward(C.byref(fa)), "ags_render_forward")
         vis = None
         if self.dist is not None:
-            # every rank must take the same overflow decision: stats[0:2] = (instances, overflow) -> MAX
-            self.dist.all_reduce_max_(rb.stats[:2])
+            if not self.fused:
+                # every rank must take the same overflow decision: (instances, overflow) -> MAX.
+                # (the fused kernel reads the peers' flags itself; the host gets them via the gather)
+                self.dist.all_reduce_max_(rb.stats[:2])
             torch.sum(rb.opacity[:, 0] > 1e-3, dim=0, dtype=torch.int32, out=self.vis_count)
             self.dist.all_reduce_sum_(self.vis_count)
             vis = self.vis_count
@@ -174,10 +180,12 @@ class _TrainEngine:
         if self.dist is not None:
             # loss terms + per-frame performance of every rank, gathered on the stream before the
             # backward is enqueued: the host waits for this small copy only
-            self.dist.all_gather_into_(self.terms_all, lo.terms)
+            self.terms_loc[:self.nterm - 2].copy_(lo.terms)
+            self.terms_loc[self.nterm - 2:].copy_(rb.stats[:2])
+            self.dist.all_gather_into_(self.terms_all, self.terms_loc)
             self.host.copy_(self.terms_all, non_blocking=True)
         else:
-            self.host.copy_(lo.terms, non_blocking=True)
+            self.host[:self.nterm - 2].copy_(lo.terms, non_blocking=True)
         self.host_stats.copy_(rb.stats, non_blocking=True)
         self.event.record(torch.cuda.current_stream(self.dev))
         if self.grad_args is None:
@@ -209,8 +217,7 @@ class _TrainEngine:
             a.world, a.rank, a.num_groups = d.world, d.rank, len(self.params)
             for p in range(d.world):
                 a.grad_peers[p], a.param_peers[p] = f.grad_ptrs[p], f.param_ptrs[p]
-                a.skip_peers[p] = None
-            a.skip_peers[d.rank] = self.rb.stats.data_ptr() + 4 * L.STAT_OVERFLOW   # already the global MAX
+                a.skip_peers[p] = f.stats_ptrs[p] + 4 * L.STAT_OVERFLOW           # any rank's flag skips the step
             use_mc = d.use_multicast and f.grad_mc != 0 and f.param_mc != 0
             a.grad_multicast = f.grad_mc if use_mc else None
             a.param_multicast = f.param_mc if use_mc else None
@@ -232,10 +239,15 @@ class _TrainEngine:
         was just enqueued (the sampler needs them, mapping/utils.py:206-218)."""
         B = self.B
         self.event.synchronize()
-        h = self.host.clone().view(-1, 2 * B + 4)           # one row per rank
+        h = self.host.clone().view(-1, self.nterm)          # one row per rank
         terms = h[:, :4].sum(0)                             # every rank's terms are already / B_total
-        perf = (h[:, 4::2] + h[:, 5::2]).reshape(-1)        # ordered like the sampled ids
-        return terms, perf, self.host_stats.to(torch.int64)
+        pf = h[:, 4:4 + 2 * B]
+        perf = (pf[:, 0::2] + pf[:, 1::2]).reshape(-1)      # ordered like the sampled ids
+        stats = self.host_stats.to(torch.int64)
+        if self.dist is not None:                           # global view: max instances, any overflow
+            stats[L.STAT_INSTANCES] = int(h[:, self.nterm - 2].max())
+            stats[L.STAT_OVERFLOW] = int(h[:, self.nterm - 1].max())
+        return terms, perf, stats
 
 
 class GaussianMap:
