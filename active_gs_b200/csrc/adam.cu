@@ -23,29 +23,57 @@ struct AdamParams {
     const int* skip_flag;
 };
 
+// grid = (blocks, groups): blockIdx.y selects the parameter group, every thread owns quads of four
+// consecutive elements (128-bit accesses on the 16-byte aligned tensors; scalar tail).  The bias
+// corrections are computed once per block (double precision pow) and broadcast through smem.
 __global__ void __launch_bounds__(256)
 adam_kernel(AdamParams P, long long total) {
     if (P.skip_flag && *P.skip_flag != 0) return;
-    const int t = P.step_dev ? (*P.step_dev + 1) : P.step;
-    const double bc1 = 1.0 - pow((double)P.b1, (double)t);
-    const double bc2 = 1.0 - pow((double)P.b2, (double)t);
-    const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    __shared__ float s_c[2];
+    if (threadIdx.x == 0) {
+        const int t = P.step_dev ? (*P.step_dev + 1) : P.step;
+        const double bc1 = 1.0 - pow((double)P.b1, (double)t);
+        const double bc2 = 1.0 - pow((double)P.b2, (double)t);
+        s_c[0] = (float)(1.0 / sqrt(bc2));
+        s_c[1] = (float)(1.0 / bc1);
+    }
+    __syncthreads();
+    const float inv_sqrt_bc2 = s_c[0];
+    const int grp = blockIdx.y;
+    const long long n = P.end[grp] - (grp ? P.end[grp - 1] : 0);
+    const float step_size = P.lr[grp] * s_c[1];
+    float* __restrict__ p = P.p[grp];
+    const float* __restrict__ g = P.g[grp];
+    float* __restrict__ m = P.m[grp];
+    float* __restrict__ v = P.v[grp];
+    const float b1 = P.b1, b2 = P.b2, eps = P.eps;
+    const long long nq = n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        int grp = 0;
-        long long start = 0;
+    const bool aligned = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+    if (aligned) {
+        for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + q);
+            float4 m4 = reinterpret_cast<float4*>(m)[q], v4 = reinterpret_cast<float4*>(v)[q];
+            float4 p4 = reinterpret_cast<float4*>(p)[q];
+            const float* gg = &g4.x; float* mm = &m4.x; float* vv = &v4.x; float* pp = &p4.x;
 #pragma unroll
-        for (int k = 0; k < AGS_ADAM_GROUPS - 1; ++k)
-            if (k < P.groups - 1 && e >= P.end[k]) { grp = k + 1; start = P.end[k]; }
-        const long long i = e - start;
-        const float g = P.g[grp][i];
-        const float m = P.b1 * P.m[grp][i] + (1.f - P.b1) * g;
-        const float v = P.b2 * P.v[grp][i] + (1.f - P.b2) * g * g;
-        const float step_size = (float)((double)P.lr[grp] / bc1);
-        const float denom = sqrtf(v) * inv_sqrt_bc2 + P.eps;
-        P.m[grp][i] = m;
-        P.v[grp][i] = v;
-        P.p[grp][i] -= step_size * (m / denom);
+            for (int k = 0; k < 4; ++k) {
+                mm[k] = b1 * mm[k] + (1.f - b1) * gg[k];
+                vv[k] = b2 * vv[k] + (1.f - b2) * gg[k] * gg[k];
+                pp[k] -= step_size * (mm[k] / (sqrtf(vv[k]) * inv_sqrt_bc2 + eps));
+            }
+            reinterpret_cast<float4*>(m)[q] = m4;
+            reinterpret_cast<float4*>(v)[q] = v4;
+            reinterpret_cast<float4*>(p)[q] = p4;
+        }
+    }
+    const long long tail_from = aligned ? (nq << 2) : 0;
+    for (long long i = tail_from + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gi = g[i];
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        p[i] -= step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
     }
 }
 
@@ -82,10 +110,14 @@ extern "C" int ags_adam_step(const AgsAdamArgs* a) {
     if (total == 0) return 0;
     cudaStream_t st = (cudaStream_t)a->stream;
     const int threads = 256;
-    long long blocks = (total + threads - 1) / threads;
-    const long long max_blocks = 148LL * 16;          // 16 resident CTAs of 256 threads per SM
+    long long biggest = 0;
+    for (int k = 0; k < a->num_groups; ++k) biggest = a->numel[k] > biggest ? a->numel[k] : biggest;
+    long long blocks = (biggest / 4 + threads - 1) / threads;
+    const long long max_blocks = 148LL * 4;           // x groups in grid.y
     if (blocks > max_blocks) blocks = max_blocks;
-    adam_kernel<<<(int)blocks, threads, 0, st>>>(P, total);
+    if (blocks < 1) blocks = 1;
+    dim3 grid((unsigned)blocks, a->num_groups);
+    adam_kernel<<<grid, threads, 0, st>>>(P, total);
     AGS_CHECK_CUDA(cudaGetLastError());
     if (a->step_dev) {
         tick_kernel<<<1, 1, 0, st>>>(a->step_dev, a->skip_flag);

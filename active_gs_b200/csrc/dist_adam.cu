@@ -70,10 +70,16 @@ __global__ void __launch_bounds__(256)
 dist_adam_kernel(DistAdamParams P) {
     for (int p = 0; p < P.world; ++p)
         if (P.skip[p] && *reinterpret_cast<const volatile int*>(P.skip[p]) != 0) return;
-    const double bc1 = 1.0 - pow((double)P.b1, (double)P.step);
-    const double bc2 = 1.0 - pow((double)P.b2, (double)P.step);
-    const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
-    const float inv_bc1 = (float)(1.0 / bc1);
+    __shared__ float s_c[2];
+    if (threadIdx.x == 0) {                     // bias corrections once per block (double pow)
+        const double bc1 = 1.0 - pow((double)P.b1, (double)P.step);
+        const double bc2 = 1.0 - pow((double)P.b2, (double)P.step);
+        s_c[0] = (float)(1.0 / sqrt(bc2));
+        s_c[1] = (float)(1.0 / bc1);
+    }
+    __syncthreads();
+    const float inv_sqrt_bc2 = s_c[0];
+    const float inv_bc1 = s_c[1];
     const long long n4 = (P.shard_end - P.shard_begin + 3) / 4;        // shard is 4-aligned; tail padded
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
