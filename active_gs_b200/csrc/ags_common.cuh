@@ -26,13 +26,11 @@ struct AgsWorkspace {
     float4* feat1;      // (B*N) nx, ny, nz, confidence
     uint2* rect;        // (B*N) packed tile rect: x = minx | maxx<<16, y = miny | maxy<<16
     int32_t* vis_list;  // (B*N) compact list of visible pair indices v*N+i (count in counters[1])
-    int32_t* vis_ibase; // (B*N) per visible pair: first slot of its ranks in inst_rank
-    int32_t* inst_rank; // (inst_cap) rank of the instance inside its tile (returned by the counting atomic)
     float* dsplat;      // (B*N*16) per-view per-Gaussian gradient record (backward)
     int32_t* tile_count;   // (B*tiles)
     int32_t* tile_offset;  // (B*tiles)
     int32_t* tile_fill;    // (B*tiles)
-    int32_t* counters;     // (8) [0] = instance allocator, [1] = visible pairs, [2] = rank slots
+    int32_t* counters;     // (8) [0] = instance allocator, [1] = visible pairs
     uint64_t* inst_key;    // (inst_cap) depth_bits<<32 | gaussian id, grouped per tile
     uint64_t* inst_key_alt;// (inst_cap) ping-pong buffer for oversize tiles
     int32_t* inst_sorted;  // (inst_cap) gaussian ids, front-to-back per tile
@@ -57,8 +55,6 @@ inline AgsWorkspace ags_carve(void* base, int N, int B, int H, int W, int inst_c
     w.feat1 = (float4*)take(BN * 16);
     w.rect = (uint2*)take(BN * 8);
     w.vis_list = (int32_t*)take(BN * 4);
-    w.vis_ibase = (int32_t*)take(BN * 4);
-    w.inst_rank = (int32_t*)take((size_t)inst_cap * 4);
     w.dsplat = (float*)take(BN * 64);
     w.tile_count = (int32_t*)take(BT * 4);
     w.tile_offset = (int32_t*)take(BT * 4);

@@ -6,7 +6,7 @@
 //   2. alloc_kernel: block-scan of the counts + ONE atomic per block on a device allocator
 //      -> tile_offset (segments are contiguous per tile; their order in memory is irrelevant)
 //   3. scatter_kernel: every visible (view, Gaussian) writes key = depth_bits<<32 | id into its
-//      tiles' segments at offset + the rank K1's counting atomic returned (no atomics here) -> inst_key
+//      tiles' segments (slot claimed with an atomic)                       -> inst_key
 //   4. tile_sort_kernel: one CTA per tile sorts its segment in shared memory (bitonic on 64-bit
 //      keys; unique keys => deterministic, ties in depth resolved by Gaussian id exactly like the
 //      stable radix sort of the lineage).  Segments larger than the smem chunk are chunk-sorted and
@@ -74,12 +74,11 @@ scatter_kernel(AgsRenderArgs a, AgsWorkspace w) {
         const size_t tbase = (size_t)v * tiles_x * tiles_y;
         const float depth = w.feat0[idx].w;
         const uint64_t key = ((uint64_t)__float_as_uint(depth) << 32) | i;
-        const int32_t* rank = w.inst_rank + w.vis_ibase[e];      // ranks claimed by K1's counting atomics
-        int j = 0;
         for (int ty = miny; ty < maxy; ++ty)
-            for (int tx = minx; tx < maxx; ++tx, ++j) {
+            for (int tx = minx; tx < maxx; ++tx) {
                 const size_t t = tbase + (size_t)ty * tiles_x + tx;
-                w.inst_key[w.tile_offset[t] + rank[j]] = key;
+                const int slot = w.tile_offset[t] + atomicAdd(w.tile_fill + t, 1);
+                w.inst_key[slot] = key;
             }
     }
 }

@@ -189,7 +189,7 @@ constexpr int K1_PAIRS = K1_THREADS * K1_PER_THREAD;
 __global__ void __launch_bounds__(K1_THREADS)
 project_fwd_kernel(AgsRenderArgs a, AgsWorkspace w, int for_backward) {
     __shared__ Cam s_cam;                 // the view is uniform per block (blockIdx.y)
-    __shared__ int s_cand[K1_PAIRS], s_vis[K1_PAIRS], s_ibase[K1_PAIRS];
+    __shared__ int s_cand[K1_PAIRS], s_vis[K1_PAIRS];
     __shared__ int s_ncand, s_nvis, s_base;
     const int v = blockIdx.y;
     const int tid = threadIdx.x;
@@ -243,73 +243,39 @@ project_fwd_kernel(AgsRenderArgs a, AgsWorkspace w, int for_backward) {
     __syncthreads();
     // ---- phase 2: exact projection of the candidates
     const int ncand = s_ncand;
-    const int lane = tid & 31;
-    for (int c0 = 0; c0 < ncand; c0 += K1_THREADS) {
-        const int c = c0 + tid;
-        bool vis = false;
+    for (int c = tid; c < ncand; c += K1_THREADS) {
+        const int i = s_cand[c];
+        const size_t idx = vN + i;
+        GaussAct g;
+        activate(g, a, i);
         ViewProj p;
-        size_t idx = 0;
-        if (c < ncand) {
-            const int i = s_cand[c];
-            idx = vN + i;
-            GaussAct g;
-            activate(g, a, i);
-            project_view(p, g, cam, a.H, a.W, a.front_only != 0);
-            a.radii[idx] = p.valid ? p.radius : 0;
-            vis = p.valid;
-            if (vis) {
-                const float conf = a.confidences ? __ldg(a.confidences + i) : 0.f;
-                w.geom0[idx] = make_float4(p.xg, p.yg, p.ca, p.cb);
-                w.geom1[idx] = make_float4(p.cc, g.o, p.sx, p.sy);
-                w.feat0[idx] = make_float4(__ldg(a.colors + 3 * i), __ldg(a.colors + 3 * i + 1),
-                                           __ldg(a.colors + 3 * i + 2), p.t[2]);
-                w.feat1[idx] = make_float4(p.nv[0], p.nv[1], p.nv[2], conf);
-                w.rect[idx] = make_uint2((unsigned)p.minx | ((unsigned)p.maxx << 16),
-                                         (unsigned)p.miny | ((unsigned)p.maxy << 16));
-                if (for_backward) {
-                    float4* d = reinterpret_cast<float4*>(w.dsplat + idx * 16);
-                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    d[0] = z; d[1] = z; d[2] = z; d[3] = z;
-                }
-            }
+        project_view(p, g, cam, a.H, a.W, a.front_only != 0);
+        a.radii[idx] = p.valid ? p.radius : 0;
+        if (!p.valid) continue;
+        const float conf = a.confidences ? __ldg(a.confidences + i) : 0.f;
+        w.geom0[idx] = make_float4(p.xg, p.yg, p.ca, p.cb);
+        w.geom1[idx] = make_float4(p.cc, g.o, p.sx, p.sy);
+        w.feat0[idx] = make_float4(__ldg(a.colors + 3 * i), __ldg(a.colors + 3 * i + 1),
+                                   __ldg(a.colors + 3 * i + 2), p.t[2]);
+        w.feat1[idx] = make_float4(p.nv[0], p.nv[1], p.nv[2], conf);
+        w.rect[idx] = make_uint2((unsigned)p.minx | ((unsigned)p.maxx << 16),
+                                 (unsigned)p.miny | ((unsigned)p.maxy << 16));
+        if (for_backward) {
+            float4* d = reinterpret_cast<float4*>(w.dsplat + idx * 16);
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            d[0] = z; d[1] = z; d[2] = z; d[3] = z;
         }
-        // rank slots of the warp's visible pairs: warp prefix sum of the tile counts, one atomic per warp
-        const int nt = vis ? (p.maxx - p.minx) * (p.maxy - p.miny) : 0;
-        int incl = nt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int up = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += up;
-        }
-        const int wtot = __shfl_sync(0xffffffffu, incl, 31);
-        int wbase = 0;
-        if (lane == 31 && wtot) wbase = atomicAdd(w.counters + 2, wtot);
-        wbase = __shfl_sync(0xffffffffu, wbase, 31);
-        if (vis) {
-            const int ibase = wbase + incl - nt;
-            // the counting atomic returns this instance's rank inside its tile: the scatter needs no
-            // atomics.  Slots beyond the capacity are dropped (the overflow flag stops the pipeline).
-            int32_t* tc = w.tile_count + (size_t)v * tiles_x * tiles_y;
-            int j = 0;
-            for (int ty = p.miny; ty < p.maxy; ++ty)
-                for (int tx = p.minx; tx < p.maxx; ++tx, ++j) {
-                    const int rank = atomicAdd(tc + ty * tiles_x + tx, 1);
-                    if (ibase + j < a.inst_cap) w.inst_rank[ibase + j] = rank;
-                }
-            const int slot = atomicAdd(&s_nvis, 1);
-            s_vis[slot] = (int)idx;
-            s_ibase[slot] = ibase;
-        }
+        int32_t* tc = w.tile_count + (size_t)v * tiles_x * tiles_y;
+        for (int ty = p.miny; ty < p.maxy; ++ty)
+            for (int tx = p.minx; tx < p.maxx; ++tx) atomicAdd(tc + ty * tiles_x + tx, 1);
+        s_vis[atomicAdd(&s_nvis, 1)] = (int)idx;
     }
     __syncthreads();
     // ---- phase 3: append to the global visible list
     const int nvis = s_nvis;
     if (tid == 0) s_base = nvis ? atomicAdd(w.counters + 1, nvis) : 0;
     __syncthreads();
-    for (int c = tid; c < nvis; c += K1_THREADS) {
-        w.vis_list[s_base + c] = s_vis[c];
-        w.vis_ibase[s_base + c] = s_ibase[c];
-    }
+    for (int c = tid; c < nvis; c += K1_THREADS) w.vis_list[s_base + c] = s_vis[c];
 }
 
 // K6 ---------------------------------------------------------------------------------------------
@@ -346,7 +312,7 @@ project_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
         project_view(p, g, cam, a.H, a.W, false);
         float4* dr = reinterpret_cast<float4*>(w.dsplat + idx * 16);
         const float4 d0 = dr[0], d1 = dr[1], d2 = dr[2], d3 = dr[3];
-        {   // consume-and-clear: a second backward on the same forward starts from zero again
+        if (gr.clear_records) {   // consume-and-clear: a second backward on the same forward starts from zero again
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             dr[0] = z; dr[1] = z; dr[2] = z; dr[3] = z;
         }

@@ -196,6 +196,7 @@ class _TrainEngine:
                 L.ptr(t) for t in self.grads]
             g.d_means2D = None
             g.accumulate = 0
+            g.clear_records = 0                 # exactly one backward per forward in this loop
             self.grad_args = g
         L.check(lib.ags_render_backward(C.byref(fa), C.byref(self.grad_args)), "ags_render_backward")
         self.step += 1

@@ -38,7 +38,7 @@ class RenderGradArgs(C.Structure):
     _fields_ = [
         ("d_rgb", _f), ("d_normal", _f), ("d_depth", _f), ("d_opacity", _f), ("d_confidence", _f),
         ("d_means3D", _f), ("d_scales", _f), ("d_rotations", _f), ("d_opacities", _f),
-        ("d_colors", _f), ("d_means2D", _f), ("accumulate", C.c_int32),
+        ("d_colors", _f), ("d_means2D", _f), ("accumulate", C.c_int32), ("clear_records", C.c_int32),
     ]
 
 

@@ -148,6 +148,7 @@ class RenderBatch:
         g.d_means3D, g.d_scales, g.d_rotations = L.ptr(dm), L.ptr(ds), L.ptr(dr)
         g.d_opacities, g.d_colors, g.d_means2D = L.ptr(do), L.ptr(dc), L.ptr(dm2)
         g.accumulate = 0
+        g.clear_records = 1
         L.check(lib.ags_render_backward(C.byref(self._args()), C.byref(g)), "ags_render_backward")
         return dm, ds, dr, do, dc, dm2
 

@@ -106,6 +106,8 @@ typedef struct AgsRenderGradArgs {
     float* d_colors;               /* (N,3) */
     float* d_means2D;              /* (B,N,3) pixel-space mean gradient, or NULL */
     int32_t accumulate;            /* 0: overwrite the d_* outputs, 1: add to them */
+    int32_t clear_records;         /* 1: leave the workspace ready for another backward on the same forward
+                                      (autograd may call it twice); 0: one backward per forward (training loop) */
 } AgsRenderGradArgs;
 
 size_t ags_scratch_bytes(int32_t N, int32_t B, int32_t H, int32_t W, int32_t inst_cap);

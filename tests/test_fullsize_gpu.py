@@ -55,8 +55,7 @@ def workspace_views(rb):
     al = lambda x: (x + 255) & ~255
     off = rb.ws_ptr - rb.workspace.data_ptr()
     sizes = [("geom0", B * N * 16), ("geom1", B * N * 16), ("feat0", B * N * 16), ("feat1", B * N * 16),
-             ("rect", B * N * 8), ("vis_list", B * N * 4), ("vis_ibase", B * N * 4), ("inst_rank", cap * 4),
-             ("dsplat", B * N * 64), ("tile_count", B * tiles * 4),
+             ("rect", B * N * 8), ("vis_list", B * N * 4), ("dsplat", B * N * 64), ("tile_count", B * tiles * 4),
              ("tile_offset", B * tiles * 4), ("tile_fill", B * tiles * 4), ("counters", 32),
              ("inst_key", cap * 8), ("inst_key_alt", cap * 8), ("inst_sorted", cap * 4),
              ("final_T", B * H * W * 4), ("n_contrib", B * H * W * 4)]
