@@ -169,6 +169,23 @@ __device__ __forceinline__ void project_view(ViewProj& o, const GaussAct& g, con
     if (!(o.xg == o.xg) || !(o.yg == o.yg) || !(rf == rf)) valid = false;   // NaN guard
     o.valid = valid;
     if (!valid) o.radius = 0;
+    // Tight tile range (output preserving): inside the 3-sigma rect only tiles that the splat's cutoff
+    // box reaches can hold a pixel with alpha >= 1/255 (alpha = o*exp(-q/2) >= 1/255 <=> q <= 2 ln(255 o),
+    // extent along x = sqrt(tau * cov_xx)); the other tiles never see a contribution, so they get no
+    // instance.  Conservative margins as in the compositing kernels' warp-level test.
+    if (valid) {
+        const float tau = 2.f * __logf(255.f * g.o);
+        if (!(tau > 0.f)) {
+            o.maxx = o.minx; o.maxy = o.miny;                // contributes nowhere: zero instances
+        } else {
+            const float hx = sqrtf(tau * o.a) * 1.0001f + 1e-2f, hy = sqrtf(tau * o.c) * 1.0001f + 1e-2f;
+            // tile t covers pixel centres [16t, 16t+15]
+            const int bx0 = (int)floorf((o.xg - hx) / TILE), bx1 = (int)floorf((o.xg + hx) / TILE) + 1;
+            const int by0 = (int)floorf((o.yg - hy) / TILE), by1 = (int)floorf((o.yg + hy) / TILE) + 1;
+            o.minx = max(o.minx, min(bx0, o.maxx)); o.maxx = min(o.maxx, max(bx1, o.minx));
+            o.miny = max(o.miny, min(by0, o.maxy)); o.maxy = min(o.maxy, max(by1, o.miny));
+        }
+    }
 }
 
 // K1 ---------------------------------------------------------------------------------------------

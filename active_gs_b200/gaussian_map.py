@@ -92,8 +92,15 @@ class _TrainEngine:
                     gm.cfg.optimizer.opacity_lr, gm.cfg.optimizer.harmonic_lr]
         self.step = 0
         self.conf = gm.get_confidences.contiguous()
-        self.rgb_gt = torch.empty(B, 3, H, W, **o)
-        self.depth_gt = torch.empty(B, 1, H, W, **o)
+        # ground-truth staging is double buffered: with host-resident keyframes the H2D of step i+1
+        # runs on a copy stream while backward/Adam of step i and the forward of step i+1 execute
+        # (only the loss kernel reads the ground truth)
+        self.gt = [(torch.empty(B, 3, H, W, **o), torch.empty(B, 1, H, W, **o)) for _ in range(2)]
+        self.gt_k = 0
+        self.rgb_gt, self.depth_gt = self.gt[0]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.copy_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.copy_pending = False
         # camera blocks of the batch: one flat device buffer [B*16 view | B*16 proj | B*2 tanfov]
         # refreshed by ONE small H2D copy per iteration from a pinned staging buffer
         self.cam_flat = torch.empty(B * 34, **o)
@@ -124,7 +131,8 @@ class _TrainEngine:
         self.host_stats = torch.empty(L.AGS_NUM_STATS, dtype=torch.int32).pin_memory()
         self.event = torch.cuda.Event()
         self.fwd_args = self.rb._args()      # argument structs are built once: pointers never change
-        self.grad_args = None
+        self.grad_args = [None, None]        # one per ground-truth buffer (each has its own loss outputs)
+        self.loss_outs = [None, None]
         self.adam_cache = {}
         self.dist_args = None
 
@@ -134,13 +142,20 @@ class _TrainEngine:
         this the per-step H2D of the end-to-end path; device frames are gathered with one stack
         kernel per tensor."""
         B = self.B
+        self.gt_k ^= 1
+        self.rgb_gt, self.depth_gt = self.gt[self.gt_k]
         if rgbs[0].is_cuda:
             torch.stack(rgbs, out=self.rgb_gt)
             torch.stack(depths, out=self.depth_gt)
+            self.copy_pending = False
         else:
-            for k in range(B):
-                self.rgb_gt[k].copy_(rgbs[k], non_blocking=True)
-                self.depth_gt[k].copy_(depths[k], non_blocking=True)
+            # buffer gt_k was last read by the loss of step i-2, which finished before fetch(i-1)
+            with torch.cuda.stream(self.copy_stream):
+                for k in range(B):
+                    self.rgb_gt[k].copy_(rgbs[k], non_blocking=True)
+                    self.depth_gt[k].copy_(depths[k], non_blocking=True)
+                self.copy_done[self.gt_k].record(self.copy_stream)
+            self.copy_pending = True
         h = self.cam_host
         torch.index_select(views_h, 0, idx, out=h[:B * 16].view(B, 16))
         torch.index_select(projs_h, 0, idx, out=h[B * 16:B * 32].view(B, 16))
@@ -173,10 +188,12 @@ class _TrainEngine:
             torch.sum(rb.opacity[:, 0] > 1e-3, dim=0, dtype=torch.int32, out=self.vis_count)
             self.dist.all_reduce_sum_(self.vis_count)
             vis = self.vis_count
-        self.loss_out = ops.loss_forward_backward(
+        if self.copy_pending:
+            torch.cuda.current_stream(self.dev).wait_event(self.copy_done[self.gt_k])
+        self.loss_outs[self.gt_k] = ops.loss_forward_backward(
             rb.rgb, rb.normal, rb.depth, rb.opacity, self.rgb_gt, self.depth_gt, self.tanfov,
-            B_total=self.B_total, vis_count=vis, out=self.loss_out)
-        lo = self.loss_out
+            B_total=self.B_total, vis_count=vis, out=self.loss_outs[self.gt_k])
+        lo = self.loss_out = self.loss_outs[self.gt_k]
         if self.dist is not None:
             # loss terms + per-frame performance of every rank, gathered on the stream before the
             # backward is enqueued: the host waits for this small copy only
@@ -188,7 +205,7 @@ class _TrainEngine:
             self.host[:self.nterm - 2].copy_(lo.terms, non_blocking=True)
         self.host_stats.copy_(rb.stats, non_blocking=True)
         self.event.record(torch.cuda.current_stream(self.dev))
-        if self.grad_args is None:
+        if self.grad_args[self.gt_k] is None:
             g = L.RenderGradArgs()
             g.d_rgb, g.d_normal, g.d_depth = L.ptr(lo.d_rgb), L.ptr(lo.d_normal), L.ptr(lo.d_depth)
             g.d_opacity = g.d_confidence = None
@@ -197,8 +214,8 @@ class _TrainEngine:
             g.d_means2D = None
             g.accumulate = 0
             g.clear_records = 0                 # exactly one backward per forward in this loop
-            self.grad_args = g
-        L.check(lib.ags_render_backward(C.byref(fa), C.byref(self.grad_args)), "ags_render_backward")
+            self.grad_args[self.gt_k] = g
+        L.check(lib.ags_render_backward(C.byref(fa), C.byref(self.grad_args[self.gt_k])), "ags_render_backward")
         self.step += 1
         if self.fused:
             self._fused_exchange_and_adam(lib, st)

@@ -146,8 +146,9 @@ def stage_profile(eng, reps=5):
         for k, stage in enumerate([0, 1, 2, 3]):
             L.check(lib.ags_render_stage(C.byref(a), None, stage), "stage")
             ev[k + 1].record(st)
-        eng.loss_out = ops.loss_forward_backward(rb.rgb, rb.normal, rb.depth, rb.opacity, eng.rgb_gt, eng.depth_gt,
-                                                 eng.tanfov, B_total=eng.B_total, out=eng.loss_out)
+        eng.loss_out = eng.loss_outs[eng.gt_k] = ops.loss_forward_backward(
+            rb.rgb, rb.normal, rb.depth, rb.opacity, eng.rgb_gt, eng.depth_gt, eng.tanfov, B_total=eng.B_total,
+            out=eng.loss_outs[eng.gt_k])
         ev[5].record(st)
         lo = eng.loss_out
         g = L.RenderGradArgs()
