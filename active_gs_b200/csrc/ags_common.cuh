@@ -15,6 +15,9 @@
 #define AGS_ALPHA_MIN (1.0f / 255.0f)
 #define AGS_T_EPS 1e-4f
 #define AGS_SLOPE_COS_MIN 0.1f
+// tiles with at most this many instances are depth-sorted inside composite_fwd's prologue (keys alias
+// the 20 KB staging buffer); larger tiles go through tile_sort_kernel first
+#define AGS_FUSED_SORT_MAX 2048
 
 // ------------------------------------------------------------------------------------------------
 // Workspace layout (all offsets 256-byte aligned). One workspace serves one batch of B views and

@@ -7,10 +7,11 @@
 //      -> tile_offset (segments are contiguous per tile; their order in memory is irrelevant)
 //   3. scatter_kernel: every visible (view, Gaussian) writes key = depth_bits<<32 | id into its
 //      tiles' segments (slot claimed with an atomic)                       -> inst_key
-//   4. tile_sort_kernel: one CTA per tile sorts its segment in shared memory (bitonic on 64-bit
-//      keys; unique keys => deterministic, ties in depth resolved by Gaussian id exactly like the
-//      stable radix sort of the lineage).  Segments larger than the smem chunk are chunk-sorted and
-//      then merged through a ping-pong buffer (rank-by-binary-search merge).   -> inst_sorted
+//   4. depth sort per tile (bitonic on 64-bit keys in shared memory; unique keys => deterministic, ties
+//      in depth resolved by Gaussian id exactly like the stable radix sort of the lineage).  Tiles with
+//      <= AGS_FUSED_SORT_MAX instances are sorted in the PROLOGUE of composite_fwd (composite.cu), where
+//      the barrier latency hides behind other CTAs' compositing; tile_sort_kernel only handles larger
+//      tiles: chunk sort + rank-by-binary-search merges through a ping-pong buffer.   -> inst_sorted
 // Everything is sized by device-side counters; when the batch needs more than inst_cap instances the
 // overflow flag is raised and all later kernels render empty tiles.
 #include "ags_common.cuh"
@@ -19,7 +20,6 @@ namespace {
 
 constexpr int SORT_CHUNK = 4096;
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_SMALL = 256;          // tiles up to this size are sorted by ONE warp
 
 __global__ void __launch_bounds__(256)
 alloc_kernel(AgsWorkspace w, int n_tiles_total, int inst_cap, int32_t* stats) {
@@ -98,47 +98,13 @@ __device__ __forceinline__ void bitonic_smem(uint64_t* s, int m) {
     }
 }
 
-// Small tiles (the common case: ~80 instances): one WARP per tile, 8 tiles per CTA, bitonic network
-// in the warp's private slice of shared memory with __syncwarp only -- no CTA barriers.
-__global__ void __launch_bounds__(256)
-tile_sort_small_kernel(AgsWorkspace w, int n_tiles_total, int inst_cap) {
-    __shared__ uint64_t s_all[8][SORT_SMALL];
-    if (w.counters[0] > inst_cap) return;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int t = blockIdx.x * 8 + wid;
-    if (t >= n_tiles_total) return;
-    const int n = w.tile_count[t];
-    if (n == 0 || n > SORT_SMALL) return;
-    const int off = w.tile_offset[t];
-    const uint64_t* keys = w.inst_key + off;
-    int32_t* out = w.inst_sorted + off;
-    uint64_t* s = s_all[wid];
-    int m = 2;
-    while (m < n) m <<= 1;
-    for (int k = lane; k < m; k += 32) s[k] = (k < n) ? keys[k] : ~0ull;
-    __syncwarp();
-    for (int k = 2; k <= m; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int q = lane; q < (m >> 1); q += 32) {
-                const int lo = ((q & ~(j - 1)) << 1) | (q & (j - 1));
-                const int hi = lo | j;
-                const bool asc = ((lo & k) == 0);
-                const uint64_t x = s[lo], y = s[hi];
-                if ((x > y) == asc) { s[lo] = y; s[hi] = x; }
-            }
-            __syncwarp();
-        }
-    }
-    for (int k = lane; k < n; k += 32) out[k] = (int32_t)(s[k] & 0xffffffffu);
-}
-
 __global__ void __launch_bounds__(SORT_THREADS)
 tile_sort_kernel(AgsWorkspace w, int inst_cap) {
     __shared__ uint64_t s[SORT_CHUNK];
     if (w.counters[0] > inst_cap) return;
     const int t = blockIdx.x;
     const int n = w.tile_count[t];
-    if (n <= SORT_SMALL) return;             // handled by tile_sort_small_kernel
+    if (n <= AGS_FUSED_SORT_MAX) return;     // sorted in the prologue of composite_fwd
     const int off = w.tile_offset[t];
     uint64_t* keys = w.inst_key + off;
     int32_t* out = w.inst_sorted + off;
@@ -198,8 +164,8 @@ int ags_launch_binning(const AgsRenderArgs& a, const AgsWorkspace& w) {
         scatter_kernel<<<(int)blocks, 256, 0, st>>>(a, w);
         AGS_CHECK_CUDA(cudaGetLastError());
     }
-    tile_sort_small_kernel<<<(nt + 7) / 8, 256, 0, st>>>(w, nt, a.inst_cap);
-    AGS_CHECK_CUDA(cudaGetLastError());
+    // only tiles with more than AGS_FUSED_SORT_MAX instances are sorted here (chunk sort + merge);
+    // all others are sorted in the prologue of composite_fwd
     tile_sort_kernel<<<nt, SORT_THREADS, 0, st>>>(w, a.inst_cap);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;

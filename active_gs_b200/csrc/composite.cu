@@ -19,6 +19,7 @@
 namespace {
 
 constexpr int BATCH = 256;
+constexpr int FUSED_SORT_MAX = AGS_FUSED_SORT_MAX;   // 64-bit keys that fit the staging buffer (20 KB)
 
 // one staged splat in shared memory: 80 B, read with 128-bit broadcast loads at immediate offsets
 struct __align__(16) SplatRec {
@@ -92,7 +93,10 @@ __device__ __forceinline__ bool bbox_hits(const float4 bb, const WarpBlock& b) {
 // K4 ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
-    __shared__ SplatRec s_rec[BATCH];
+    // shared memory: the staging records; the same bytes first serve the tile's depth sort
+    __shared__ __align__(16) unsigned char s_raw[sizeof(SplatRec) * BATCH];
+    SplatRec* s_rec = reinterpret_cast<SplatRec*>(s_raw);
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_raw);
     __shared__ int s_id[BATCH];
     const int v = blockIdx.z;
     const int tiles_x = gridDim.x, tiles_y = gridDim.y;
@@ -107,6 +111,31 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
     const bool overflow = w.counters[0] > a.inst_cap;
     const int n = overflow ? 0 : w.tile_count[gt];
     const int off = overflow ? 0 : w.tile_offset[gt];
+    // ---- prologue: depth sort of this tile's instance keys (K3 fused here: its barrier latency hides
+    // behind the compositing of the other resident CTAs).  Keys (depth_bits<<32 | id) are unique, so
+    // the bitonic network is deterministic; ids go to inst_sorted for the batches below and for the
+    // backward.  Tiles above the shared-memory capacity were sorted by tile_sort_kernel beforehand.
+    if (n > 0 && n <= FUSED_SORT_MAX) {
+        const uint64_t* keys = w.inst_key + off;
+        int m = 2;
+        while (m < n) m <<= 1;
+        for (int k = tid; k < m; k += 256) s_keys[k] = (k < n) ? keys[k] : ~0ull;
+        __syncthreads();
+        for (int kk = 2; kk <= m; kk <<= 1) {
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (m >> 1); t += 256) {
+                    const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int hi = lo | j;
+                    const bool asc = ((lo & kk) == 0);
+                    const uint64_t x = s_keys[lo], y = s_keys[hi];
+                    if ((x > y) == asc) { s_keys[lo] = y; s_keys[hi] = x; }
+                }
+                __syncthreads();
+            }
+        }
+        for (int k = tid; k < n; k += 256) w.inst_sorted[off + k] = (int32_t)(s_keys[k] & 0xffffffffu);
+        __syncthreads();            // ids visible to the whole CTA; s_raw free for the records
+    }
     const size_t vN = (size_t)v * a.N;
     const size_t P = (size_t)a.H * a.W;
     const size_t pix = (size_t)py * a.W + px;
