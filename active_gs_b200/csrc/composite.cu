@@ -119,18 +119,40 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
         const uint64_t* keys = w.inst_key + off;
         int m = 2;
         while (m < n) m <<= 1;
-        for (int k = tid; k < m; k += 256) s_keys[k] = (k < n) ? keys[k] : ~0ull;
-        __syncthreads();
-        for (int kk = 2; kk <= m; kk <<= 1) {
-            for (int j = kk >> 1; j > 0; j >>= 1) {
-                for (int t = tid; t < (m >> 1); t += 256) {
-                    const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                    const int hi = lo | j;
-                    const bool asc = ((lo & kk) == 0);
-                    const uint64_t x = s_keys[lo], y = s_keys[hi];
-                    if ((x > y) == asc) { s_keys[lo] = y; s_keys[hi] = x; }
+        if (m <= 512) {
+            // small tile (the common case): ONE warp runs the network with __syncwarp only; the other
+            // seven warps wait at the barrier below without consuming issue slots
+            if (tid < 32) {
+                for (int k = lane; k < m; k += 32) s_keys[k] = (k < n) ? keys[k] : ~0ull;
+                __syncwarp();
+                for (int kk = 2; kk <= m; kk <<= 1) {
+                    for (int j = kk >> 1; j > 0; j >>= 1) {
+                        for (int t = lane; t < (m >> 1); t += 32) {
+                            const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                            const int hi = lo | j;
+                            const bool asc = ((lo & kk) == 0);
+                            const uint64_t x = s_keys[lo], y = s_keys[hi];
+                            if ((x > y) == asc) { s_keys[lo] = y; s_keys[hi] = x; }
+                        }
+                        __syncwarp();
+                    }
                 }
-                __syncthreads();
+            }
+            __syncthreads();
+        } else {
+            for (int k = tid; k < m; k += 256) s_keys[k] = (k < n) ? keys[k] : ~0ull;
+            __syncthreads();
+            for (int kk = 2; kk <= m; kk <<= 1) {
+                for (int j = kk >> 1; j > 0; j >>= 1) {
+                    for (int t = tid; t < (m >> 1); t += 256) {
+                        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                        const int hi = lo | j;
+                        const bool asc = ((lo & kk) == 0);
+                        const uint64_t x = s_keys[lo], y = s_keys[hi];
+                        if ((x > y) == asc) { s_keys[lo] = y; s_keys[hi] = x; }
+                    }
+                    __syncthreads();
+                }
             }
         }
         for (int k = tid; k < n; k += 256) w.inst_sorted[off + k] = (int32_t)(s_keys[k] & 0xffffffffu);
