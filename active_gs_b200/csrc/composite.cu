@@ -119,7 +119,7 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
         const uint64_t* keys = w.inst_key + off;
         int m = 2;
         while (m < n) m <<= 1;
-        if (m <= 512) {
+        if (m <= 128) {
             // small tile (the common case): ONE warp runs the network with __syncwarp only; the other
             // seven warps wait at the barrier below without consuming issue slots
             if (tid < 32) {
