@@ -27,6 +27,8 @@ static int check_render_args(const AgsRenderArgs* a) {
     AGS_CHECK_ARG((a->W + TILE - 1) / TILE < 65536 && (a->H + TILE - 1) / TILE < 65536, "image too large");
     AGS_CHECK_ARG(a->param_mode == AGS_PARAMS_ACTIVATED || a->param_mode == AGS_PARAMS_RAW, "bad param_mode %d", a->param_mode);
     AGS_CHECK_ARG(a->inst_cap >= 0, "negative inst_cap");
+    AGS_CHECK_ARG((long long)a->B * a->N < 2147483647LL, "B*N = %lld does not fit the 32-bit pair index",
+                  (long long)a->B * a->N);
     if (a->N > 0)
         AGS_CHECK_ARG(a->means3D && a->scales && a->rotations && a->opacities && a->colors,
                       "NULL per-Gaussian input");

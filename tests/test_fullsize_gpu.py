@@ -194,3 +194,48 @@ def test_update_loop_spawn_train_prune():
     assert psnrs[-1] > 20.0 and min(psnrs) > 15.0
     l0, l1 = gm.last_train_log[0][0], gm.last_train_log[-1][0]
     assert l1 < l0
+
+
+def test_planner_shaped_batch_100_views_128():
+    """the planners render ~100 candidate views at 128x128 per step, forward only
+    (planning/confidence.py:15-46).  One GaussianRenderer call = one launch chain for all views;
+    every view must equal the same view rendered alone."""
+    dev = _dev()
+    from active_gs_b200 import operations as O
+    from active_gs_b200.gaussian_map import GaussianMap
+    box, H, W, N, V = (6.0, 4.5, 2.7), 128, 128, 100000, 100
+    st = syn.make_room_scene(N, box=box, seed=21)
+    gm = GaussianMap(default_gaussian_map_config(), dev)
+    for k, v in st.items():
+        setattr(gm, k if k.startswith("view_") else "_" + k, v.to(dev))
+    ext, K = syn.make_cameras(V, box=box, H=H, W=W, hfov=60.0, seed=22)
+    with torch.no_grad():
+        r = O.GaussianRenderer(ext.to(dev), K.to(dev), gm.get_attr(), gm.background_color, (0.001, 10.0), (H, W), dev)
+        all_ = r.render_view_all()
+        assert all_[0].shape == (V, 3, H, W) and all_[8].shape == (N,)
+        assert torch.isfinite(all_[0]).all() and float(all_[3].max()) <= 1 + 1e-6
+        for i in (0, 37, 99):
+            one = r.render_view(i)
+            for k in range(6):
+                assert torch.equal(one[k], all_[k][i]), (i, k)
+        # confidence map is a blend of per-Gaussian confidences in [0,1]
+        assert float(all_[5].min()) >= 0 and float(all_[5].max()) <= 1 + 1e-5
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    """mapping/gaussian_map.py:491-527: the .th dict keeps the reference's keys and raw tensors."""
+    dev = _dev()
+    from active_gs_b200.gaussian_map import GaussianMap
+    st = syn.make_room_scene(5000, seed=3)
+    gm = GaussianMap(default_gaussian_map_config(), dev)
+    for k, v in st.items():
+        setattr(gm, k if k.startswith("view_") else "_" + k, v.to(dev))
+    gm.save(str(tmp_path), index=7)
+    d = torch.load(tmp_path / "map_7.th", weights_only=False)
+    assert set(d.keys()) == {"means", "scales", "harmonics", "opacities", "rotations", "view_scores", "view_supports",
+                             "view_means", "near", "far", "use_view_direction", "background_color", "scale_factor"}
+    g2 = GaussianMap(default_gaussian_map_config(), dev)
+    g2.load(str(tmp_path / "map_7.th"))
+    for a, b in zip(gm.get_params(), g2.get_params()):
+        assert torch.equal(a, b)
+    assert g2.is_init and g2.scene_far == 10.0
