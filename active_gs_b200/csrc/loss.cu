@@ -36,8 +36,8 @@ struct FrameGeom {       // per-frame constants of depth2normal (quirk Q2)
 
 __device__ __forceinline__ FrameGeom frame_geom(const float* tanfov, int f, int H, int W) {
     FrameGeom g;
-    g.ik00 = (2.f * __ldg(tanfov + 2 * f)) / (float)H;
-    g.ik11 = (2.f * __ldg(tanfov + 2 * f + 1)) / (float)W;
+    g.ik00 = 2.f * __ldg(tanfov + 2 * f) * (1.f / (float)H);      // 1/H, 1/W fold to constants per launch
+    g.ik11 = 2.f * __ldg(tanfov + 2 * f + 1) * (1.f / (float)W);
     g.cx = 0.5f * W;
     g.cy = 0.5f * H;
     return g;
@@ -117,12 +117,21 @@ __device__ __forceinline__ float vis_sum(const AgsLossArgs& a, size_t P, int p) 
     return m;
 }
 
+// pre-pass: per-pixel visibility count over the frames of this call (quirk Q1), once per pixel
+__global__ void __launch_bounds__(256)
+loss_vis_count(AgsLossArgs a, float* __restrict__ msum_plane) {
+    const size_t P = (size_t)a.H * a.W;
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    msum_plane[p] = vis_sum(a, P, (int)p);
+}
+
 // pass A: one thread per (pixel, frame).  Writes normal_unit, d2n, d_rgb, the pixel's own depth
 // gradient (L1 term + its share of the depth2normal adjoint) and the four contributions it makes
 // to its neighbours' depth gradients as four planes (up, left, bottom, right) that pass B gathers:
 // no atomics, deterministic.
 __global__ void __launch_bounds__(256)
-loss_pass_a(AgsLossArgs a, float* __restrict__ nb, float* __restrict__ msum_plane) {
+loss_pass_a(AgsLossArgs a, float* __restrict__ nb, const float* __restrict__ msum_plane) {
     const int H = a.H, W = a.W;
     const size_t P = (size_t)H * W;
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
@@ -135,8 +144,7 @@ loss_pass_a(AgsLossArgs a, float* __restrict__ nb, float* __restrict__ msum_plan
     const float inv_cons = 1.f / (Bt * Bt * (float)P);
     float fr_rgb = 0.f, fr_d = 0.f, acc_cons = 0.f;
     if (in) {
-        const float msum = vis_sum(a, P, p);
-        if (f == 0) msum_plane[p] = msum;
+        const float msum = __ldg(msum_plane + p);
         const float* opac = a.opacity + (size_t)f * P;
         const float* depth = a.depth + (size_t)f * P;
         float* ddep = a.d_depth + (size_t)f * P;
@@ -164,16 +172,15 @@ loss_pass_a(AgsLossArgs a, float* __restrict__ nb, float* __restrict__ msum_plan
         // ---- unit normal
         const float* np_ = a.normal + (size_t)f * 3 * P + p;
         const F3 n = f3(__ldg(np_), __ldg(np_ + P), __ldg(np_ + 2 * P));
-        const float nn = fmaxf(sqrtf(dot(n, n)), 1e-12f);
-        const F3 nu = n * (m2 / nn);
+        const F3 nu = n * (m2 * rsqrtf(fmaxf(dot(n, n), 1e-24f)));
         float* no = a.normal_unit + (size_t)f * 3 * P + p;
         no[0] = nu.x; no[P] = nu.y; no[2 * P] = nu.z;
         // ---- depth2normal
         const FrameGeom g = frame_geom(a.tanfov, f, H, W);
         const D2N v = d2n_vectors(depth, opac, g, H, W, y, x);
         const F3 ns = cross(v.pu, v.pl) + cross(v.pr, v.pu) + cross(v.pb, v.pr) + cross(v.pl, v.pb);
-        const float nsn = fmaxf(sqrtf(dot(ns, ns)), 1e-12f);
-        const F3 u = ns * (1.f / nsn);
+        const float insn = rsqrtf(fmaxf(dot(ns, ns), 1e-24f));
+        const F3 u = ns * insn;
         const F3 d2n = u * m2;
         float* dn = a.d2n + (size_t)f * 3 * P + p;
         dn[0] = d2n.x; dn[P] = d2n.y; dn[2 * P] = d2n.z;
@@ -182,7 +189,7 @@ loss_pass_a(AgsLossArgs a, float* __restrict__ nb, float* __restrict__ msum_plan
         if (m2 > 0.f && msum > 0.f) {
             const float wc = -a.w_cons * msum * inv_cons;                // dL/d(nu . d2n)
             const F3 gd = nu * wc;                                       // dL/d u  (d2n = u*m2, m2 = 1)
-            const F3 gq = (gd - u * dot(u, gd)) * (1.f / nsn);
+            const F3 gq = (gd - u * dot(u, gd)) * insn;
             const F3 dpu = (cross(v.pl, gq) + cross(gq, v.pr)) * v.mu;
             const F3 dpl = (cross(gq, v.pu) + cross(v.pb, gq)) * v.ml;
             const F3 dpb = (cross(v.pr, gq) + cross(gq, v.pl)) * v.mb;
@@ -278,9 +285,9 @@ loss_pass_b(AgsLossArgs a, const float* __restrict__ nb, const float* __restrict
             tv_term(nq[k], nu, dq[k], dp, mdq[k], inv2s2, val, coef);
             gnu = gnu - (nq[k] - nu) * (2.f * coef * ctv);
         }
-        const float nn = fmaxf(sqrtf(dot(n, n)), 1e-12f);
-        const F3 uh = n * (1.f / nn);
-        const F3 gn = (gnu - uh * dot(uh, gnu)) * (m2 / nn);
+        const float inn = rsqrtf(fmaxf(dot(n, n), 1e-24f));
+        const F3 uh = n * inn;
+        const F3 gn = (gnu - uh * dot(uh, gnu)) * (m2 * inn);
         float* dn = a.d_normal + (size_t)f * 3 * P + p;
         dn[0] = gn.x; dn[P] = gn.y; dn[2 * P] = gn.z;
     }
@@ -351,6 +358,8 @@ extern "C" int ags_loss_forward_backward(const AgsLossArgs* a) {
     float* nb = (float*)a->workspace;                     // (B,4,H,W) neighbour contributions
     float* msum_plane = nb + (size_t)a->B * 4 * P;        // (H,W) visibility count (quirk Q1)
     dim3 grid((a->W + 31) / 32, (a->H + 7) / 8, a->B), block(32, 8);
+    loss_vis_count<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(*a, msum_plane);
+    AGS_CHECK_CUDA(cudaGetLastError());
     loss_pass_a<<<grid, block, 0, st>>>(*a, nb, msum_plane);
     AGS_CHECK_CUDA(cudaGetLastError());
     loss_pass_b<<<grid, block, 0, st>>>(*a, nb, msum_plane);
