@@ -29,8 +29,8 @@ sys.path.insert(0, ROOT)
 from active_gs_b200 import synthetic as syn  # noqa: E402
 from active_gs_b200.config import default_gaussian_map_config  # noqa: E402
 
-CONFIG_IDX = 2
-B_PER_GPU = 8
+CONFIG_IDX = 2          # BASELINE.json config[1] (the headline workload); --config 3 / 5 select the
+B_PER_GPU = 8           # larger parity configurations (not the headline line)
 METRIC, UNIT = "train_mpix_per_s", "Mpix/s"
 
 
@@ -251,8 +251,9 @@ def run_ours(args, rank, world, local_rank):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "iters_per_s": args.steps / (ms / 1e3),
-        "config": {"workload": "BASELINE config[1]: office0-shaped room, 200k Gaussian surfels, 640x480, "
-                               "train-loop iteration (render 8 keyframes fwd+bwd, 4-term loss, Adam)",
+        "config": {"workload": ("BASELINE config[1]: office0-shaped room, 200k Gaussian surfels, 640x480, "
+                                "train-loop iteration (render 8 keyframes fwd+bwd, 4-term loss, Adam)") if CONFIG_IDX == 2
+                               else f"SURVEY 8d config {CONFIG_IDX}: {N} surfels, {W}x{H}, {B} keyframes per step",
                    "gaussians": N, "H": H, "W": W, "keyframes_per_gpu": B, "global_batch": Bg,
                    "parallelism": f"frame-shard x{world}" + ("" if world == 1 else
                                    (" fused NVLink RS+Adam+AG" if shard.fused else " NCCL all-reduce")), "instances_per_step": inst, "visible_per_step": vis,
@@ -283,7 +284,7 @@ def run_ours(args, rank, world, local_rank):
         line["kernels"] = kern
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_reference_run(1, [{k: (v.cpu() if torch.is_tensor(v) else v) for k, v in f.items()}
-                                                     for f in frames[:4]], start, H, W, quiet=True)
+                                                     for f in frames[:4]], start, H, W, quiet=True, warmup=1)
     return line
 
 
@@ -359,7 +360,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5],
+                    help="SURVEY 8d config index: 2 = 200k/640x480 (headline), 3 = 500k/1280x720, 5 = 1M/1920x1080")
+    ap.add_argument("--frames-per-gpu", type=int, default=8)
     args = ap.parse_args()
+    global CONFIG_IDX, B_PER_GPU
+    CONFIG_IDX, B_PER_GPU = args.config, args.frames_per_gpu
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
