@@ -91,7 +91,13 @@ __device__ __forceinline__ bool bbox_hits(const float4 bb, const WarpBlock& b) {
 }
 
 // K4 ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+#ifndef AGS_FWD_MINB
+#define AGS_FWD_MINB 6
+#endif
+#ifndef AGS_BWD_MINB
+#define AGS_BWD_MINB 5
+#endif
+__global__ void __launch_bounds__(256, AGS_FWD_MINB)
 composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
     // shared memory: the staging records; the same bytes first serve the tile's depth sort
     __shared__ __align__(16) unsigned char s_raw[sizeof(SplatRec) * BATCH];
@@ -262,7 +268,7 @@ __device__ __forceinline__ float warp_reduce15(const float (&v)[15], unsigned st
     return r;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, AGS_BWD_MINB)
 composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
     __shared__ SplatRec s_rec[BATCH];
     __shared__ int s_id[BATCH];

@@ -130,7 +130,10 @@ loss_vis_count(AgsLossArgs a, float* __restrict__ msum_plane) {
 // gradient (L1 term + its share of the depth2normal adjoint) and the four contributions it makes
 // to its neighbours' depth gradients as four planes (up, left, bottom, right) that pass B gathers:
 // no atomics, deterministic.
-__global__ void __launch_bounds__(256)
+#ifndef AGS_LOSS_MINB
+#define AGS_LOSS_MINB 4
+#endif
+__global__ void __launch_bounds__(256, AGS_LOSS_MINB)
 loss_pass_a(AgsLossArgs a, float* __restrict__ nb, const float* __restrict__ msum_plane) {
     const int H = a.H, W = a.W;
     const size_t P = (size_t)H * W;
@@ -225,7 +228,7 @@ __device__ __forceinline__ void tv_term(F3 np_, F3 nq, float dp, float dq, float
 
 // pass B: one thread per (pixel, frame): normal gradient (consistency + TV gather, through
 // normalize*mask) and the TV loss sum.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, AGS_LOSS_MINB)
 loss_pass_b(AgsLossArgs a, const float* __restrict__ nb, const float* __restrict__ msum_plane) {
     const int H = a.H, W = a.W;
     const size_t P = (size_t)H * W;

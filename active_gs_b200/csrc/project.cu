@@ -200,7 +200,10 @@ __device__ __forceinline__ void project_view(ViewProj& o, const GaussAct& g, con
 //   3. the visible pairs of the CTA are appended to the global compact list (one atomic per CTA)
 //      that drives the scatter and K6.
 constexpr int K1_THREADS = 256;
-constexpr int K1_PER_THREAD = 4;
+#ifndef AGS_K1_PER_THREAD
+#define AGS_K1_PER_THREAD 4
+#endif
+constexpr int K1_PER_THREAD = AGS_K1_PER_THREAD;
 constexpr int K1_PAIRS = K1_THREADS * K1_PER_THREAD;
 
 __global__ void __launch_bounds__(K1_THREADS)

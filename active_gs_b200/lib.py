@@ -8,7 +8,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libags_b200.so")
+# AGS_B200_LIB selects an alternative build of the same library (tuning experiments only)
+LIB_PATH = os.environ.get("AGS_B200_LIB") or os.path.join(_HERE, "libags_b200.so")
 
 AGS_NUM_STATS = 8
 STAT_INSTANCES, STAT_OVERFLOW, STAT_VISIBLE = 0, 1, 2
