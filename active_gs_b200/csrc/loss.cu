@@ -126,58 +126,58 @@ loss_vis_count(AgsLossArgs a, float* __restrict__ msum_plane) {
     msum_plane[p] = vis_sum(a, P, (int)p);
 }
 
+#ifndef AGS_LOSS_MINB
+#define AGS_LOSS_MINB 4
+#endif
+
+// Addressing: every tensor is indexed as  kernel-parameter pointer + 32-bit unsigned element offset
+// (B*3*H*W < 2^32, checked by the launcher), which lets the compiler use the uniform-base +
+// 32-bit-offset addressing mode instead of 64-bit pointer arithmetic per access.
+
 // pass A: one thread per (pixel, frame).  Writes normal_unit, d2n, d_rgb, the pixel's own depth
 // gradient (L1 term + its share of the depth2normal adjoint) and the four contributions it makes
 // to its neighbours' depth gradients as four planes (up, left, bottom, right) that pass B gathers:
 // no atomics, deterministic.
-#ifndef AGS_LOSS_MINB
-#define AGS_LOSS_MINB 4
-#endif
 __global__ void __launch_bounds__(256, AGS_LOSS_MINB)
 loss_pass_a(AgsLossArgs a, float* __restrict__ nb, const float* __restrict__ msum_plane) {
     const int H = a.H, W = a.W;
-    const size_t P = (size_t)H * W;
+    const unsigned P = (unsigned)H * (unsigned)W;
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    const int f = blockIdx.z;
+    const unsigned f = blockIdx.z;
     const bool in = (x < W) && (y < H);
-    const int p = y * W + x;                 // 32-bit pixel index (P < 2^31)
+    const unsigned p = (unsigned)y * (unsigned)W + (unsigned)x;
     const float Bt = (float)a.B_total;
     const float inv_rgb = 1.f / (Bt * 3.f * (float)P);
     const float inv_d = 1.f / (Bt * (float)P);
     const float inv_cons = 1.f / (Bt * Bt * (float)P);
     float fr_rgb = 0.f, fr_d = 0.f, acc_cons = 0.f;
     if (in) {
+        const unsigned o1 = f * P + p;             // single-channel planes
+        const unsigned o3 = f * 3u * P + p;        // three-channel planes
+        const unsigned o4 = f * 4u * P + p;        // neighbour planes
         const float msum = __ldg(msum_plane + p);
-        const float* opac = a.opacity + (size_t)f * P;
-        const float* depth = a.depth + (size_t)f * P;
-        float* ddep = a.d_depth + (size_t)f * P;
-        float* nbf = nb + (size_t)f * 4 * P + p;
-        float c_up = 0.f, c_left = 0.f, c_bottom = 0.f, c_right = 0.f;
-        const float A = __ldg(opac + p);
+        const float* opac = a.opacity + f * P;     // frame bases for the stencil helpers
+        const float* depth = a.depth + f * P;
+        const float A = __ldg(a.opacity + o1);
         const float mvis = (A > 1e-3f) ? 1.f : 0.f;
         const float m2 = (A > 1e-2f) ? 1.f : 0.f;
         // ---- L1 rgb + gradient
-        const float* rp = a.rgb + (size_t)f * 3 * P + p;
-        const float* rg = a.rgb_gt + (size_t)f * 3 * P + p;
-        float* drgb = a.d_rgb + (size_t)f * 3 * P + p;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float e = (__ldg(rp + c * P) - __ldg(rg + c * P)) * mvis;
+        for (unsigned c = 0; c < 3; ++c) {
+            const float e = (__ldg(a.rgb + o3 + c * P) - __ldg(a.rgb_gt + o3 + c * P)) * mvis;
             fr_rgb += fabsf(e);
-            drgb[c * P] = (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f)) * mvis * inv_rgb;
+            a.d_rgb[o3 + c * P] = (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f)) * mvis * inv_rgb;
         }
         // ---- L1 depth + gradient
-        const float dg = __ldg(a.depth_gt + (size_t)f * P + p);
+        const float dg = __ldg(a.depth_gt + o1);
         const float md = (dg > 0.f) ? 1.f : 0.f;
-        const float ed = (__ldg(depth + p) - dg) * md;
+        const float ed = (__ldg(a.depth + o1) - dg) * md;
         fr_d = fabsf(ed);
         float dd_self = a.w_depth * (ed > 0.f ? 1.f : (ed < 0.f ? -1.f : 0.f)) * md * inv_d;
         // ---- unit normal
-        const float* np_ = a.normal + (size_t)f * 3 * P + p;
-        const F3 n = f3(__ldg(np_), __ldg(np_ + P), __ldg(np_ + 2 * P));
+        const F3 n = f3(__ldg(a.normal + o3), __ldg(a.normal + o3 + P), __ldg(a.normal + o3 + 2u * P));
         const F3 nu = n * (m2 * rsqrtf(fmaxf(dot(n, n), 1e-24f)));
-        float* no = a.normal_unit + (size_t)f * 3 * P + p;
-        no[0] = nu.x; no[P] = nu.y; no[2 * P] = nu.z;
+        a.normal_unit[o3] = nu.x; a.normal_unit[o3 + P] = nu.y; a.normal_unit[o3 + 2u * P] = nu.z;
         // ---- depth2normal
         const FrameGeom g = frame_geom(a.tanfov, f, H, W);
         const D2N v = d2n_vectors(depth, opac, g, H, W, y, x);
@@ -185,10 +185,10 @@ loss_pass_a(AgsLossArgs a, float* __restrict__ nb, const float* __restrict__ msu
         const float insn = rsqrtf(fmaxf(dot(ns, ns), 1e-24f));
         const F3 u = ns * insn;
         const F3 d2n = u * m2;
-        float* dn = a.d2n + (size_t)f * 3 * P + p;
-        dn[0] = d2n.x; dn[P] = d2n.y; dn[2 * P] = d2n.z;
+        a.d2n[o3] = d2n.x; a.d2n[o3 + P] = d2n.y; a.d2n[o3 + 2u * P] = d2n.z;
         // ---- consistency loss; adjoint of the un-normalised d2n vector, pushed to the five depths
         acc_cons = (1.f - dot(nu, d2n)) * msum;
+        float c_up = 0.f, c_left = 0.f, c_bottom = 0.f, c_right = 0.f;
         if (m2 > 0.f && msum > 0.f) {
             const float wc = -a.w_cons * msum * inv_cons;                // dL/d(nu . d2n)
             const F3 gd = nu * wc;                                       // dL/d u  (d2n = u*m2, m2 = 1)
@@ -205,8 +205,8 @@ loss_pass_a(AgsLossArgs a, float* __restrict__ nb, const float* __restrict__ msu
             c_bottom = dpb.x * rx + dpb.y * (ry + g.ik11) + dpb.z;
             c_right = dpr.x * (rx + g.ik00) + dpr.y * ry + dpr.z;
         }
-        ddep[p] = dd_self;
-        nbf[0] = c_up; nbf[P] = c_left; nbf[2 * P] = c_bottom; nbf[3 * P] = c_right;
+        a.d_depth[o1] = dd_self;
+        nb[o4] = c_up; nb[o4 + P] = c_left; nb[o4 + 2u * P] = c_bottom; nb[o4 + 3u * P] = c_right;
     }
     float v5[5] = {fr_rgb * inv_rgb, fr_d * inv_d, acc_cons * inv_cons, fr_rgb / (3.f * (float)P), fr_d / (float)P};
     float* const d5[5] = {a.loss_terms + 0, a.loss_terms + 1, a.loss_terms + 2,
@@ -226,39 +226,37 @@ __device__ __forceinline__ void tv_term(F3 np_, F3 nq, float dp, float dq, float
     coef = gate * e * (1.f - nd * inv2s2);       // d val / d nd
 }
 
-// pass B: one thread per (pixel, frame): normal gradient (consistency + TV gather, through
-// normalize*mask) and the TV loss sum.
+// pass B: one thread per (pixel, frame): depth gradient += the neighbours' planes; normal gradient
+// (consistency + TV gather, through normalize*mask) and the TV loss sum.
 __global__ void __launch_bounds__(256, AGS_LOSS_MINB)
 loss_pass_b(AgsLossArgs a, const float* __restrict__ nb, const float* __restrict__ msum_plane) {
     const int H = a.H, W = a.W;
-    const size_t P = (size_t)H * W;
+    const unsigned P = (unsigned)H * (unsigned)W;
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    const int f = blockIdx.z;
+    const unsigned f = blockIdx.z;
     const bool in = (x < W) && (y < H);
-    const int p = y * W + x;                 // 32-bit pixel index (P < 2^31)
+    const unsigned p = (unsigned)y * (unsigned)W + (unsigned)x;
     const float Bt = (float)a.B_total;
     const float inv_cons = 1.f / (Bt * Bt * (float)P);
     const float inv_tv = 1.f / (Bt * 4.f * (float)P);
     const float inv2s2 = 1.f / (2.f * 0.3f * 0.3f);
     float acc_tv = 0.f;
     if (in) {
+        const unsigned b1 = f * P, b3 = f * 3u * P, b4 = f * 4u * P;
         const float msum = __ldg(msum_plane + p);
         {   // depth gradient: own term (pass A) + what the four neighbours push to this pixel
-            const float* nbf = nb + (size_t)f * 4 * P;
             float dd = 0.f;
-            if (y < H - 1) dd += __ldg(nbf + p + W);          // "up" plane of the pixel below
-            if (x < W - 1) dd += __ldg(nbf + P + p + 1);      // "left" plane of the pixel to the right
-            if (y > 0) dd += __ldg(nbf + 2 * P + p - W);      // "bottom" plane of the pixel above
-            if (x > 0) dd += __ldg(nbf + 3 * P + p - 1);      // "right" plane of the pixel to the left
-            a.d_depth[(size_t)f * P + p] += dd;
+            if (y < H - 1) dd += __ldg(nb + b4 + p + (unsigned)W);              // "up" plane of the pixel below
+            if (x < W - 1) dd += __ldg(nb + b4 + P + p + 1u);                   // "left" plane of the pixel to the right
+            if (y > 0) dd += __ldg(nb + b4 + 2u * P + p - (unsigned)W);         // "bottom" plane of the pixel above
+            if (x > 0) dd += __ldg(nb + b4 + 3u * P + p - 1u);                  // "right" plane of the pixel to the left
+            a.d_depth[b1 + p] += dd;
         }
-        const float* depth = a.depth + (size_t)f * P;
-        const float* dgt = a.depth_gt + (size_t)f * P;
-        const float* nu_ = a.normal_unit + (size_t)f * 3 * P;
-        auto NU = [&](int q) { return f3(__ldg(nu_ + q), __ldg(nu_ + P + q), __ldg(nu_ + 2 * P + q)); };
+        auto NU = [&](unsigned q) { return f3(__ldg(a.normal_unit + b3 + q), __ldg(a.normal_unit + b3 + P + q),
+                                              __ldg(a.normal_unit + b3 + 2u * P + q)); };
         // all loads of the 5-point stencil up front (clamped coordinates, validity folded into flags)
-        const int qs[4] = {y * W + min(x + 1, W - 1), y * W + max(x - 1, 0),
-                           min(y + 1, H - 1) * W + x, max(y - 1, 0) * W + x};
+        const unsigned qs[4] = {(unsigned)(y * W + min(x + 1, W - 1)), (unsigned)(y * W + max(x - 1, 0)),
+                                (unsigned)(min(y + 1, H - 1) * W + x), (unsigned)(max(y - 1, 0) * W + x)};
         const float ok[4] = {x < W - 1 ? 1.f : 0.f, x > 0 ? 1.f : 0.f, y < H - 1 ? 1.f : 0.f, y > 0 ? 1.f : 0.f};
         const F3 nu = NU(p);
         F3 nq[4];
@@ -266,16 +264,15 @@ loss_pass_b(AgsLossArgs a, const float* __restrict__ nb, const float* __restrict
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             nq[k] = NU(qs[k]);
-            dq[k] = __ldg(depth + qs[k]);
-            mdq[k] = (__ldg(dgt + qs[k]) > 0.f) ? ok[k] : 0.f;
+            dq[k] = __ldg(a.depth + b1 + qs[k]);
+            mdq[k] = (__ldg(a.depth_gt + b1 + qs[k]) > 0.f) ? ok[k] : 0.f;
         }
-        const float dp = __ldg(depth + p);
-        const float md_p = (__ldg(dgt + p) > 0.f) ? 1.f : 0.f;
-        const float m2 = (__ldg(a.opacity + (size_t)f * P + p) > 1e-2f) ? 1.f : 0.f;
-        const float* d2p = a.d2n + (size_t)f * 3 * P + p;
-        F3 gnu = f3(__ldg(d2p), __ldg(d2p + P), __ldg(d2p + 2 * P)) * (-a.w_cons * msum * inv_cons);
-        const float* np_ = a.normal + (size_t)f * 3 * P + p;
-        const F3 n = f3(__ldg(np_), __ldg(np_ + P), __ldg(np_ + 2 * P));
+        const float dp = __ldg(a.depth + b1 + p);
+        const float md_p = (__ldg(a.depth_gt + b1 + p) > 0.f) ? 1.f : 0.f;
+        const float m2 = (__ldg(a.opacity + b1 + p) > 1e-2f) ? 1.f : 0.f;
+        F3 gnu = f3(__ldg(a.d2n + b3 + p), __ldg(a.d2n + b3 + P + p), __ldg(a.d2n + b3 + 2u * P + p))
+                 * (-a.w_cons * msum * inv_cons);
+        const F3 n = f3(__ldg(a.normal + b3 + p), __ldg(a.normal + b3 + P + p), __ldg(a.normal + b3 + 2u * P + p));
         const float ctv = a.w_tv * inv_tv;
         // each neighbour q contributes the own one-sided difference (mask of p) and the mirrored
         // difference of q that references p (mask of q)
@@ -291,8 +288,7 @@ loss_pass_b(AgsLossArgs a, const float* __restrict__ nb, const float* __restrict
         const float inn = rsqrtf(fmaxf(dot(n, n), 1e-24f));
         const F3 uh = n * inn;
         const F3 gn = (gnu - uh * dot(uh, gnu)) * (m2 * inn);
-        float* dn = a.d_normal + (size_t)f * 3 * P + p;
-        dn[0] = gn.x; dn[P] = gn.y; dn[2 * P] = gn.z;
+        a.d_normal[b3 + p] = gn.x; a.d_normal[b3 + P + p] = gn.y; a.d_normal[b3 + 2u * P + p] = gn.z;
     }
     float v1[1] = {acc_tv * inv_tv};
     float* const d1[1] = {a.loss_terms + 3};
@@ -355,6 +351,7 @@ extern "C" int ags_loss_forward_backward(const AgsLossArgs* a) {
                   "NULL output");
     AGS_CHECK_ARG(a->workspace && a->workspace_bytes >= ags_loss_scratch_bytes(a->B, a->H, a->W),
                   "loss workspace too small");
+    AGS_CHECK_ARG((unsigned long long)a->B * 4ull * a->H * a->W < 4294967295ull, "B*4*H*W exceeds 32-bit indexing");
     cudaStream_t st = (cudaStream_t)a->stream;
     AGS_CHECK_CUDA(cudaMemsetAsync(a->loss_terms, 0, (4 + 2 * (size_t)a->B) * sizeof(float), st));
     const size_t P = (size_t)a->H * a->W;
