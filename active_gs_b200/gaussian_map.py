@@ -46,6 +46,26 @@ class WeightedSampler:
         return sel
 
 
+class _BufferPool:
+    """Device buffers that survive across train() calls and grow geometrically: the map gains
+    Gaussians at every keyframe, so exact-size allocations would miss the caching allocator and pay
+    a cudaMalloc (milliseconds) per buffer per keyframe."""
+
+    def __init__(self, device):
+        self.device, self.bufs = device, {}
+
+    def get(self, name, nbytes):
+        b = self.bufs.get(name)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(int(nbytes * 1.5) + 4096, dtype=torch.uint8, device=self.device)
+            self.bufs[name] = b
+        return b
+
+    def floats(self, name, numel, zero=False):
+        t = self.get(name, numel * 4)[:numel * 4].view(torch.float32)
+        return t.zero_() if zero else t
+
+
 class _TrainEngine:
     """Preallocated buffers + the fused iteration for one train() call (fixed N, B, H, W)."""
 
@@ -81,13 +101,19 @@ class _TrainEngine:
         else:
             # gradients are views of ONE flat buffer (14 floats per Gaussian): a single all-reduce
             # in the frame-sharded multi-GPU path
-            self.grad_flat = torch.empty(total, **o)
+            self.grad_flat = gm._pool.floats("grad", total)
         self.grads, off = [], 0
         for p in self.params:
             self.grads.append(self.grad_flat[off:off + p.numel()].view(p.shape))
             off += p.numel()
-        self.m = [torch.zeros_like(p) for p in self.params] if not self.fused else None
-        self.v = [torch.zeros_like(p) for p in self.params] if not self.fused else None
+        self.m = self.v = None
+        if not self.fused:                       # fresh Adam state every train() call (gaussian_map.py:259-292)
+            mf, vf = gm._pool.floats("adam_m", total, zero=True), gm._pool.floats("adam_v", total, zero=True)
+            self.m, self.v, off = [], [], 0
+            for p in self.params:
+                self.m.append(mf[off:off + p.numel()].view(p.shape))
+                self.v.append(vf[off:off + p.numel()].view(p.shape))
+                off += p.numel()
         self.lrs = [gm.cfg.optimizer.mean_lr, gm.cfg.optimizer.scale_lr, gm.cfg.optimizer.rotation_lr,
                     gm.cfg.optimizer.opacity_lr, gm.cfg.optimizer.harmonic_lr]
         self.step = 0
@@ -113,7 +139,8 @@ class _TrainEngine:
         self.rb = RenderBatch(gm._means, gm._scales, gm._rotations, gm._opacities,
                               gm._harmonics.reshape(N, 3), self.conf, self.view, self.proj, self.tanfov,
                               self.bg, H, W, param_mode=L.PARAMS_RAW, scale_factor=gm.scale_factor,
-                              scale_max=0.05, inst_cap=cap, with_importance=False)
+                              scale_max=0.05, inst_cap=cap, with_importance=False,
+                              pool=lambda nbytes: gm._pool.get("workspace", nbytes))
         # RenderBatch copies nothing for contiguous fp32 inputs, but make the aliasing explicit
         self.rb.inputs = [gm._means, gm._scales, gm._rotations, gm._opacities,
                           gm._harmonics.reshape(N, 3), self.conf]
@@ -290,6 +317,7 @@ class GaussianMap:
         self.dist = None                     # active_gs_b200.distributed.FrameShard or None
         self.last_train_log = []
         self._cap_per_gaussian = 4.0
+        self._pool = _BufferPool(self.device)
         if cfg is not None:
             self.cfg = cfg
             self.use_view_distribution = cfg.use_view_distribution
@@ -421,7 +449,7 @@ class GaussianMap:
         rgb, depth = dataframe["rgb"].to(dev), dataframe["depth"].to(dev)
         intrinsic, extrinsic = dataframe["intrinsic"].to(dev), dataframe["extrinsic"].to(dev)
         _, H, W = rgb.shape
-        smooth = torch.tensor(O.get_smooth_depth(depth.squeeze(0).cpu().numpy()), device=dev).unsqueeze(0)
+        smooth = O.get_smooth_depth_device(depth)          # (1,H,W); reference: cv2 on the CPU, :297-298
         valid = (depth > 0.0).view(-1)
         origins, directions = O.get_world_rays(H, W, extrinsic, intrinsic, dev)
         pcd = origins + directions * depth.view(-1, 1)

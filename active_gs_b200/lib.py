@@ -83,7 +83,7 @@ _lib = None
 
 EXPORTS = ["ags_scratch_bytes", "ags_render_forward", "ags_render_backward", "ags_render_stage",
            "ags_loss_scratch_bytes", "ags_loss_forward_backward", "ags_postprocess", "ags_adam_step",
-           "ags_dist_adam_step",
+           "ags_dist_adam_step", "ags_smooth_depth",
            "ags_last_error", "ags_version"]
 
 
@@ -107,6 +107,9 @@ def load():
     lib.ags_render_stage.restype = C.c_int
     lib.ags_loss_forward_backward.argtypes = [C.POINTER(LossArgs)]
     lib.ags_adam_step.argtypes = [C.POINTER(AdamArgs)]
+    lib.ags_smooth_depth.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
+                                     C.c_float, C.c_void_p, C.c_void_p]
+    lib.ags_smooth_depth.restype = C.c_int
     lib.ags_dist_adam_step.argtypes = [C.POINTER(DistAdamArgs)]
     lib.ags_dist_adam_step.restype = C.c_int
     lib.ags_postprocess.argtypes = [C.c_int32] * 3 + [C.c_void_p] * 7

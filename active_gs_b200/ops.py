@@ -97,3 +97,17 @@ def postprocess(normal, depth, opacity, tanfov):
                                 L.ptr(nu), L.ptr(d2n), L.current_stream(normal.device)),
             "ags_postprocess")
     return nu, d2n
+
+
+def smooth_depth(depth, d=15, sigma_color=0.5, sigma_space=20.0):
+    """get_smooth_depth (utils/operations.py:161-169) on the device: (H,W) or (1,H,W) CUDA float32
+    depth with invalid < 0 -> bilateral-filtered depth, -1 at invalid pixels."""
+    lib = L.load()
+    shape = depth.shape
+    H, W = shape[-2], shape[-1]
+    src = depth.reshape(H, W).to(torch.float32).contiguous()
+    out = torch.empty_like(src)
+    scratch = torch.empty(4, dtype=torch.int32, device=src.device)
+    L.check(lib.ags_smooth_depth(H, W, L.ptr(src), L.ptr(out), d, sigma_color, sigma_space, L.ptr(scratch),
+                                 L.current_stream(src.device)), "ags_smooth_depth")
+    return out.reshape(shape)

@@ -45,7 +45,7 @@ class RenderBatch:
                  projmatrix, tanfov, bg, H, W, *, render_mask=None, scale_modifier=1.0,
                  weight_thres=0.03, require_importance=False, front_only=False,
                  param_mode=L.PARAMS_ACTIVATED, scale_factor=0.01, scale_max=0.05, inst_cap=None,
-                 with_importance=True):
+                 with_importance=True, pool=None):
         lib = L.load()
         dev = means3D.device
         if dev.type != "cuda":
@@ -85,11 +85,15 @@ class RenderBatch:
             inst_cap = int(per * N * B) + 4096
         self.inst_cap = int(inst_cap)
         self.workspace = None
+        self.pool = pool                 # optional callable(nbytes) -> uint8 tensor with >= nbytes (reused across calls)
         self._alloc(lib)
 
     def _alloc(self, lib):
         nbytes = lib.ags_scratch_bytes(self.N, self.B, self.H, self.W, self.inst_cap)
-        self.workspace = torch.empty(nbytes + 256, device=self.dev, dtype=torch.uint8)
+        if self.pool is not None:
+            self.workspace = self.pool(nbytes + 256)
+        else:
+            self.workspace = torch.empty(nbytes + 256, device=self.dev, dtype=torch.uint8)
         self.ws_ptr = (self.workspace.data_ptr() + 255) & ~255
         self.ws_bytes = nbytes
 

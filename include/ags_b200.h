@@ -157,6 +157,13 @@ int ags_postprocess(int32_t B, int32_t H, int32_t W, const float* normal, const 
                     const float* opacity, const float* tanfov, float* normal_unit, float* d2n,
                     void* stream);
 
+/* Spawn step (mapping/gaussian_map.py:294-322): get_smooth_depth (utils/operations.py:161-169) on the
+ * device -- OpenCV's float32 bilateral filter (d, sigmaColor, sigmaSpace; BORDER_REFLECT_101, circular
+ * support, 4096-bin exp LUT semantics) over the depth image with invalid (< 0) pixels zero-filled on
+ * input and set to -1 on output.  depth/out: (H,W) device; scratch: >= 16 bytes device. */
+int ags_smooth_depth(int32_t H, int32_t W, const float* depth, float* out, int32_t d, float sigma_color,
+                     float sigma_space, void* scratch, void* stream);
+
 #define AGS_ADAM_GROUPS 5
 typedef struct AgsAdamArgs {
     int32_t num_groups;                    /* <= AGS_ADAM_GROUPS */

@@ -133,3 +133,27 @@ def test_fused_adam_matches_torch():
         assert l2 < 1e-6 and emax < 1e-5, (emax, l2)
     # zero-gradient lane stays exactly inert (0/(0+1e-15) = 0)
     assert torch.equal(ours[1][:, 2].cpu(), p0[1][:, 2])
+
+
+def test_device_bilateral_matches_cv2():
+    """ags_smooth_depth restates cv2.bilateralFilter(depth, 15, 0.5, 20) as used by get_smooth_depth
+    (utils/operations.py:161-169): compare with OpenCV itself (CPU) on depth images with holes."""
+    dev = _dev()
+    cv2 = pytest.importorskip("cv2")
+    from active_gs_b200 import operations as O
+    rng = np.random.default_rng(0)
+    for (H, W) in [(96, 128), (37, 53), (480, 640)]:
+        xs = np.arange(W)[None, :] / W
+        ys = np.arange(H)[:, None] / H
+        depth = (2 + 0.5 * xs + 0.3 * ys + 0.01 * rng.standard_normal((H, W))).astype(np.float32)
+        depth[:, W // 2:] += 0.8
+        depth[rng.random((H, W)) < 0.05] = -1.0
+        depth[:4, :10] = -2.0
+        ref = O.get_smooth_depth(depth)                      # the reference's CPU path (cv2)
+        got = O.get_smooth_depth_device(torch.tensor(depth, device=dev)[None])[0].cpu().numpy()
+        assert np.array_equal(got < 0, depth < 0) and np.all(got[depth < 0] == -1.0)
+        err = np.abs(got - ref).max() / np.abs(ref).max()
+        print(f"  bilateral {H}x{W}: max rel err vs cv2 {err:.2e}")
+        assert err < 2e-5
+    flat = torch.full((1, 20, 30), 1.5, device=dev)
+    assert torch.equal(O.get_smooth_depth_device(flat), flat)   # max == min: copied unchanged
