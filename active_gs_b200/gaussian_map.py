@@ -69,7 +69,7 @@ class _BufferPool:
 class _TrainEngine:
     """Preallocated buffers + the fused iteration for one train() call (fixed N, B, H, W)."""
 
-    def __init__(self, gm, B, H, W, dist_ctx=None):
+    def __init__(self, gm, B, H, W, dist_ctx=None, cam_table=None):
         dev = gm.device
         self.gm, self.B, self.H, self.W, self.dev = gm, B, H, W, dev
         self.dist = dist_ctx
@@ -127,13 +127,15 @@ class _TrainEngine:
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.copy_done = [torch.cuda.Event(), torch.cuda.Event()]
         self.copy_pending = False
+        self.prefetched = [{}, {}]          # per ground-truth buffer: local slot -> keyframe id already staged
         # camera blocks of the batch: one flat device buffer [B*16 view | B*16 proj | B*2 tanfov]
         # refreshed by ONE small H2D copy per iteration from a pinned staging buffer
         self.cam_flat = torch.empty(B * 34, **o)
         self.view = self.cam_flat[:B * 16].view(B, 16)
         self.proj = self.cam_flat[B * 16:B * 32].view(B, 16)
         self.tanfov = self.cam_flat[B * 32:].view(B, 2)
-        self.cam_host = torch.empty(B * 34, dtype=torch.float32).pin_memory()
+        self.cam_table = cam_table                       # (T, 34) device: view | proj | tanfov per keyframe
+        self.cam_ids = (C.c_int32 * B)()
         self.bg = gm.background_color.to(dev).float().contiguous()
         cap = gm._inst_cap_hint(N, B)
         self.rb = RenderBatch(gm._means, gm._scales, gm._rotations, gm._opacities,
@@ -163,31 +165,60 @@ class _TrainEngine:
         self.adam_cache = {}
         self.dist_args = None
 
-    def set_batch(self, rgbs, depths, views_h, projs_h, tanfovs_h, idx):
+    def set_batch(self, rgbs, depths, idx, ids=None):
         """Stage this iteration's keyframes (lists of (3,H,W)/(1,H,W) tensors) and camera blocks
-        (rows `idx` of the host camera tables) in the fixed device buffers.  Pinned host frames make
+        (rows `idx` of the device camera table) in the fixed device buffers.  Pinned host frames make
         this the per-step H2D of the end-to-end path; device frames are gathered with one stack
-        kernel per tensor."""
+        kernel per tensor.  `ids` (keyframe ids of the batch) lets the copy skip frames that
+        prefetch_next() already staged in this buffer."""
         B = self.B
         self.gt_k ^= 1
         self.rgb_gt, self.depth_gt = self.gt[self.gt_k]
+        # camera blocks: gathered on the device from the table of all keyframes; the ids travel as
+        # kernel arguments (an H2D copy here would queue on the copy engine behind the keyframe
+        # uploads and stall the forward)
+        for k in range(B):
+            self.cam_ids[k] = int(idx[k])
+        L.check(L.load().ags_stage_cameras(self.cam_table.data_ptr(), self.cam_table.shape[0], self.cam_ids, B,
+                                           self.view.data_ptr(), self.proj.data_ptr(), self.tanfov.data_ptr(),
+                                           L.current_stream(self.dev)), "ags_stage_cameras")
         if rgbs[0].is_cuda:
             torch.stack(rgbs, out=self.rgb_gt)
             torch.stack(depths, out=self.depth_gt)
             self.copy_pending = False
         else:
             # buffer gt_k was last read by the loss of step i-2, which finished before fetch(i-1)
+            staged = self.prefetched[self.gt_k]
             with torch.cuda.stream(self.copy_stream):
                 for k in range(B):
+                    if ids is not None and staged.get(k) == int(ids[k]):
+                        continue
                     self.rgb_gt[k].copy_(rgbs[k], non_blocking=True)
                     self.depth_gt[k].copy_(depths[k], non_blocking=True)
                 self.copy_done[self.gt_k].record(self.copy_stream)
+            staged.clear()
             self.copy_pending = True
-        h = self.cam_host
-        torch.index_select(views_h, 0, idx, out=h[:B * 16].view(B, 16))
-        torch.index_select(projs_h, 0, idx, out=h[B * 16:B * 32].view(B, 16))
-        torch.index_select(tanfovs_h, 0, idx, out=h[B * 32:].view(B, 2))
-        self.cam_flat.copy_(h, non_blocking=True)
+
+    def prefetch_next(self, fixed, training_data):
+        """Start the H2D of the NEXT step's keyframes whose ids do not depend on the sampler draw
+        (`fixed`: local batch slot -> keyframe id; the sampler's always-selected active frames,
+        mapping/utils.py:196-204) into the other ground-truth buffer.  Called right after a step is
+        enqueued and before the host waits for its loss terms, so this part of the per-step copy
+        overlaps the forward + loss of the current step; the drawn frames follow in set_batch().
+        The target buffer was last read by the loss of the previous step, which the host has
+        already waited for."""
+        if not fixed or training_data[next(iter(fixed.values()))]["rgb"].is_cuda:
+            return
+        nk = self.gt_k ^ 1
+        staged = self.prefetched[nk]
+        if staged:
+            return                                   # already staged (overflow retry of the same step)
+        rgb_gt, depth_gt = self.gt[nk]
+        with torch.cuda.stream(self.copy_stream):
+            for k, fid in fixed.items():
+                rgb_gt[k].copy_(training_data[fid]["rgb"], non_blocking=True)
+                depth_gt[k].copy_(training_data[fid]["depth"], non_blocking=True)
+                staged[k] = int(fid)
 
     def grow(self, need):
         """re-plan the instance capacity after an overflow (nothing was rendered or updated)"""
@@ -354,23 +385,31 @@ class GaussianMap:
         B = sampler.v if self.dist is None else self.dist.local_batch(sampler.v)
         _, H, W = self.training_data[0]["rgb"].shape
         fovs, views, projs, tanfovs = self._camera_table()           # host tensors (T, .)
-        return SimpleNamespace(
-            sampler=sampler, B=B, H=H, W=W, views=views.contiguous(), projs=projs.contiguous(),
-            tanfovs=tanfovs.contiguous(), eng=_TrainEngine(self, B, H, W, self.dist),
+        # batch slots whose keyframe never changes (the sampler's active frames come first in the
+        # sampled ids): local slot k of this rank is global slot rank*B + k
+        first = 0 if self.dist is None else self.dist.rank * B
+        fixed = {k: int(sampler.active_ids[first + k]) for k in range(B) if first + k < len(sampler.active_ids)}
+        return SimpleNamespace(fixed=fixed,
+            sampler=sampler, B=B, H=H, W=W,
+            eng=_TrainEngine(self, B, H, W, self.dist,
+                             cam_table=torch.cat([views, projs, tanfovs], dim=1).contiguous().to(self.device)),
             perf_host=self.training_performance.detach().float().cpu().clone(), log=[])
 
     def train_step(self, ctx, ids=None):
         """One iteration of mapping/gaussian_map.py:76-127: sample keyframes, stage them, enqueue
         forward/loss/backward/Adam, wait for the loss terms (sampler dependency)."""
         eng = ctx.eng
+        sampled = ids is None
         ids = np.asarray(ids) if ids is not None else ctx.sampler.next_ids(ctx.perf_host)
         my = ids if self.dist is None else self.dist.my_frames(ids)
         idx = torch.as_tensor(my, dtype=torch.long)
         eng.set_batch([self.training_data[i]["rgb"] for i in my],
                       [self.training_data[i]["depth"] for i in my],
-                      ctx.views, ctx.projs, ctx.tanfovs, idx)
+                      idx, ids=my)
         while True:
             eng.iterate()
+            if sampled:
+                eng.prefetch_next(ctx.fixed, self.training_data)
             terms, perf, stats = eng.fetch()
             if stats[L.STAT_OVERFLOW] == 0:
                 break

@@ -15,6 +15,7 @@ AGS_NUM_STATS = 8
 STAT_INSTANCES, STAT_OVERFLOW, STAT_VISIBLE = 0, 1, 2
 PARAMS_ACTIVATED, PARAMS_RAW = 0, 1
 ADAM_GROUPS = 5
+CAM_ROW = 34
 
 _f = C.c_void_p  # device pointers travel as void*
 
@@ -83,7 +84,7 @@ _lib = None
 
 EXPORTS = ["ags_scratch_bytes", "ags_render_forward", "ags_render_backward", "ags_render_stage",
            "ags_loss_scratch_bytes", "ags_loss_forward_backward", "ags_postprocess", "ags_adam_step",
-           "ags_dist_adam_step", "ags_smooth_depth",
+           "ags_dist_adam_step", "ags_smooth_depth", "ags_stage_cameras",
            "ags_last_error", "ags_version"]
 
 
@@ -110,6 +111,9 @@ def load():
     lib.ags_smooth_depth.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
                                      C.c_float, C.c_void_p, C.c_void_p]
     lib.ags_smooth_depth.restype = C.c_int
+    lib.ags_stage_cameras.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ags_stage_cameras.restype = C.c_int
     lib.ags_dist_adam_step.argtypes = [C.POINTER(DistAdamArgs)]
     lib.ags_dist_adam_step.restype = C.c_int
     lib.ags_postprocess.argtypes = [C.c_int32] * 3 + [C.c_void_p] * 7

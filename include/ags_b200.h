@@ -211,6 +211,18 @@ typedef struct AgsDistAdamArgs {
 } AgsDistAdamArgs;
 int ags_dist_adam_step(const AgsDistAdamArgs* args);
 
+/* Per-iteration camera staging (new; replaces the per-view host work of GaussianRenderer.__init__,
+ * utils/operations.py:748-762, inside the training loop): gathers the camera blocks of the sampled
+ * keyframes from a device-resident table into the (B,16)/(B,16)/(B,2) tensors AgsRenderArgs points
+ * at.  The keyframe ids travel BY VALUE as kernel arguments (ids_host is read before the call
+ * returns), so no host-to-device copy is enqueued: a copy on the compute stream would share the
+ * H2D copy engine with the keyframe uploads and stall the forward behind them.
+ * table: (T, AGS_CAM_ROW) floats per keyframe = viewmatrix 16 | projmatrix 16 | tanfov 2. */
+#define AGS_CAM_ROW 34
+#define AGS_MAX_BATCH 64
+int ags_stage_cameras(const float* table, int32_t T, const int32_t* ids_host, int32_t B,
+                      float* viewmatrix, float* projmatrix, float* tanfov, void* stream);
+
 const char* ags_last_error(void);
 int ags_version(void);
 
