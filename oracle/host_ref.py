@@ -327,3 +327,150 @@ def post_process(state, frames, bg, near_far, hw, prune_interval=5, rasterize_fn
                   "view_supports", "view_means"]:
             state[k] = state[k][keep]
     return keep
+
+
+# ---------------------------------------------------------------- spawn (add_gaussians)
+def smooth_depth(depth, tolerance=0.5):
+    """utils/operations.py:161-169 -- OpenCV bilateral filter (d=15, sigmaColor=tolerance,
+    sigmaSpace=20) of the zero-filled depth, invalid (< 0) pixels back to -1.  (1,H,W) -> (1,H,W)."""
+    import cv2
+    d = depth.squeeze(0).cpu().numpy()
+    bad = d < 0.0
+    filt = cv2.bilateralFilter(np.where(bad, 0.0, d).astype(np.float32), 15, tolerance, 20)
+    filt[bad] = -1.0
+    return torch.tensor(filt).unsqueeze(0)
+
+
+def pixel_world_rays(H, W, extrinsic, intrinsic):
+    """utils/operations.py:372-392 (pixel centres (x+.5)/W, (y+.5)/H), :464-478 (K^-1 [x,y,1]) and
+    :544-569 (rotate into the world, origin = camera position): (H*W,3) origins, directions
+    (un-normalised, camera z = 1), row-major pixel order."""
+    ys = (torch.arange(H, dtype=torch.float32) + 0.5) / H
+    xs = (torch.arange(W, dtype=torch.float32) + 0.5) / W
+    yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+    pix = torch.stack([xx, yy, torch.ones_like(xx)], -1).reshape(-1, 3)
+    d_cam = pix @ torch.linalg.inv(intrinsic).t()
+    d_world = d_cam @ extrinsic[:3, :3].t()
+    return extrinsic[:3, 3].expand_as(d_world), d_world
+
+
+def normal_to_quaternion(n):
+    """utils/operations.py:481-500 (normal2rotation) + :526-541 (rotmat2quaternion): frame with z = n,
+    x = the world x axis (y axis when |n_x| > 0.99) made orthogonal to n; quaternion (r,x,y,z) from
+    the trace formula with the +1e-6 the reference adds, normalised."""
+    z = n / n.norm(dim=1, keepdim=True)
+    ref = torch.zeros_like(z)
+    ref[:, 0] = 1.0
+    ref[z[:, 0].abs() > 0.99] = torch.tensor([0.0, 1.0, 0.0])
+    x = ref - (ref * z).sum(1, keepdim=True) * z
+    x = x / x.norm(dim=1, keepdim=True)
+    y = torch.linalg.cross(z, x, dim=1)
+    y = y / y.norm(dim=1, keepdim=True)
+    R = torch.stack([x, y, z], dim=-1)
+    r = torch.sqrt(1 + (R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2] + 1e-6)) / 2
+    q = torch.stack([r, (R[:, 2, 1] - R[:, 1, 2]) / (4 * r), (R[:, 0, 2] - R[:, 2, 0]) / (4 * r),
+                     (R[:, 1, 0] - R[:, 0, 1]) / (4 * r)], -1)
+    return F.normalize(q, dim=-1)
+
+
+def spawn_mask(rgb_gt, depth_gt, pred, error_thres=0.25):
+    """mapping/gaussian_map.py:470-489 (cal_mask) for one frame: spawn where the map renders the wrong
+    colour (MSE over channels > error_thres), is not opaque (< 0.5) or lies more than 5 % BEHIND the
+    sensor depth.  pred = None (no map yet) selects every pixel.  Returns (H*W,) bool."""
+    H, W = rgb_gt.shape[1:]
+    if pred is None:
+        return torch.ones(H * W, dtype=torch.bool)
+    err = ((rgb_gt - pred["rgb"]) ** 2).mean(0)
+    m = err > error_thres
+    m = m | (pred["opacity"] < 0.5)
+    m = m | ((depth_gt[0] - pred["depth"]) < -0.05 * depth_gt[0])
+    return m.reshape(-1)
+
+
+def spawn_candidates(frame, pred=None, error_thres=0.25, depth_smooth=None):
+    """mapping/gaussian_map.py:294-400 up to (not including) the random voxel filter: the per-pixel
+    candidate Gaussians of one RGB-D keyframe.  Returns dict(select (H*W,) bool, means (H*W,3),
+    rotations (H*W,4), colors (H*W,3)); the new Gaussians are rows `select` in pixel order with raw
+    scales (0,0,-1e10), raw opacity 0, and zero view statistics (:369-381)."""
+    rgb, depth = frame["rgb"], frame["depth"]
+    _, H, W = rgb.shape
+    if depth_smooth is None:
+        depth_smooth = smooth_depth(depth)
+    valid = (depth > 0.0).reshape(-1)
+    origins, directions = pixel_world_rays(H, W, frame["extrinsic"], frame["intrinsic"])
+    pcd = origins + directions * depth.reshape(-1, 1)
+    # normals from the smoothed depth with a hard-wired 60 x 60 degree fov (:316-322)
+    n_cam = depth2normal(depth_smooth, valid.view(1, H, W), (np.pi / 3, np.pi / 3)).permute(1, 2, 0).reshape(-1, 3)
+    valid = valid & ((n_cam ** 2).sum(-1) > 0.0)
+    n_world = n_cam @ frame["extrinsic"][:3, :3].t()
+    normals = torch.zeros(H * W, 3)
+    normals[:, 2] = 1.0
+    normals[valid] = n_world[valid]
+    cos = (F.normalize(directions, dim=1) * normals).sum(-1)              # back-facing normals out (:330-335)
+    valid = valid & (cos < -0.01)
+    q = normal_to_quaternion(normals)
+    valid = valid & ~torch.any(q.isnan(), dim=1)
+    select = spawn_mask(rgb, depth, pred, error_thres) & valid
+    return dict(select=select, means=pcd, rotations=q, colors=rgb.permute(1, 2, 0).reshape(-1, 3))
+
+
+def voxel_ids(points, voxel_size=0.02):
+    """utils/operations.py:603-606: integer voxel coordinates floor(p / voxel_size), (n,3) int64."""
+    return torch.floor(points / voxel_size).long()
+
+
+def voxel_filter_is_valid(points, selected, voxel_size=0.02):
+    """What voxel_downsample (utils/operations.py:603-625) guarantees whatever its random draw:
+    `selected` is sorted, holds exactly one point of every occupied voxel and nothing else."""
+    vox = voxel_ids(points, voxel_size)
+    uniq = torch.unique(vox, dim=0)
+    sel = torch.as_tensor(selected).long()
+    if sel.numel() != uniq.shape[0] or not bool((sel[1:] > sel[:-1]).all()):
+        return False
+    return torch.unique(vox[sel], dim=0).shape[0] == uniq.shape[0]
+
+
+# ---------------------------------------------------------------- planner utilities (section 8 f1)
+def voxel_visible_mask(voxel_centers, extrinsic, intrinsic, depth):
+    """mapping/voxel_map.py:226-278 (cal_visible_mask): voxel centres in front of the camera that
+    project inside the image (normalised K; x*w, y*h truncated to the pixel index) and lie in front of
+    the depth stored there.  depth (h,w); returns (M,) bool."""
+    h, w = depth.shape
+    hom = torch.cat([voxel_centers, torch.ones(voxel_centers.shape[0], 1)], -1)
+    cam = (torch.linalg.inv(extrinsic) @ hom.t()).t()[:, :3]
+    z = cam[:, 2]
+    img = (intrinsic @ cam.t()).t()
+    xy = img[:, :2] / img[:, 2:3]
+    x, y = xy[:, 0] * w, xy[:, 1] * h
+    inside = (x >= 0) & (x < w) & (y >= 0) & (y < h)
+    dval = torch.full((voxel_centers.shape[0],), -1.0)
+    dval[inside] = depth[y[inside].long(), x[inside].long()]
+    return (z > 0) & inside & (dval > z)
+
+
+def view_utilities(depth, confidence, voxel_centers, unexplored, extrinsics, intrinsics, depth_range,
+                   valid_mask=None):
+    """planning/confidence.py:69-101 (and planning/exploration.py:62-86, which is the exploration
+    half alone) for V rendered candidate views: depth, confidence (V,h,w).  Returns
+    (explore (V,), exploit (V,)): the fraction of all voxels that are visible AND unexplored, and the
+    mean distance-weighted uncertainty (1 - confidence)."""
+    V, h, w = depth.shape
+    lo, hi = float(depth_range[0]), float(depth_range[1])
+    explore, exploit = torch.zeros(V), torch.zeros(V)
+    for i in range(V):
+        valid = torch.ones(h, w, dtype=torch.bool) if valid_mask is None else valid_mask[i]
+        dv = depth[i].clone()
+        dv[dv < 0.001] = 10000.0                                           # nothing rendered: free up to the range
+        dv = dv.clamp(lo, hi)
+        dv[~valid] = -1.0
+        vis = voxel_visible_mask(voxel_centers, extrinsics[i], intrinsics[i], dv)
+        explore[i] = (vis & unexplored).sum() / voxel_centers.shape[0]
+        conf = confidence[i].clone()
+        conf[depth[i] > hi] = 1.0
+        conf[~valid] = 1.0
+        ds = depth[i].clone()
+        ds[ds < 0.001] = hi * 0.5
+        exploit[i] = ((1 - conf) * ds / hi).mean()
+    explore[torch.isnan(explore)] = 0.0
+    exploit[torch.isnan(exploit)] = 0.0
+    return explore, exploit
