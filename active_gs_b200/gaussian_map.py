@@ -66,6 +66,58 @@ class _BufferPool:
         return t.zero_() if zero else t
 
 
+_ATTR = {"means": "_means", "scales": "_scales", "rotations": "_rotations", "opacities": "_opacities",
+         "harmonics": "_harmonics", "view_scores": "view_scores", "view_supports": "view_supports",
+         "view_means": "view_means"}
+
+
+class _MapStore:
+    """Capacity buffers behind the eight SoA tensors of the map.  The reference re-allocates all of
+    them with torch.cat at every keyframe and with boolean indexing at every prune
+    (mapping/gaussian_map.py:403-462, 240-246); here the spawn kernel appends in place, the prune
+    kernel compacts into a second set of buffers (ping-pong), and GaussianMap's attributes are
+    [:N] views.  Tensors assigned from outside (load(), tests, the fused multi-GPU engine) are
+    detected by their data pointers and copied back in."""
+
+    def __init__(self, device):
+        self.device, self.cap, self.buf, self.alt = device, 0, None, None
+
+    def _alloc(self, cap):
+        o = dict(device=self.device, dtype=torch.float32)
+        return {n: (torch.empty(cap, w, **o) if w > 1 else torch.empty(cap, **o)) for n, w in ops.MAP_FIELDS}
+
+    def owns(self, gm):
+        if self.buf is None:
+            return False
+        return all(getattr(gm, _ATTR[n]).data_ptr() == self.buf[n].data_ptr() and
+                   getattr(gm, _ATTR[n]).dtype == torch.float32 for n, _ in ops.MAP_FIELDS)
+
+    def adopt(self, gm, extra):
+        """make sure the map's tensors are prefix views of buffers with room for `extra` more rows"""
+        N = gm._means.shape[0]
+        if self.owns(gm) and N + extra <= self.cap:
+            return
+        cap = max(int(1.5 * (N + extra)) + 1024, 65536)
+        new = self._alloc(cap)
+        for n, w in ops.MAP_FIELDS:
+            new[n][:N].copy_(getattr(gm, _ATTR[n]).detach().reshape((N, w) if w > 1 else (N,)))
+        self.buf, self.cap, self.alt = new, cap, None
+        self.expose(gm, N)
+
+    def expose(self, gm, n):
+        for name, _ in ops.MAP_FIELDS:
+            t = self.buf[name][:n]
+            setattr(gm, _ATTR[name], t.view(n, 1, 3) if name == "harmonics" else t)
+
+    def other(self):
+        if self.alt is None:
+            self.alt = self._alloc(self.cap)
+        return self.alt
+
+    def swap(self):
+        self.buf, self.alt = self.alt, self.buf
+
+
 class _TrainEngine:
     """Preallocated buffers + the fused iteration for one train() call (fixed N, B, H, W)."""
 
@@ -349,6 +401,8 @@ class GaussianMap:
         self.last_train_log = []
         self._cap_per_gaussian = 4.0
         self._pool = _BufferPool(self.device)
+        self._store = _MapStore(self.device)
+        self._cams = []                      # per keyframe: host camera products, computed once
         if cfg is not None:
             self.cfg = cfg
             self.use_view_distribution = cfg.use_view_distribution
@@ -368,12 +422,26 @@ class GaussianMap:
     def _inst_cap_hint(self, N, B):
         return int(self._cap_per_gaussian * N * B) + 65536
 
-    def _camera_table(self):
-        """camera blocks of all keyframes, computed on the host once per train() call"""
-        ext = torch.stack([f["extrinsic"].detach().float().cpu() for f in self.training_data])
-        K = torch.stack([f["intrinsic"].detach().float().cpu() for f in self.training_data])
-        fovs, view, proj, _, tanfov = O.camera_blocks(ext, K, (self.scene_near, self.scene_far))
-        return fovs, view.reshape(-1, 16), proj.reshape(-1, 16), tanfov
+    def _camera(self, i):
+        """Host-side camera products of keyframe i (utils/operations.py:748-762 for one view),
+        computed once per keyframe instead of once per view per iteration: (34,) row
+        [viewmatrix 16 | projmatrix 16 | tanfov 2], camera position, c2w, K^-1."""
+        f = self.training_data[i]
+        while len(self._cams) <= i:
+            self._cams.append(None)
+        c = self._cams[i]
+        if c is None or c["ext"] is not f["extrinsic"] or c["K"] is not f["intrinsic"]:
+            ext = f["extrinsic"].detach().float().cpu()
+            K = f["intrinsic"].detach().float().cpu()
+            _, view, proj, campos, tanfov = O.camera_blocks(ext[None], K[None], (self.scene_near, self.scene_far))
+            c = dict(ext=f["extrinsic"], K=f["intrinsic"], c2w=ext, Kinv=torch.linalg.inv(K), campos=campos[0],
+                     row=torch.cat([view.reshape(16), proj.reshape(16), tanfov.reshape(2)]))
+            self._cams[i] = c
+        return c
+
+    def _camera_rows(self, ids):
+        """(len(ids), 34) host tensor of camera rows"""
+        return torch.stack([self._camera(i)["row"] for i in ids])
 
     def begin_training(self):
         """Everything train() sets up once per call (mapping/gaussian_map.py:71-74): fresh Adam
@@ -384,7 +452,7 @@ class GaussianMap:
         sampler = WeightedSampler(self.cfg.sampler, T)
         B = sampler.v if self.dist is None else self.dist.local_batch(sampler.v)
         _, H, W = self.training_data[0]["rgb"].shape
-        fovs, views, projs, tanfovs = self._camera_table()           # host tensors (T, .)
+        cam_rows = self._camera_rows(range(T))                       # host (T, 34), cached per keyframe
         # batch slots whose keyframe never changes (the sampler's active frames come first in the
         # sampled ids): local slot k of this rank is global slot rank*B + k
         first = 0 if self.dist is None else self.dist.rank * B
@@ -392,7 +460,7 @@ class GaussianMap:
         return SimpleNamespace(fixed=fixed,
             sampler=sampler, B=B, H=H, W=W,
             eng=_TrainEngine(self, B, H, W, self.dist,
-                             cam_table=torch.cat([views, projs, tanfovs], dim=1).contiguous().to(self.device)),
+                             cam_table=cam_rows.to(self.device)),
             perf_host=self.training_performance.detach().float().cpu().clone(), log=[])
 
     def train_step(self, ctx, ids=None):
@@ -444,89 +512,99 @@ class GaussianMap:
             setattr(self, n, getattr(self, n).detach().float().contiguous())
 
     # ------------------------------------------------------------------ :141-246
+    POST_CHUNK = 16          # views per count-render launch when all T keyframes are re-rendered
+
+    def _render_raw(self, ids, H, W, *, render_mask=None, require_importance=False, front_only=False,
+                    with_confidence=False):
+        """Forward-only render of keyframes `ids` straight from the RAW parameters (activations fused
+        in the projection kernel: no get_attr() pass), cameras from the per-keyframe cache."""
+        rows = self._camera_rows(ids).to(self.device)
+        B = len(ids)
+        N = self._means.shape[0]
+        rb = RenderBatch(self._means, self._scales, self._rotations, self._opacities,
+                         self._harmonics.reshape(N, 3), self.get_confidences if with_confidence else None,
+                         rows[:, :16], rows[:, 16:32], rows[:, 32:34], self.background_color, H, W,
+                         render_mask=render_mask, require_importance=require_importance, front_only=front_only,
+                         param_mode=L.PARAMS_RAW, scale_factor=self.scale_factor, scale_max=0.05,
+                         pool=lambda nbytes: self._pool.get("workspace_aux", nbytes))
+        rb.forward(check_overflow=True)
+        return rb
+
     def post_processing(self):
+        """:141-232.  One count-only render of the newest keyframe (all T keyframes every
+        prune_interval-th time, in chunks) from the raw parameters, the confidence bookkeeping in one
+        kernel (ags_view_stats_update) and the prune as one ordered compaction (ags_prune_compact)."""
         T = len(self.training_data)
         require_prune = T % self.prune_interval == 0
         ids = list(range(T)) if require_prune else [T - 1]
-        ext = torch.stack([self.training_data[i]["extrinsic"] for i in ids]).to(self.device)
-        intr = torch.stack([self.training_data[i]["intrinsic"] for i in ids]).to(self.device)
-        dgt = torch.stack([self.training_data[i]["depth"] for i in ids]).to(self.device)
-        depth_ranges = self.training_data[-1]["depth_range"]
-        _, _, H, W = dgt.shape
-        counts = O.GaussianRenderer(
-            ext, intr, self.get_attr(), self.background_color, (self.scene_near, self.scene_far),
-            (H, W), self.device, render_masks=(dgt > 0.0).float(),
-        ).render_view_all(require_importance=True, front_only=True)[7]
-        update_mask = counts[-1] >= 1.0
-        self.view_supports = self.view_supports + update_mask.float()
-        if self.use_view_distribution:
-            means = self.get_means.detach()
-            normals = self.get_normals.detach()
-            vdir = ext[-1:, :3, 3] - means
-            dist = torch.linalg.norm(vdir, dim=1)
-            vdir = vdir / dist.unsqueeze(-1)
-            delta = vdir[update_mask] - self.view_means[update_mask]
-            self.view_means[update_mask] += delta / self.view_supports[update_mask].unsqueeze(-1)
-            cos = torch.clamp(torch.sum(normals * vdir, 1), min=0, max=1)
-            dfac = torch.clamp(dist / float(depth_ranges[1]), min=0, max=1)
-            self.view_scores[update_mask] += (1 - dfac)[update_mask] * cos[update_mask]
+        self._make_contiguous()
+        _, H, W = self.training_data[-1]["depth"].shape
+        N = self._means.shape[0]
+        seen = None                                   # (1,N) int32: times counted over all views but the last chunk
+        last = None
+        for c0 in range(0, len(ids), self.POST_CHUNK):
+            chunk = ids[c0:c0 + self.POST_CHUNK]
+            dgt = torch.stack([self.training_data[i]["depth"] for i in chunk]).to(self.device)
+            rb = self._render_raw(chunk, H, W, render_mask=(dgt > 0.0).float(), require_importance=True,
+                                  front_only=True)
+            if last is not None:
+                part = last.sum(0, keepdim=True, dtype=torch.int32)
+                seen = part if seen is None else seen + part
+            last = rb.count
+        for n in ["view_scores", "view_supports", "view_means"]:
+            setattr(self, n, getattr(self, n).float().contiguous())
+        ops.view_stats_update(last[-1], self._means, self._rotations, self._camera(T - 1)["campos"],
+                              float(self.training_data[-1]["depth_range"][1]), self.use_view_distribution,
+                              self.view_supports, self.view_means, self.view_scores)
         if require_prune:
-            vis_mask = torch.sum(counts, dim=0) >= 1.0
-            self.prune(~vis_mask)
+            counts = last if seen is None else torch.cat([seen, last], 0).contiguous()
+            self._compact(counts=counts)
+
+    def _compact(self, counts=None, prune_mask=None):
+        N = self._means.shape[0]
+        st = self._store
+        st.adopt(self, 0)
+        n = ops.prune_compact(st.buf, st.other(), N, counts=counts, prune_mask=prune_mask, pool=self._pool)
+        st.swap()
+        st.expose(self, n)
+        print(f"delete {N - n} gaussians")
 
     def prune(self, prune_mask):
-        prune_mask += self.get_opacities < 0.1              # quirk Q5: in-place OR on the caller's mask
-        keep = ~prune_mask.bool()
-        for n in ["_means", "_scales", "_rotations", "_opacities", "_harmonics", "view_scores",
-                  "view_supports", "view_means"]:
-            setattr(self, n, getattr(self, n)[keep])
-        print(f"delete {int(torch.sum(prune_mask))} gaussians")
+        """:234-246.  `prune_mask` (N,) bool is OR-ed in place with opacity < 0.1 (quirk Q5)."""
+        if prune_mask.dtype not in (torch.bool, torch.uint8) or not prune_mask.is_contiguous():
+            raise TypeError("prune_mask must be a contiguous bool tensor")
+        self._make_contiguous()
+        self._compact(prune_mask=prune_mask)
 
     # ------------------------------------------------------------------ :294-489
     def add_gaussians(self, dataframe):
+        """:294-468 on the device: bilateral filter (ags_smooth_depth), render of the current map from
+        the raw parameters, then ONE fused pass (ags_spawn) for back-projection, normals, rejection
+        tests, cal_mask, the random voxel filter and the in-place append.  The voxel filter's random
+        draw is seeded from torch's CPU generator (torch.manual_seed reproduces it; replicas agree)."""
         dev = self.device
-        rgb, depth = dataframe["rgb"].to(dev), dataframe["depth"].to(dev)
-        intrinsic, extrinsic = dataframe["intrinsic"].to(dev), dataframe["extrinsic"].to(dev)
+        rgb = dataframe["rgb"].to(dev).float().contiguous()
+        depth = dataframe["depth"].to(dev).float().contiguous()
         _, H, W = rgb.shape
-        smooth = O.get_smooth_depth_device(depth)          # (1,H,W); reference: cv2 on the CPU, :297-298
-        valid = (depth > 0.0).view(-1)
-        origins, directions = O.get_world_rays(H, W, extrinsic, intrinsic, dev)
-        pcd = origins + directions * depth.view(-1, 1)
-        P = H * W
-        normals_w = torch.zeros(P, 3, device=dev)
-        normals_w[:, 2] = 1.0
-        n_cam = O.depth2normal(smooth, valid.view(1, H, W), fov=(np.pi / 3, np.pi / 3)).permute(1, 2, 0).reshape(-1, 3)
-        valid = valid & (torch.sum(n_cam ** 2, dim=-1) > 0.0)
-        n_world = n_cam @ extrinsic[:3, :3].t()
-        normals_w[valid] = n_world[valid]
-        cos = torch.sum(F.normalize(directions, dim=1) * normals_w, dim=-1)
-        valid = valid & (cos < -0.01)
-        pred = None
-        if self.is_init:
-            r = O.GaussianRenderer(extrinsic[None], intrinsic[None], self.get_attr(), self.background_color,
-                                   (self.scene_near, self.scene_far), (H, W), dev).render_view_all()
-            pred = dict(rgb=r[0], depth=r[1].squeeze(1), opacity=r[3].squeeze(1))
-        rot_new, _ = O.normal2rotation(normals_w)
-        valid = valid & ~torch.any(rot_new.isnan(), dim=1)
-        select = self.cal_mask(rgb[None], depth[None], pred).to(dev) & valid
-        sel_idx = torch.nonzero(select).flatten()
-        keep = O.voxel_downsample(pcd[select])
-        sel_idx = sel_idx[keep]
-        n_new = sel_idx.numel()
-        scales_new = torch.zeros(n_new, 3, device=dev)
-        scales_new[:, -1] -= 1e10
-        cat = lambda a, b: torch.cat((a.detach(), b.float()), dim=0)
-        self._means = cat(self._means, pcd[sel_idx])
-        self._scales = cat(self._scales, scales_new)
-        self._harmonics = cat(self._harmonics, rgb.permute(1, 2, 0).reshape(-1, 3)[sel_idx][:, None, :])
-        self._opacities = cat(self._opacities, torch.zeros(n_new, device=dev))
-        self._rotations = cat(self._rotations, rot_new[sel_idx])
-        self.view_scores = cat(self.view_scores, torch.zeros(n_new, device=dev))
-        self.view_supports = cat(self.view_supports, torch.zeros(n_new, device=dev))
-        self.view_means = cat(self.view_means, torch.zeros(n_new, 3, device=dev))
         self.training_data.append(dataframe)
         self.training_performance = torch.cat(
             (self.training_performance, torch.tensor([10.0], device=dev)), 0)
+        k = len(self.training_data) - 1
+        cam = self._camera(k)
+        smooth = O.get_smooth_depth_device(depth)          # (1,H,W); reference: cv2 on the CPU, :297-298
+        pred = None
+        if self.is_init:
+            self._make_contiguous()
+            rb = self._render_raw([k], H, W)
+            pred = (rb.rgb, rb.depth, rb.opacity)
+        n_old = self._means.shape[0]
+        st = self._store
+        seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+        st.adopt(self, H * W)                              # room for one Gaussian per pixel: no retry needed
+        n_new, _, wanted = ops.spawn(rgb, depth, smooth, cam["c2w"], cam["Kinv"], pred, st.buf, n_old, st.cap,
+                                     error_thres=self.error_thres, voxel_size=0.02, seed=seed, pool=self._pool)
+        assert wanted == n_new
+        st.expose(self, n_old + n_new)
 
     def cal_mask(self, rgb_gt, depth_gt, pred):
         """:470-489 -- spawn where rgb MSE > error_thres, opacity < 0.5 or the render is > 5 % behind."""

@@ -80,11 +80,45 @@ class DistAdamArgs(C.Structure):
     ]
 
 
+class SpawnArgs(C.Structure):
+    _fields_ = [
+        ("H", C.c_int32), ("W", C.c_int32),
+        ("rgb", _f), ("depth", _f), ("depth_smooth", _f),
+        ("c2w", C.c_float * 16), ("Kinv", C.c_float * 9),
+        ("pred_rgb", _f), ("pred_depth", _f), ("pred_opacity", _f),
+        ("error_thres", C.c_float), ("voxel_size", C.c_float), ("seed", C.c_uint32),
+        ("n_old", C.c_int32), ("capacity", C.c_int32),
+        ("means", _f), ("scales", _f), ("rotations", _f), ("opacities", _f), ("harmonics", _f),
+        ("view_scores", _f), ("view_supports", _f), ("view_means", _f),
+        ("counters", _f), ("select_out", _f),
+        ("workspace", _f), ("workspace_bytes", C.c_size_t), ("stream", _f),
+    ]
+
+
+class PruneArgs(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("T", C.c_int32), ("counts", _f), ("prune_mask", _f),
+        ("src", _f * 8), ("dst", _f * 8), ("n_kept", _f),
+        ("workspace", _f), ("workspace_bytes", C.c_size_t), ("stream", _f),
+    ]
+
+
+class UtilityArgs(C.Structure):
+    _fields_ = [
+        ("V", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("M", C.c_int32),
+        ("depth", _f), ("confidence", _f), ("valid", _f), ("voxel_centers", _f), ("unexplored", _f),
+        ("w2c", _f), ("K", _f), ("depth_lo", C.c_float), ("depth_hi", C.c_float),
+        ("explore", _f), ("exploit", _f), ("stream", _f),
+    ]
+
+
 _lib = None
 
 EXPORTS = ["ags_scratch_bytes", "ags_render_forward", "ags_render_backward", "ags_render_stage",
            "ags_loss_scratch_bytes", "ags_loss_forward_backward", "ags_postprocess", "ags_adam_step",
            "ags_dist_adam_step", "ags_smooth_depth", "ags_stage_cameras",
+           "ags_spawn_scratch_bytes", "ags_spawn", "ags_view_stats_update", "ags_prune_scratch_bytes",
+           "ags_prune_compact", "ags_view_utility",
            "ags_last_error", "ags_version"]
 
 
@@ -114,6 +148,20 @@ def load():
     lib.ags_stage_cameras.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ags_stage_cameras.restype = C.c_int
+    lib.ags_spawn_scratch_bytes.restype = C.c_size_t
+    lib.ags_spawn_scratch_bytes.argtypes = [C.c_int32] * 2
+    lib.ags_spawn.argtypes = [C.POINTER(SpawnArgs)]
+    lib.ags_spawn.restype = C.c_int
+    lib.ags_view_stats_update.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                          C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]
+    lib.ags_view_stats_update.restype = C.c_int
+    lib.ags_prune_scratch_bytes.restype = C.c_size_t
+    lib.ags_prune_scratch_bytes.argtypes = [C.c_int32]
+    lib.ags_prune_compact.argtypes = [C.POINTER(PruneArgs)]
+    lib.ags_prune_compact.restype = C.c_int
+    lib.ags_view_utility.argtypes = [C.POINTER(UtilityArgs)]
+    lib.ags_view_utility.restype = C.c_int
     lib.ags_dist_adam_step.argtypes = [C.POINTER(DistAdamArgs)]
     lib.ags_dist_adam_step.restype = C.c_int
     lib.ags_postprocess.argtypes = [C.c_int32] * 3 + [C.c_void_p] * 7
@@ -133,7 +181,7 @@ def check(rc, what):
 
 
 def ptr(t):
-    """Device pointer of a contiguous float32/int32 CUDA tensor (or None)."""
+    """Device pointer of a contiguous CUDA tensor (or None)."""
     if t is None:
         return None
     if not t.is_cuda:

@@ -111,3 +111,105 @@ def smooth_depth(depth, d=15, sigma_color=0.5, sigma_space=20.0):
     L.check(lib.ags_smooth_depth(H, W, L.ptr(src), L.ptr(out), d, sigma_color, sigma_space, L.ptr(scratch),
                                  L.current_stream(src.device)), "ags_smooth_depth")
     return out.reshape(shape)
+
+
+# ------------------------------------------------------------------ per-keyframe map maintenance
+MAP_FIELDS = (("means", 3), ("scales", 3), ("rotations", 4), ("opacities", 1), ("harmonics", 3),
+              ("view_scores", 1), ("view_supports", 1), ("view_means", 3))
+
+
+def _u8_scratch(pool, name, nbytes, device):
+    """256-byte aligned scratch pointer of >= nbytes (from a buffer pool when given)."""
+    t = pool.get(name, nbytes + 256) if pool is not None else torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+    return t, (t.data_ptr() + 255) & ~255
+
+
+def spawn(rgb, depth, depth_smooth, c2w, Kinv, pred, store, n_old, capacity, *, error_thres, voxel_size=0.02,
+          seed=0, select_out=None, pool=None):
+    """ags_spawn: append the new Gaussians of one RGB-D keyframe to the capacity buffers `store`
+    (dict name -> (capacity, width) float32 CUDA tensors, MAP_FIELDS).  `pred` = (rgb, depth, opacity)
+    render of the current map at the keyframe's pose or None.  c2w (4,4) / Kinv (3,3) are HOST
+    tensors.  Returns (appended, candidates, wanted) -- one 16-byte D2H read, the only sync."""
+    lib = L.load()
+    dev = rgb.device
+    _, H, W = rgb.shape
+    a = L.SpawnArgs()
+    a.H, a.W = H, W
+    a.rgb, a.depth, a.depth_smooth = L.ptr(rgb), L.ptr(depth), L.ptr(depth_smooth)
+    a.c2w = (C.c_float * 16)(*[float(x) for x in c2w.reshape(-1).tolist()])
+    a.Kinv = (C.c_float * 9)(*[float(x) for x in Kinv.reshape(-1).tolist()])
+    if pred is not None:
+        a.pred_rgb, a.pred_depth, a.pred_opacity = L.ptr(pred[0]), L.ptr(pred[1]), L.ptr(pred[2])
+    a.error_thres, a.voxel_size, a.seed = float(error_thres), float(voxel_size), int(seed) & 0xffffffff
+    a.n_old, a.capacity = int(n_old), int(capacity)
+    for name, _ in MAP_FIELDS:
+        setattr(a, name, L.ptr(store[name]))
+    counters = torch.empty(4, dtype=torch.int32, device=dev)
+    a.counters = L.ptr(counters)
+    a.select_out = L.ptr(select_out)
+    keep, a.workspace = _u8_scratch(pool, "spawn", lib.ags_spawn_scratch_bytes(H, W), dev)
+    a.workspace_bytes = lib.ags_spawn_scratch_bytes(H, W)
+    a.stream = L.current_stream(dev)
+    L.check(lib.ags_spawn(C.byref(a)), "ags_spawn")
+    c = counters.tolist()
+    return c[0], c[1], c[2]
+
+
+def view_stats_update(count_last, means, rotations_raw, cam_pos, depth_max, use_view_distribution,
+                      view_supports, view_means, view_scores):
+    """ags_view_stats_update (mapping/gaussian_map.py:195-227), in place."""
+    lib = L.load()
+    N = means.shape[0]
+    L.check(lib.ags_view_stats_update(N, L.ptr(count_last), L.ptr(means), L.ptr(rotations_raw), float(cam_pos[0]),
+                                      float(cam_pos[1]), float(cam_pos[2]), float(depth_max),
+                                      int(bool(use_view_distribution)), L.ptr(view_supports), L.ptr(view_means),
+                                      L.ptr(view_scores), L.current_stream(means.device)), "ags_view_stats_update")
+
+
+def prune_compact(src, dst, N, *, counts=None, prune_mask=None, pool=None):
+    """ags_prune_compact: compact the eight SoA tensors of `src` (dict, MAP_FIELDS) into `dst`, dropping
+    Gaussians flagged in `prune_mask` (uint8/bool (N), updated in place: quirk Q5), never counted in
+    `counts` ((T,N) int32) or with sigmoid(opacity) < 0.1.  Returns the number kept (one 4-byte D2H)."""
+    lib = L.load()
+    dev = src["means"].device
+    a = L.PruneArgs()
+    a.N = int(N)
+    a.T = int(counts.shape[0]) if counts is not None else 0
+    a.counts = L.ptr(counts)
+    if prune_mask is not None:
+        assert prune_mask.dtype in (torch.uint8, torch.bool) and prune_mask.numel() == N
+        a.prune_mask = L.ptr(prune_mask)
+    for k, (name, _) in enumerate(MAP_FIELDS):
+        a.src[k], a.dst[k] = L.ptr(src[name]), L.ptr(dst[name])
+    n_kept = torch.empty(1, dtype=torch.int32, device=dev)
+    a.n_kept = L.ptr(n_kept)
+    need = lib.ags_prune_scratch_bytes(int(N))
+    keep, a.workspace = _u8_scratch(pool, "prune", need, dev)
+    a.workspace_bytes = need
+    a.stream = L.current_stream(dev)
+    L.check(lib.ags_prune_compact(C.byref(a)), "ags_prune_compact")
+    return int(n_kept.item())
+
+
+def view_utility(depth, confidence, voxel_centers, unexplored, w2c, K, depth_range, valid=None):
+    """ags_view_utility: (explore (V,), exploit (V,)) of V rendered candidate views (planning/
+    confidence.py:69-101, planning/exploration.py:62-86).  depth/confidence (V,h,w) float32; voxel_centers
+    (M,3); unexplored (M) bool; w2c (V,4,4) inverse extrinsics; K (V,3,3) normalised intrinsics."""
+    lib = L.load()
+    dev = depth.device
+    V, h, w = depth.shape
+    a = L.UtilityArgs()
+    a.V, a.h, a.w, a.M = V, h, w, int(voxel_centers.shape[0])
+    un = unexplored.to(torch.uint8).contiguous() if unexplored.dtype != torch.uint8 else unexplored.contiguous()
+    va = None if valid is None else valid.to(torch.uint8).contiguous()
+    vc, wm, km = voxel_centers.float().contiguous(), w2c.float().contiguous(), K.float().contiguous()
+    dc, cc = depth.float().contiguous(), confidence.float().contiguous()      # keep the temporaries alive
+    a.depth, a.confidence, a.valid = L.ptr(dc), L.ptr(cc), L.ptr(va)
+    a.voxel_centers, a.unexplored, a.w2c, a.K = L.ptr(vc), L.ptr(un), L.ptr(wm), L.ptr(km)
+    a.depth_lo, a.depth_hi = float(depth_range[0]), float(depth_range[1])
+    explore = torch.empty(V, dtype=torch.float32, device=dev)
+    exploit = torch.empty(V, dtype=torch.float32, device=dev)
+    a.explore, a.exploit = L.ptr(explore), L.ptr(exploit)
+    a.stream = L.current_stream(dev)
+    L.check(lib.ags_view_utility(C.byref(a)), "ags_view_utility")
+    return explore, exploit

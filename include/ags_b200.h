@@ -223,6 +223,104 @@ int ags_dist_adam_step(const AgsDistAdamArgs* args);
 int ags_stage_cameras(const float* table, int32_t T, const int32_t* ids_host, int32_t B,
                       float* viewmatrix, float* projmatrix, float* tanfov, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Per-keyframe map maintenance: the map lives in CAPACITY
+ * buffers owned by the caller (row-major SoA, `capacity` rows each); the kernels below append to /
+ * compact them on the device, and the caller reads back only the new row count.
+ *
+ * ags_spawn   mapping/gaussian_map.py:294-468 (add_gaussians) after the bilateral filter and the
+ *             optional render of the current map: per pixel back-projection (utils/operations.py:
+ *             372-392,464-478,544-569), normal from the smoothed depth with the hard-wired 60 x 60
+ *             degree fov (gaussian_map.py:316-322 -> operations.py:172-219), back-facing / NaN
+ *             rejection (:324-335,386-387), normal2rotation (operations.py:481-541), cal_mask
+ *             (gaussian_map.py:470-489), the voxel filter (operations.py:603-625: ONE randomly chosen
+ *             candidate per occupied voxel of edge voxel_size; here a device hash table with a random
+ *             priority per candidate instead of unique/randperm/scatter), and the append of the
+ *             survivors in pixel order (gaussian_map.py:403-462: raw scales (0,0,-1e10), raw opacity
+ *             0, colour = pixel rgb, zero view statistics).
+ *             Coordinates must satisfy |p / voxel_size| < 2^20 (20 km at 2 cm).
+ *             counters[0] = rows appended (clamped so that n_old + appended <= capacity),
+ *             counters[1] = candidates before the voxel filter, counters[2] = survivors wanted
+ *             (> counters[0] only if the capacity was too small: grow and call again). */
+typedef struct AgsSpawnArgs {
+    int32_t H, W;
+    const float* rgb;              /* (3,H,W) keyframe colour */
+    const float* depth;            /* (1,H,W) sensor depth, <= 0 invalid */
+    const float* depth_smooth;     /* (1,H,W) ags_smooth_depth(depth) */
+    float c2w[16];                 /* keyframe extrinsic, row-major camera-to-world, BY VALUE */
+    float Kinv[9];                 /* inverse of the normalised intrinsic, row-major, BY VALUE */
+    const float* pred_rgb;         /* (3,H,W) render of the current map at this pose, or NULL (empty map) */
+    const float* pred_depth;       /* (1,H,W) */
+    const float* pred_opacity;     /* (1,H,W) */
+    float error_thres;             /* cfg.error_thres */
+    float voxel_size;              /* 0.02; <= 0 disables the voxel filter */
+    uint32_t seed;                 /* random priorities of the voxel filter */
+    int32_t n_old, capacity;       /* rows in use / rows allocated in the buffers below */
+    float* means;                  /* (capacity,3) */
+    float* scales;                 /* (capacity,3) */
+    float* rotations;              /* (capacity,4) */
+    float* opacities;              /* (capacity)   */
+    float* harmonics;              /* (capacity,3) */
+    float* view_scores;            /* (capacity)   */
+    float* view_supports;          /* (capacity)   */
+    float* view_means;             /* (capacity,3) */
+    int32_t* counters;             /* (4) device, see above */
+    uint8_t* select_out;           /* optional (H*W): 1 = candidate before the voxel filter, 2 = appended */
+    void* workspace; size_t workspace_bytes;   /* >= ags_spawn_scratch_bytes(H, W) */
+    void* stream;
+} AgsSpawnArgs;
+size_t ags_spawn_scratch_bytes(int32_t H, int32_t W);
+int ags_spawn(const AgsSpawnArgs* args);
+
+/* ags_view_stats_update   mapping/gaussian_map.py:195-227: confidence bookkeeping after a keyframe.
+ *             For every Gaussian counted (count_last >= 1) in the newest keyframe: supports += 1,
+ *             view_means += (dir - view_means)/supports, view_scores += (1 - clamp(dist/depth_max))
+ *             * clamp(normal . dir), dir = normalised vector to the camera, normal = third column
+ *             of R(normalize(raw rotation)).  In place, one thread per Gaussian. */
+int ags_view_stats_update(int32_t N, const int32_t* count_last, const float* means, const float* rotations_raw,
+                          float cam_x, float cam_y, float cam_z, float depth_max, int32_t use_view_distribution,
+                          float* view_supports, float* view_means, float* view_scores, void* stream);
+
+/* ags_prune_compact   mapping/gaussian_map.py:229-246 (post_processing's prune + prune()): drops the
+ *             Gaussians flagged in prune_mask (which is OR-ed IN PLACE with sigmoid(opacity) < 0.1,
+ *             quirk Q5) and, if `counts` is given, those never counted in any of the T views
+ *             (sum_t counts[t][i] < 1); the survivors of all eight SoA tensors are written, order
+ *             preserved, to the dst buffers (src and dst must not overlap: ping-pong stores).
+ *             n_kept (device int32) receives the new row count. */
+typedef struct AgsPruneArgs {
+    int32_t N, T;
+    const int32_t* counts;         /* (T,N) or NULL */
+    uint8_t* prune_mask;           /* (N) in/out, or NULL (treated as all zero, not written) */
+    const float* src[8];           /* means, scales, rotations, opacities, harmonics, view_scores, view_supports, view_means */
+    float* dst[8];
+    int32_t* n_kept;               /* device */
+    void* workspace; size_t workspace_bytes;   /* >= ags_prune_scratch_bytes(N) */
+    void* stream;
+} AgsPruneArgs;
+size_t ags_prune_scratch_bytes(int32_t N);
+int ags_prune_compact(const AgsPruneArgs* args);
+
+/* ags_view_utility   planning/confidence.py:69-101 and planning/exploration.py:62-86 for V rendered
+ *             candidate views at once (the reference loops over views with ~40 ATen launches and a
+ *             nonzero sync each): explore[v] = |{voxels visible in view v (mapping/voxel_map.py:
+ *             226-278) and unexplored}| / M, exploit[v] = mean((1 - conf') * depth' / depth_hi).
+ *             One CTA per view; no atomics (deterministic). */
+typedef struct AgsUtilityArgs {
+    int32_t V, h, w, M;
+    const float* depth;            /* (V,h,w) rendered depth, 0 where nothing was rendered */
+    const float* confidence;       /* (V,h,w) rendered confidence */
+    const uint8_t* valid;          /* (V,h,w) simulator validity mask or NULL (all valid) */
+    const float* voxel_centers;    /* (M,3) */
+    const uint8_t* unexplored;     /* (M) */
+    const float* w2c;              /* (V,16) inverse extrinsics, row-major */
+    const float* K;                /* (V,9) normalised intrinsics, row-major */
+    float depth_lo, depth_hi;      /* simulator.depth_range */
+    float* explore;                /* (V) */
+    float* exploit;                /* (V) */
+    void* stream;
+} AgsUtilityArgs;
+int ags_view_utility(const AgsUtilityArgs* args);
+
 const char* ags_last_error(void);
 int ags_version(void);
 

@@ -284,6 +284,27 @@ def train_iterations(state, frames, frame_id_batches, bg, near_far, hw, rasteriz
 
 
 # ---------------------------------------------------------------- post-processing + prune
+def view_stats_update(state, upd, cam_pos, depth_max, use_view_distribution=True):
+    """mapping/gaussian_map.py:195-227: confidence bookkeeping for the Gaussians counted in the newest
+    keyframe (`upd` (N,) bool): supports += 1; running mean of the unit view direction; score +=
+    (1 - clamp(dist/depth_max)) * clamp(normal . dir).  Updates `state` in place."""
+    state["view_supports"] = state["view_supports"] + upd.float()
+    if not use_view_distribution:
+        return
+    normals = F.normalize(rr.quat_to_rotmat(F.normalize(state["rotations"]))[:, :3, 2])
+    vdir = cam_pos[None] - state["means"]
+    dist = torch.linalg.norm(vdir, dim=1)
+    vdir = vdir / dist[:, None]
+    vm = state["view_means"].clone()
+    vm[upd] += (vdir[upd] - vm[upd]) / state["view_supports"][upd][:, None]
+    state["view_means"] = vm
+    cos = torch.clamp((normals * vdir).sum(1), 0, 1)
+    dfac = torch.clamp(dist / depth_max, 0, 1)
+    vs = state["view_scores"].clone()
+    vs[upd] += ((1 - dfac) * cos)[upd]
+    state["view_scores"] = vs
+
+
 def post_process(state, frames, bg, near_far, hw, prune_interval=5, rasterize_fn=None,
                  scale_factor=0.01, use_view_distribution=True):
     """mapping/gaussian_map.py:141-246.  Confidence bookkeeping from the newest keyframe's
@@ -303,22 +324,7 @@ def post_process(state, frames, bg, near_far, hw, prune_interval=5, rasterize_fn
     counts = render_view_all(rasterize_fn, ext, intr, attrs, bg, near_far, hw,
                              render_masks=(d_gt > 0.0).float(), require_importance=True,
                              front_only=True)[7]
-    upd = counts[-1] >= 1.0
-    state["view_supports"] = state["view_supports"] + upd.float()
-    if use_view_distribution:
-        means = state["means"]
-        normals = F.normalize(rr.quat_to_rotmat(F.normalize(state["rotations"]))[:, :3, 2])
-        vdir = ext[-1:, :3, 3] - means
-        dist = torch.linalg.norm(vdir, dim=1)
-        vdir = vdir / dist[:, None]
-        vm = state["view_means"].clone()
-        vm[upd] += (vdir[upd] - vm[upd]) / state["view_supports"][upd][:, None]
-        state["view_means"] = vm
-        cos = torch.clamp((normals * vdir).sum(1), 0, 1)
-        dfac = torch.clamp(dist / frames[-1]["depth_range"][1], 0, 1)
-        vs = state["view_scores"].clone()
-        vs[upd] += ((1 - dfac) * cos)[upd]
-        state["view_scores"] = vs
+    view_stats_update(state, counts[-1] >= 1.0, ext[-1, :3, 3], frames[-1]["depth_range"][1], use_view_distribution)
     keep = torch.ones(state["means"].shape[0], dtype=torch.bool)
     if prune:
         never_seen = ~(counts.sum(0) >= 1.0)

@@ -40,14 +40,18 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_struct_layouts_match_c(lib, tmp_path):
     prog = tmp_path / "sz.c"
-    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ags_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ags_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                     'sizeof(AgsRenderArgs),sizeof(AgsRenderGradArgs),sizeof(AgsLossArgs),sizeof(AgsAdamArgs),'
-                    'offsetof(AgsRenderArgs,workspace_bytes),offsetof(AgsLossArgs,workspace),offsetof(AgsAdamArgs,skip_flag));return 0;}\n')
+                    'offsetof(AgsRenderArgs,workspace_bytes),offsetof(AgsLossArgs,workspace),offsetof(AgsAdamArgs,skip_flag),'
+                    'sizeof(AgsSpawnArgs),sizeof(AgsPruneArgs),sizeof(AgsUtilityArgs),offsetof(AgsSpawnArgs,counters),'
+                    'offsetof(AgsPruneArgs,n_kept),offsetof(AgsUtilityArgs,explore));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [C.sizeof(lib.RenderArgs), C.sizeof(lib.RenderGradArgs), C.sizeof(lib.LossArgs), C.sizeof(lib.AdamArgs),
-            lib.RenderArgs.workspace_bytes.offset, lib.LossArgs.workspace.offset, lib.AdamArgs.skip_flag.offset]
+            lib.RenderArgs.workspace_bytes.offset, lib.LossArgs.workspace.offset, lib.AdamArgs.skip_flag.offset,
+            C.sizeof(lib.SpawnArgs), C.sizeof(lib.PruneArgs), C.sizeof(lib.UtilityArgs), lib.SpawnArgs.counters.offset,
+            lib.PruneArgs.n_kept.offset, lib.UtilityArgs.explore.offset]
     assert got == want
 
 
