@@ -91,6 +91,9 @@ __device__ __forceinline__ bool bbox_hits(const float4 bb, const WarpBlock& b) {
 }
 
 // K4 ---------------------------------------------------------------------------------------------
+#ifndef AGS_RANKSORT
+#define AGS_RANKSORT 1        // single-batch tiles: rank sort fused with the staging (0 = bitonic prologue)
+#endif
 #ifndef AGS_FWD_MINB
 #define AGS_FWD_MINB 6
 #endif
@@ -121,7 +124,40 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
     // behind the compositing of the other resident CTAs).  Keys (depth_bits<<32 | id) are unique, so
     // the bitonic network is deterministic; ids go to inst_sorted for the batches below and for the
     // backward.  Tiles above the shared-memory capacity were sorted by tile_sort_kernel beforehand.
-    if (n > 0 && n <= FUSED_SORT_MAX) {
+    int32_t first_id = -1;
+    bool prestaged = false;
+    const size_t vN = (size_t)v * a.N;
+    if (AGS_RANKSORT && n > 0 && n <= BATCH) {
+        // ---- single-batch tile (the common case): rank sort fused with the staging.  Thread t owns
+        // key t, fetches that splat's record while it counts the keys in front of its own
+        // (broadcast shared-memory reads, no barrier per stage), and stores the record at its rank.
+        const uint64_t my = (tid < n) ? w.inst_key[off + tid] : ~0ull;
+        if (tid < n) s_keys[tid] = my;
+        const int id = (int)(uint32_t)(my & 0xffffffffu);
+        float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+        if (tid < n) {
+            g0 = ldg4(w.geom0 + vN + id);
+            g1 = ldg4(w.geom1 + vN + id);
+        }
+        __syncthreads();
+        int rank = 0;
+        if (tid < n) {
+#pragma unroll 4
+            for (int j = 0; j < n; ++j) rank += (s_keys[j] < my) ? 1 : 0;
+        }
+        __syncthreads();            // every key has been read: the records may overwrite them
+        if (tid < n) {
+            s_id[rank] = id;
+            SplatRec& r = s_rec[rank];
+            r.g0 = make_float4(g0.x, g0.y, g0.z * AGS_LOG2E, g0.w * AGS_LOG2E);   // conic * log2(e)
+            r.g1 = make_float4(g1.x * AGS_LOG2E, g1.y, g1.z, g1.w);
+            r.f0 = ldg4(w.feat0 + vN + id);
+            r.f1 = ldg4(w.feat1 + vN + id);
+            r.bb = splat_bbox(g0, g1);
+            w.inst_sorted[off + rank] = id;                                       // the backward walks the same order
+        }
+        prestaged = true;
+    } else if (n > 0 && n <= FUSED_SORT_MAX) {
         const uint64_t* keys = w.inst_key + off;
         int m = 2;
         while (m < n) m <<= 1;
@@ -161,10 +197,12 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
                 }
             }
         }
+        // the first batch takes its ids straight from shared memory (register), so the global
+        // store of the sorted ids (needed by later batches and by the backward) is off the critical path
+        if (tid < n) first_id = (int32_t)(s_keys[tid] & 0xffffffffu);
         for (int k = tid; k < n; k += 256) w.inst_sorted[off + k] = (int32_t)(s_keys[k] & 0xffffffffu);
         __syncthreads();            // ids visible to the whole CTA; s_raw free for the records
     }
-    const size_t vN = (size_t)v * a.N;
     const size_t P = (size_t)a.H * a.W;
     const size_t pix = (size_t)py * a.W + px;
     const bool want_imp = a.require_importance != 0;
@@ -179,8 +217,8 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
     for (int base = 0; base < n; base += BATCH) {
         if (__syncthreads_and(warp_done)) break;
         const int j = base + tid;
-        if (j < n) {
-            const int id = w.inst_sorted[off + j];
+        if (j < n && !prestaged) {
+            const int id = (base == 0 && first_id >= 0) ? first_id : w.inst_sorted[off + j];
             const size_t idx = vN + id;
             const float4 g0 = ldg4(w.geom0 + idx), g1 = ldg4(w.geom1 + idx);
             s_id[tid] = id;

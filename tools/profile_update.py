@@ -32,8 +32,11 @@ for i in range(12):
     t0 = sync(); gm.add_gaussians(frame)
     t1 = sync(); ctx = gm.begin_training()
     t2 = sync()
+    its = []
     for _ in range(10):
-        gm.train_step(ctx)
+        a = sync(); gm.train_step(ctx); its.append(1e3 * (sync() - a))
+    if i == 11:
+        print("   per-iteration ms (synchronised):", [round(x, 2) for x in its], "instances", ctx.log[-1][2], "visible", ctx.log[-1][3])
     gm.end_training(ctx)
     t3 = sync(); gm.post_processing(); gm.is_init = True
     t4 = sync()
