@@ -1,0 +1,83 @@
+"""Host-side mirror of the utility evaluation of the reference's planners (SURVEY.md section 8 row
+f1): planning/confidence.py:6-101 (class Confidence) and planning/exploration.py:6-86 (class
+Exploration), `cal_utility` only -- candidate sampling, path planning and the GUI queues of
+planning/plan_base.py are outside the hot path and are not rebuilt.
+
+The reference renders the ~100 candidate views one by one and evaluates each with ~40 small ATen
+launches plus a nonzero() sync; here all candidates are rendered by ONE rasterizer launch per chunk
+and evaluated by ONE kernel (ags_view_utility): visible-and-unexplored voxel fraction and mean
+distance-weighted uncertainty per view, no host round trip until the final (V,) result.
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import ops
+from . import operations as O
+
+
+class _UtilityBase:
+    CHUNK = 128            # candidate views per rasterizer launch
+
+    def __init__(self, cfg, device):
+        self.device = torch.device(device)
+        self.render_ratio = cfg.render_ratio
+
+    def _render(self, gaussian_map, extrinsics, intrinsics, h, w):
+        depth, conf = [], []
+        attrs = gaussian_map.get_attr()
+        for c0 in range(0, extrinsics.shape[0], self.CHUNK):
+            out = O.GaussianRenderer(extrinsics[c0:c0 + self.CHUNK], intrinsics[c0:c0 + self.CHUNK], attrs,
+                                     gaussian_map.background_color, (gaussian_map.scene_near, gaussian_map.scene_far),
+                                     (h, w), self.device).render_view_all()
+            depth.append(out[1][:, 0])
+            conf.append(out[5][:, 0])
+        return torch.cat(depth).contiguous(), torch.cat(conf).contiguous()
+
+    def _valid_masks(self, simulator, extrinsics, h, w):
+        """planning/confidence.py:52-66: the simulator's valid-surface mask per candidate, nearest-
+        neighbour resized to the render resolution (only for datasets with missing surfaces)."""
+        if not getattr(simulator, "has_missing_surface", False):
+            return None, 0.0
+        import cv2
+        t0 = time.time()
+        masks = []
+        for i in range(extrinsics.shape[0]):
+            m = simulator.simulate(extrinsics[i].cpu(), valid_mask_only=True)
+            masks.append(cv2.resize(m.astype(np.uint8), (int(h), int(w)), interpolation=cv2.INTER_NEAREST))
+        return torch.tensor(np.stack(masks)).to(self.device).contiguous(), time.time() - t0
+
+    @torch.no_grad()
+    def _utilities(self, gaussian_map, voxel_map, candidates, simulator):
+        t0 = time.time()
+        h, w = (int(v) for v in np.round(self.render_ratio * np.asarray(simulator.resolution)).astype(int))
+        extrinsics = candidates.to(self.device).float()
+        intrinsics = simulator.intrinsic.to(self.device).float()[None].expand(extrinsics.shape[0], 3, 3)
+        depth, conf = self._render(gaussian_map, extrinsics, intrinsics, h, w)
+        valid, t_sim = self._valid_masks(simulator, extrinsics, h, w)
+        explore, exploit = ops.view_utility(
+            depth, conf, voxel_map.voxel_centers.to(self.device), voxel_map.unexplored_mask.to(self.device),
+            torch.linalg.inv(extrinsics.cpu()).to(self.device), intrinsics, simulator.depth_range, valid=valid)
+        explore, exploit = explore.cpu(), exploit.cpu()              # the only synchronisation
+        return explore, exploit, time.time() - t0 - t_sim
+
+
+class Confidence(_UtilityBase):
+    """planning/confidence.py:6-101."""
+
+    def __init__(self, cfg, device):
+        super().__init__(cfg, device)
+        self.explore_weight = cfg.explore_weight
+
+    def cal_utility(self, gaussian_map, voxel_map, candidates, simulator):
+        explore, exploit, t = self._utilities(gaussian_map, voxel_map, candidates, simulator)
+        return self.explore_weight * explore + exploit, t
+
+
+class Exploration(_UtilityBase):
+    """planning/exploration.py:6-86."""
+
+    def cal_utility(self, gaussian_map, voxel_map, candidates, simulator):
+        explore, _, t = self._utilities(gaussian_map, voxel_map, candidates, simulator)
+        return explore, t

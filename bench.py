@@ -164,6 +164,49 @@ def stage_profile(eng, reps=5):
     return {n: v / reps for n, v in acc.items()}
 
 
+def update_loop_profile(dev, keyframes=12):
+    """BASELINE config[1] names the full mapper.update loop: time GaussianMap.update() (spawn from the
+    RGB-D keyframe -> 10 optimisation iterations -> confidence bookkeeping / prune,
+    mapping/gaussian_map.py:62-64) on a stream of office0-shaped keyframes rendered from the generating
+    scene.  Reported: mean over the keyframes that train with the full batch of 8 (steady state)."""
+    from active_gs_b200 import operations as O
+    from active_gs_b200.gaussian_map import GaussianMap
+    box, H, W, N = syn.ROOMS[2]
+    gen = syn.make_room_scene(N, box=box, seed=5)
+    ext, K = syn.make_cameras(keyframes, box=box, H=H, W=W, seed=6)
+    src = GaussianMap(default_gaussian_map_config(), dev)
+    load_state(src, gen, dev)
+    gm = GaussianMap(default_gaussian_map_config(), dev)
+    np.random.seed(0); torch.manual_seed(0)
+    rows = []
+
+    def sync():
+        torch.cuda.synchronize()
+        return time.perf_counter()
+
+    for i in range(keyframes):
+        with torch.no_grad():
+            out = O.GaussianRenderer(ext[i:i + 1].to(dev), K[i:i + 1].to(dev), src.get_attr(), src.background_color,
+                                     (0.001, 10.0), (H, W), dev).render_view_all()
+        depth = torch.where(out[3][0] > 0.5, out[1][0], torch.full_like(out[1][0], -1.0))
+        frame = dict(rgb=out[0][0].clamp(0, 1), depth=depth, extrinsic=ext[i], intrinsic=K[i],
+                     depth_range=torch.tensor([0.0, 5.0]))
+        t0 = sync(); gm.add_gaussians(frame)
+        t1 = sync(); ctx = gm.begin_training()
+        for _ in range(gm.optimization_steps):
+            gm.train_step(ctx)
+        gm.end_training(ctx)
+        t2 = sync(); gm.post_processing(); gm.is_init = True
+        t3 = sync()
+        rows.append((ctx.B, gm._means.shape[0], 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), i % gm.prune_interval == gm.prune_interval - 1))
+    full = [r for r in rows if r[0] == 8] or rows[-1:]
+    mean = lambda k: float(np.mean([r[k] for r in full]))
+    return {"ms_per_keyframe": mean(2) + mean(3) + mean(4), "spawn_ms": mean(2), "train_ms": mean(3), "post_ms": mean(4),
+            "iters_per_update": gm.optimization_steps, "keyframes_timed": len(full), "gaussians_end": rows[-1][1],
+            "what": "GaussianMap.update(): add_gaussians + 10 train iterations (batch 8) + post_processing (prune every 5th), "
+                    "640x480 keyframes of the office0-shaped scene, wall clock with device sync around each phase"}
+
+
 def algorithmic_bytes(N, B, P, I, V, tiles):
     """SURVEY.md 8(d) / DESIGN.md: bytes each kernel must move per launch (B views per launch)."""
     sort_bytes = 8 * I * 2 + 4 * I + 12 * B * tiles   # keys written+read once, ids written; tile tables
@@ -282,6 +325,11 @@ def run_ours(args, rank, world, local_rank):
                                     "the HBM fraction is reported as BASELINE.json asks",
                             "peak_source": which, "share_of_step": stages[dom] / sum(stages.values())}
         line["kernels"] = kern
+    if world == 1:
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):          # the reference's prune() prints to stdout
+            update_loop_profile(dev)                           # first pass warms the allocator (a mapper is long-lived)
+            line["update"] = update_loop_profile(dev)
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_reference_run(1, [{k: (v.cpu() if torch.is_tensor(v) else v) for k, v in f.items()}
                                                      for f in frames[:4]], start, H, W, quiet=True, warmup=1)

@@ -225,3 +225,27 @@ def test_view_utility_matches_oracle(gold):
                               torch.linalg.inv(g["ext"]).to(dev), g["K"].to(dev), g["depth_range"])
     assert float((ex.cpu() - g["utility_exploration"]).abs().max()) <= 4.5 / M
     assert torch.allclose(g["explore_weight"] * ex.cpu() + ei.cpu(), g["utility_confidence"], atol=2e-2, rtol=1e-3)
+
+
+def test_planner_mirror_matches_reference_planner_outputs(gold):
+    """active_gs_b200.planning.Confidence / Exploration.cal_utility against the numbers the reference's
+    own planning/confidence.py and planning/exploration.py produced on the same map (fixture)."""
+    from types import SimpleNamespace as ns
+    from active_gs_b200 import planning
+    from active_gs_b200.config import default_gaussian_map_config
+    from active_gs_b200.gaussian_map import GaussianMap
+    dev = _dev()
+    g = gold["planner"]
+    gm = GaussianMap(default_gaussian_map_config(), dev)
+    for k, v in g["state"].items():
+        setattr(gm, k if k.startswith("view_") else "_" + k, v.clone().to(dev))
+    vm = ns(voxel_centers=g["voxel_centers"], unexplored_mask=g["unexplored"])
+    h, w = g["hw"]
+    sim = ns(resolution=np.array([4 * h, 4 * w]), depth_range=g["depth_range"], intrinsic=g["K"][0], has_missing_surface=False)
+    cfg = ns(render_ratio=0.25, explore_weight=g["explore_weight"])
+    M = g["voxel_centers"].shape[0]
+    u_c, _ = planning.Confidence(cfg, dev).cal_utility(gm, vm, g["ext"], sim)
+    u_e, _ = planning.Exploration(cfg, dev).cal_utility(gm, vm, g["ext"], sim)
+    assert float((u_e - g["utility_exploration"]).abs().max()) <= 4.5 / M
+    assert torch.allclose(u_c, g["utility_confidence"], atol=2e-2, rtol=1e-3)
+    assert int(torch.argmax(u_c)) == int(torch.argmax(g["utility_confidence"]))
