@@ -22,12 +22,27 @@ constexpr int SORT_CHUNK = 4096;
 constexpr int SORT_THREADS = 256;
 
 __global__ void __launch_bounds__(256)
-alloc_kernel(AgsWorkspace w, int n_tiles_total, int inst_cap, int32_t* stats) {
+alloc_kernel(AgsWorkspace w, int n_tiles_total, int tiles_per_view, int inst_cap, int32_t* stats) {
     __shared__ int warp_sums[8];
     __shared__ int block_base;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int c = (t < n_tiles_total) ? w.tile_count[t] : 0;
+    {   // per-view instance totals
+        const int v = t / tiles_per_view;
+        constexpr int VMAX = AGS_NUM_STATS - AGS_STAT_VIEW0;
+        if (tiles_per_view >= 32) {               // a warp's 32 consecutive tiles span at most two views
+            const int v0 = __shfl_sync(0xffffffffu, v, 0);
+            const int s0 = __reduce_add_sync(0xffffffffu, v == v0 ? c : 0);
+            const int s1 = __reduce_add_sync(0xffffffffu, v == v0 ? 0 : c);
+            if (lane == 0) {
+                if (s0 && v0 < VMAX) atomicAdd(stats + AGS_STAT_VIEW0 + v0, s0);
+                if (s1 && v0 + 1 < VMAX) atomicAdd(stats + AGS_STAT_VIEW0 + v0 + 1, s1);
+            }
+        } else if (c && v < VMAX) {
+            atomicAdd(stats + AGS_STAT_VIEW0 + v, c);
+        }
+    }
     int incl = c;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -156,7 +171,7 @@ int ags_launch_binning(const AgsRenderArgs& a, const AgsWorkspace& w) {
     cudaStream_t st = (cudaStream_t)a.stream;
     const int tiles = ((a.W + TILE - 1) / TILE) * ((a.H + TILE - 1) / TILE);
     const int nt = a.B * tiles;
-    alloc_kernel<<<(nt + 255) / 256, 256, 0, st>>>(w, nt, a.inst_cap, a.stats);
+    alloc_kernel<<<(nt + 255) / 256, 256, 0, st>>>(w, nt, tiles, a.inst_cap, a.stats);
     AGS_CHECK_CUDA(cudaGetLastError());
     if (a.N > 0) {
         long long blocks = ((long long)a.N * a.B + 255) / 256;

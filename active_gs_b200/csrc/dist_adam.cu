@@ -66,10 +66,21 @@ __device__ __forceinline__ float lr_of(const DistAdamParams& P, long long e) {
     return lr;
 }
 
+#ifndef AGS_DIST_UNROLL
+#define AGS_DIST_UNROLL 4            // independent 16-byte elements in flight per thread
+#endif
+
+// Measured (profiles/README.md, N=2, 5.6 MB shard): ONE wave of 296 blocks with four elements in flight
+// per thread: 43 us (peer loads) / 57 us (multimem).  More, smaller blocks are slower (every block pays
+// the remote flag read + bias-correction prologue: 1184 blocks = 62-74 us); wider unrolling over the
+// peers costs occupancy (162 registers: 135 us).
 __global__ void __launch_bounds__(256)
 dist_adam_kernel(DistAdamParams P) {
+    // any rank's overflow flag skips the step everywhere; the peer loads are issued together
+    int skip = 0;
     for (int p = 0; p < P.world; ++p)
-        if (P.skip[p] && *reinterpret_cast<const volatile int*>(P.skip[p]) != 0) return;
+        if (P.skip[p]) skip |= *reinterpret_cast<const volatile int*>(P.skip[p]);
+    if (skip) return;
     __shared__ float s_c[2];
     if (threadIdx.x == 0) {                     // bias corrections once per block (double pow)
         const double bc1 = 1.0 - pow((double)P.b1, (double)P.step);
@@ -82,36 +93,51 @@ dist_adam_kernel(DistAdamParams P) {
     const float inv_bc1 = s_c[1];
     const long long n4 = (P.shard_end - P.shard_begin + 3) / 4;        // shard is 4-aligned; tail padded
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
-        const long long e = P.shard_begin + 4 * q;
-        float4 g;
-        if (P.grad_mc) {
-            g = mc_ld_reduce4(P.grad_mc + e);
-        } else {
-            g = ld_peer4(P.grad[0] + e);
-            for (int p = 1; p < P.world; ++p) {
-                const float4 h = ld_peer4(P.grad[p] + e);
-                g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+    constexpr int U = AGS_DIST_UNROLL;
+    for (long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < n4; q0 += stride * U) {
+        float4 g[U], pr[U], m4[U], v4[U];
+        // ---- all loads of the U elements first: the NVLink / switch latency is paid once
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long q = q0 + u * stride;
+            if (q < n4) {
+                const long long e = P.shard_begin + 4 * q;
+                if (P.grad_mc) {
+                    g[u] = mc_ld_reduce4(P.grad_mc + e);
+                } else {
+                    g[u] = ld_peer4(P.grad[0] + e);
+                    for (int p = 1; p < P.world; ++p) {
+                        const float4 h = ld_peer4(P.grad[p] + e);
+                        g[u].x += h.x; g[u].y += h.y; g[u].z += h.z; g[u].w += h.w;
+                    }
+                }
+                pr[u] = *reinterpret_cast<const float4*>(P.param[P.rank] + e);
+                m4[u] = *reinterpret_cast<const float4*>(P.m + e);
+                v4[u] = *reinterpret_cast<const float4*>(P.v + e);
             }
         }
-        float4 pr = *reinterpret_cast<const float4*>(P.param[P.rank] + e);
-        float4 m4 = *reinterpret_cast<const float4*>(P.m + e);
-        float4 v4 = *reinterpret_cast<const float4*>(P.v + e);
-        float* gp = &g.x; float* pp = &pr.x; float* mp = &m4.x; float* vp = &v4.x;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float lr = lr_of(P, e + k);
-            const float m = P.b1 * mp[k] + (1.f - P.b1) * gp[k];
-            const float v = P.b2 * vp[k] + (1.f - P.b2) * gp[k] * gp[k];
-            mp[k] = m; vp[k] = v;
-            pp[k] -= (lr * inv_bc1) * (m / (sqrtf(v) * inv_sqrt_bc2 + P.eps));
-        }
-        *reinterpret_cast<float4*>(P.m + e) = m4;
-        *reinterpret_cast<float4*>(P.v + e) = v4;
-        if (P.param_mc) {
-            mc_st4(P.param_mc + e, pr);
-        } else {
-            for (int p = 0; p < P.world; ++p) st_peer4(P.param[p] + e, pr);
+        for (int u = 0; u < U; ++u) {
+            const long long q = q0 + u * stride;
+            if (q < n4) {
+                const long long e = P.shard_begin + 4 * q;
+                float* gp = &g[u].x; float* pp = &pr[u].x; float* mp = &m4[u].x; float* vp = &v4[u].x;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float lr = lr_of(P, e + k);
+                    const float m = P.b1 * mp[k] + (1.f - P.b1) * gp[k];
+                    const float v = P.b2 * vp[k] + (1.f - P.b2) * gp[k] * gp[k];
+                    mp[k] = m; vp[k] = v;
+                    pp[k] -= (lr * inv_bc1) * (m / (sqrtf(v) * inv_sqrt_bc2 + P.eps));
+                }
+                *reinterpret_cast<float4*>(P.m + e) = m4[u];
+                *reinterpret_cast<float4*>(P.v + e) = v4[u];
+                if (P.param_mc) {
+                    mc_st4(P.param_mc + e, pr[u]);
+                } else {
+                    for (int p = 0; p < P.world; ++p) st_peer4(P.param[p] + e, pr[u]);
+                }
+            }
         }
     }
     __threadfence_system();
@@ -153,7 +179,7 @@ extern "C" int ags_dist_adam_step(const AgsDistAdamArgs* a) {
     P.b1 = a->beta1; P.b2 = a->beta2; P.eps = a->eps; P.step = a->step;
     const long long n4 = C / 4;
     long long blocks = (n4 + 255) / 256;
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks > 148 * 2) blocks = 148 * 2;          // one wave (see the kernel's note)
     if (blocks < 1) blocks = 1;
     dist_adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)a->stream>>>(P);
     AGS_CHECK_CUDA(cudaGetLastError());

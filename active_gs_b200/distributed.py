@@ -29,7 +29,7 @@ class SymmetricFlat:
         self.numel_padded = (numel + q - 1) // q * q
         self.param = symm.empty(self.numel_padded, dtype=torch.float32, device=device)
         self.grad = symm.empty(self.numel_padded, dtype=torch.float32, device=device)
-        self.stats = symm.empty(8, dtype=torch.int32, device=device)      # AgsRenderArgs.stats, peer readable
+        self.stats = symm.empty(72, dtype=torch.int32, device=device)           # AGS_NUM_STATS      # AgsRenderArgs.stats, peer readable
         self.param.zero_(); self.grad.zero_(); self.stats.zero_()
         g = group if group is not None else dist.group.WORLD
         self.h_param = symm.rendezvous(self.param, g)
@@ -47,6 +47,30 @@ class SymmetricFlat:
         self.h_grad.barrier()
 
 
+class SymmetricAux:
+    """Symmetric buffers of the two small per-iteration exchanges (csrc/dist_loss.cu): the (H*W) int32
+    visibility-count plane of quirk Q1 and the (world*nterm) float gather buffer of the loss terms."""
+
+    def __init__(self, group, P, nterm, device):
+        import torch.distributed._symmetric_memory as symm
+        world = dist.get_world_size(group)
+        self.P, self.nterm = P, nterm
+        self.vis = symm.empty(P, dtype=torch.int32, device=device)
+        self.gather = symm.empty(world * nterm, dtype=torch.float32, device=device)
+        self.vis.zero_(); self.gather.zero_()
+        g = group if group is not None else dist.group.WORLD
+        self.h_vis = symm.rendezvous(self.vis, g)
+        self.h_gather = symm.rendezvous(self.gather, g)
+        self.vis_ptrs = [int(p) for p in self.h_vis.buffer_ptrs]
+        self.gather_ptrs = [int(p) for p in self.h_gather.buffer_ptrs]
+        mc = bool(getattr(self.h_vis, "has_multicast_support", False))
+        self.vis_mc = int(self.h_vis.multicast_ptr) if mc else 0
+        self.gather_mc = int(self.h_gather.multicast_ptr) if mc else 0
+
+    def barrier(self):
+        self.h_vis.barrier()
+
+
 class FrameShard:
     def __init__(self, group=None, fused=False):
         self.group = group
@@ -55,14 +79,23 @@ class FrameShard:
         # fused = reduce-scatter -> Adam -> all-gather in ONE kernel over NVLink peer memory
         # (csrc/dist_adam.cu) instead of NCCL all-reduce + replicated Adam
         self.fused = fused
-        self.use_multicast = True
+        # NVLS multimem for the gradient/parameter exchange: measured faster from 4 GPUs up (N=8: 77-110 us
+        # vs 125 us with peer loads), slower at N=2 (57 vs 43 us)
+        self.use_multicast = self.world >= 4
         self._flat = None
+        self._aux = None
 
     def flat_buffers(self, numel, device):
         """symmetric buffers with head-room, re-allocated (collective!) only when the map outgrows them"""
         if self._flat is None or self._flat.numel_padded < numel:
             self._flat = SymmetricFlat(self.group, int(numel * 1.25) + 1024, device)
         return self._flat
+
+    def aux_buffers(self, P, nterm, device):
+        """symmetric buffers of the visibility / loss-term exchange (collective allocation)"""
+        if self._aux is None or self._aux.P != P or self._aux.nterm != nterm:
+            self._aux = SymmetricAux(self.group, P, nterm, device)
+        return self._aux
 
     def all_reduce_max_(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
@@ -74,10 +107,43 @@ class FrameShard:
         return B_global // self.world
 
     def my_frames(self, ids):
-        """contiguous slice of the sampled ids owned by this rank"""
+        """contiguous slice of the (balanced) sampled ids owned by this rank"""
         ids = np.asarray(ids)
         b = len(ids) // self.world
         return ids[self.rank * b:(self.rank + 1) * b]
+
+    def pinned_slot(self, j):
+        """(rank, local slot) of the j-th always-selected (active) keyframe: round robin over the
+        ranks at fixed slots, so every rank can prefetch its share before the sampler draw"""
+        return j % self.world, j // self.world
+
+    def balance(self, ids, n_active, cost):
+        """Partition the sampled keyframe ids over the ranks (the gradient sum does not depend on the
+        partition) so that the slowest rank is as fast as possible: the first `n_active` ids stay at
+        their pinned slots, the others are placed longest-first on the least loaded rank with a free
+        slot (LPT with a cardinality constraint).  `cost`: id -> instances of its last render (missing
+        ids count as the mean).  Returns the ids reordered so that rank r owns [r*b, (r+1)*b).
+        Deterministic: every rank computes the same answer from the same gathered costs."""
+        ids = [int(i) for i in ids]
+        W, b = self.world, len(ids) // self.world
+        known = [cost[i] for i in ids if i in cost]
+        mean = float(np.mean(known)) if known else 0.0
+        c = [float(cost.get(i, mean)) for i in ids]
+        slots = [[None] * b for _ in range(W)]
+        load = [0.0] * W
+        free = [b] * W
+        for j in range(min(n_active, len(ids))):
+            r, k = self.pinned_slot(j)
+            slots[r][k] = ids[j]
+            load[r] += c[j]
+            free[r] -= 1
+        rest = sorted(range(min(n_active, len(ids)), len(ids)), key=lambda j: (-c[j], j))
+        for j in rest:
+            r = min((q for q in range(W) if free[q] > 0), key=lambda q: (load[q], q))
+            slots[r][slots[r].index(None)] = ids[j]
+            load[r] += c[j]
+            free[r] -= 1
+        return np.asarray([i for r in range(W) for i in slots[r]])
 
     def all_reduce_sum_(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)

@@ -14,6 +14,7 @@ loss-weighted sampler, exactly the dependency the reference has (mapping/utils.p
 """
 import ctypes as C
 import math
+import os
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -205,12 +206,16 @@ class _TrainEngine:
         self.loss_out = None
         self.vis_count = torch.empty(H, W, device=dev, dtype=torch.int32) if dist_ctx else None
         W_ = dist_ctx.world if dist_ctx else 1
-        self.nterm = 2 * B + 4 + 2                    # loss terms, per-frame perf, (instances, overflow)
+        self.nterm = 2 * B + 4 + B + 2                # loss terms, per-frame perf | per-view instances | (instances, overflow)
         self.host = torch.empty(W_ * self.nterm, dtype=torch.float32).pin_memory()
         self.terms_all = torch.empty(W_ * self.nterm, **o) if dist_ctx else None
         self.terms_loc = torch.empty(self.nterm, **o) if dist_ctx else None
         self.host_stats = torch.empty(L.AGS_NUM_STATS, dtype=torch.int32).pin_memory()
         self.event = torch.cuda.Event()
+        self.aux = self.vis_args = self.terms_args = None
+        self.marks = [] if os.environ.get("AGS_DIST_PROFILE") else None     # (name, event) per segment boundary
+        if self.fused:
+            self.aux = dist_ctx.aux_buffers(H * W, self.nterm, dev)
         self.fwd_args = self.rb._args()      # argument structs are built once: pointers never change
         self.grad_args = [None, None]        # one per ground-truth buffer (each has its own loss outputs)
         self.loss_outs = [None, None]
@@ -288,13 +293,16 @@ class _TrainEngine:
         st = L.current_stream(self.dev)
         fa = self.fwd_args
         fa.stream = st
+        self._mark("start")
         L.check(lib.ags_render_forward(C.byref(fa)), "ags_render_forward")
+        self._mark("forward")
         vis = None
-        if self.dist is not None:
-            if not self.fused:
-                # every rank must take the same overflow decision: (instances, overflow) -> MAX.
-                # (the fused kernel reads the peers' flags itself; the host gets them via the gather)
-                self.dist.all_reduce_max_(rb.stats[:2])
+        if self.fused:
+            vis = self._fused_vis_count(lib, st)
+        elif self.dist is not None:
+            # every rank must take the same overflow decision: (instances, overflow) -> MAX.
+            # (the fused path reads the peers' flags itself; the host gets them via the gather)
+            self.dist.all_reduce_max_(rb.stats[:2])
             torch.sum(rb.opacity[:, 0] > 1e-3, dim=0, dtype=torch.int32, out=self.vis_count)
             self.dist.all_reduce_sum_(self.vis_count)
             vis = self.vis_count
@@ -304,15 +312,20 @@ class _TrainEngine:
             rb.rgb, rb.normal, rb.depth, rb.opacity, self.rgb_gt, self.depth_gt, self.tanfov,
             B_total=self.B_total, vis_count=vis, out=self.loss_outs[self.gt_k])
         lo = self.loss_out = self.loss_outs[self.gt_k]
-        if self.dist is not None:
+        self._mark("loss")
+        if self.fused:
+            self._fused_terms_gather(lib, st, lo)
+        elif self.dist is not None:
             # loss terms + per-frame performance of every rank, gathered on the stream before the
             # backward is enqueued: the host waits for this small copy only
-            self.terms_loc[:self.nterm - 2].copy_(lo.terms)
+            nt = 4 + 2 * self.B
+            self.terms_loc[:nt].copy_(lo.terms)
+            self.terms_loc[nt:nt + self.B].copy_(rb.stats[L.STAT_VIEW0:L.STAT_VIEW0 + self.B])
             self.terms_loc[self.nterm - 2:].copy_(rb.stats[:2])
             self.dist.all_gather_into_(self.terms_all, self.terms_loc)
             self.host.copy_(self.terms_all, non_blocking=True)
         else:
-            self.host[:self.nterm - 2].copy_(lo.terms, non_blocking=True)
+            self.host[:4 + 2 * self.B].copy_(lo.terms, non_blocking=True)
         self.host_stats.copy_(rb.stats, non_blocking=True)
         self.event.record(torch.cuda.current_stream(self.dev))
         if self.grad_args[self.gt_k] is None:
@@ -326,6 +339,7 @@ class _TrainEngine:
             g.clear_records = 0                 # exactly one backward per forward in this loop
             self.grad_args[self.gt_k] = g
         L.check(lib.ags_render_backward(C.byref(fa), C.byref(self.grad_args[self.gt_k])), "ags_render_backward")
+        self._mark("backward")
         self.step += 1
         if self.fused:
             self._fused_exchange_and_adam(lib, st)
@@ -334,6 +348,60 @@ class _TrainEngine:
             self.dist.all_reduce_grads_(self.grads)
         ops.adam_step(self.params, self.grads, self.m, self.v, self.lrs, step=self.step,
                       skip_flag_ptr=rb.stats.data_ptr() + 4 * L.STAT_OVERFLOW, cache=self.adam_cache)
+
+    def _mark(self, name):
+        if self.marks is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream(self.dev))
+            self.marks.append((name, e))
+
+    def segment_times(self):
+        """AGS_DIST_PROFILE=1: median device time (us) between consecutive marks, by segment name"""
+        torch.cuda.synchronize()
+        acc = {}
+        for (n0, e0), (n1, e1) in zip(self.marks[:-1], self.marks[1:]):
+            acc.setdefault("host gap" if n1 == "start" else n1, []).append(e0.elapsed_time(e1) * 1e3)
+        return {k: round(float(np.median(v)), 1) for k, v in acc.items()}
+
+    def _fused_vis_count(self, lib, st):
+        """quirk Q1 over the whole batch: local count -> cross-GPU barrier -> sum of all ranks' planes
+        over NVLink (csrc/dist_loss.cu), no NCCL collective"""
+        a, d, x = self.vis_args, self.dist, self.aux
+        if a is None:
+            a = L.DistVisArgs()
+            a.world, a.rank, a.B, a.H, a.W = d.world, d.rank, self.B, self.H, self.W
+            a.opacity, a.vis_local, a.vis_count = L.ptr(self.rb.opacity), L.ptr(x.vis), L.ptr(self.vis_count)
+            for p in range(d.world):
+                a.vis_peers[p] = x.vis_ptrs[p]
+            a.vis_multicast = x.vis_mc if (d.use_multicast and x.vis_mc) else None
+            self.vis_args = a
+        a.stream = st
+        L.check(lib.ags_dist_vis_local(C.byref(a)), "ags_dist_vis_local")
+        self._mark("vis local")
+        x.barrier()
+        self._mark("barrier A")
+        L.check(lib.ags_dist_vis_sum(C.byref(a)), "ags_dist_vis_sum")
+        self._mark("vis sum")
+        return self.vis_count
+
+    def _fused_terms_gather(self, lib, st, lo):
+        """every rank's loss terms / per-frame performance / (instances, overflow) into every rank's
+        gather buffer with peer stores, then the small D2H the host waits for"""
+        a, d, x = self.terms_args, self.dist, self.aux
+        if a is None:
+            a = L.DistTermsArgs()
+            a.world, a.rank, a.nterm, a.nview = d.world, d.rank, self.nterm, self.B
+            a.stats = L.ptr(self.rb.stats)
+            for p in range(d.world):
+                a.gather_peers[p] = x.gather_ptrs[p]
+            a.gather_multicast = x.gather_mc if (d.use_multicast and x.gather_mc) else None
+            self.terms_args = a
+        a.terms = L.ptr(lo.terms)
+        a.stream = st
+        L.check(lib.ags_dist_terms_put(C.byref(a)), "ags_dist_terms_put")
+        x.barrier()
+        self._mark("terms put + barrier T")
+        self.host.copy_(x.gather, non_blocking=True)
 
     def _fused_exchange_and_adam(self, lib, st):
         """reduce-scatter(grads) -> Adam(shard) -> all-gather(params) in one kernel, between two
@@ -359,8 +427,11 @@ class _TrainEngine:
         a.step = self.step
         a.stream = st
         f.barrier()                                  # every rank's gradients are complete
+        self._mark("barrier G1")
         L.check(lib.ags_dist_adam_step(C.byref(a)), "ags_dist_adam_step")
+        self._mark("dist adam")
         f.barrier()                                  # every rank's parameters are updated
+        self._mark("barrier G2")
 
     def fetch(self):
         """Wait for the loss terms / per-frame performance / instance statistics of the step that
@@ -372,10 +443,14 @@ class _TrainEngine:
         pf = h[:, 4:4 + 2 * B]
         perf = (pf[:, 0::2] + pf[:, 1::2]).reshape(-1)      # ordered like the sampled ids
         stats = self.host_stats.to(torch.int64)
+        nt = 4 + 2 * B
         if self.dist is not None:                           # global view: max instances, any overflow
             stats[L.STAT_INSTANCES] = int(h[:, self.nterm - 2].max())
             stats[L.STAT_OVERFLOW] = int(h[:, self.nterm - 1].max())
-        return terms, perf, stats
+            view_cost = h[:, nt:nt + B].reshape(-1)         # instances per frame, ordered like the batch
+        else:
+            view_cost = stats[L.STAT_VIEW0:L.STAT_VIEW0 + B].float()
+        return terms, perf, stats, view_cost
 
 
 class GaussianMap:
@@ -403,6 +478,7 @@ class GaussianMap:
         self._pool = _BufferPool(self.device)
         self._store = _MapStore(self.device)
         self._cams = []                      # per keyframe: host camera products, computed once
+        self._frame_cost = {}                # keyframe id -> instances of its last training render
         if cfg is not None:
             self.cfg = cfg
             self.use_view_distribution = cfg.use_view_distribution
@@ -455,8 +531,14 @@ class GaussianMap:
         cam_rows = self._camera_rows(range(T))                       # host (T, 34), cached per keyframe
         # batch slots whose keyframe never changes (the sampler's active frames come first in the
         # sampled ids): local slot k of this rank is global slot rank*B + k
-        first = 0 if self.dist is None else self.dist.rank * B
-        fixed = {k: int(sampler.active_ids[first + k]) for k in range(B) if first + k < len(sampler.active_ids)}
+        if self.dist is None:
+            fixed = {k: int(sampler.active_ids[k]) for k in range(min(B, len(sampler.active_ids)))}
+        else:                                           # active keyframes are pinned round robin (FrameShard.balance)
+            fixed = {}
+            for j, fid in enumerate(sampler.active_ids[:sampler.v]):
+                r, k = self.dist.pinned_slot(j)
+                if r == self.dist.rank:
+                    fixed[k] = int(fid)
         return SimpleNamespace(fixed=fixed,
             sampler=sampler, B=B, H=H, W=W,
             eng=_TrainEngine(self, B, H, W, self.dist,
@@ -469,6 +551,9 @@ class GaussianMap:
         eng = ctx.eng
         sampled = ids is None
         ids = np.asarray(ids) if ids is not None else ctx.sampler.next_ids(ctx.perf_host)
+        if self.dist is not None and sampled:
+            # same keyframes, load-balanced partition over the ranks (cost = instances of the last render)
+            ids = self.dist.balance(ids, len(ctx.sampler.active_ids), self._frame_cost)
         my = ids if self.dist is None else self.dist.my_frames(ids)
         idx = torch.as_tensor(my, dtype=torch.long)
         eng.set_batch([self.training_data[i]["rgb"] for i in my],
@@ -478,7 +563,7 @@ class GaussianMap:
             eng.iterate()
             if sampled:
                 eng.prefetch_next(ctx.fixed, self.training_data)
-            terms, perf, stats = eng.fetch()
+            terms, perf, stats, view_cost = eng.fetch()
             if stats[L.STAT_OVERFLOW] == 0:
                 break
             # capacity exceeded: nothing was rendered and the device-side flag turned the Adam
@@ -488,6 +573,8 @@ class GaussianMap:
         need = float(stats[L.STAT_INSTANCES]) / max(1, eng.N * ctx.B)
         self._cap_per_gaussian = max(self._cap_per_gaussian, 1.5 * need)
         ctx.perf_host[torch.as_tensor(ids, dtype=torch.long)] = perf
+        for i, c in zip(ids.tolist(), view_cost.tolist()):
+            self._frame_cost[int(i)] = c
         loss = float(terms[0] + 0.8 * terms[1] + 0.1 * terms[2] + 0.1 * terms[3])
         ctx.log.append((loss, perf.clone(), int(stats[L.STAT_INSTANCES]), int(stats[L.STAT_VISIBLE])))
         return loss

@@ -11,8 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # AGS_B200_LIB selects an alternative build of the same library (tuning experiments only)
 LIB_PATH = os.environ.get("AGS_B200_LIB") or os.path.join(_HERE, "libags_b200.so")
 
-AGS_NUM_STATS = 8
-STAT_INSTANCES, STAT_OVERFLOW, STAT_VISIBLE = 0, 1, 2
+AGS_NUM_STATS = 72
+STAT_INSTANCES, STAT_OVERFLOW, STAT_VISIBLE, STAT_VIEW0 = 0, 1, 2, 8
 PARAMS_ACTIVATED, PARAMS_RAW = 0, 1
 ADAM_GROUPS = 5
 CAM_ROW = 34
@@ -80,6 +80,22 @@ class DistAdamArgs(C.Structure):
     ]
 
 
+class DistVisArgs(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32), ("rank", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("opacity", _f), ("vis_local", _f), ("vis_peers", _f * MAX_PEERS), ("vis_multicast", _f),
+        ("vis_count", _f), ("stream", _f),
+    ]
+
+
+class DistTermsArgs(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32), ("rank", C.c_int32), ("nterm", C.c_int32), ("nview", C.c_int32), ("terms", _f),
+        ("stats", _f),
+        ("gather_peers", _f * MAX_PEERS), ("gather_multicast", _f), ("stream", _f),
+    ]
+
+
 class SpawnArgs(C.Structure):
     _fields_ = [
         ("H", C.c_int32), ("W", C.c_int32),
@@ -118,7 +134,7 @@ EXPORTS = ["ags_scratch_bytes", "ags_render_forward", "ags_render_backward", "ag
            "ags_loss_scratch_bytes", "ags_loss_forward_backward", "ags_postprocess", "ags_adam_step",
            "ags_dist_adam_step", "ags_smooth_depth", "ags_stage_cameras",
            "ags_spawn_scratch_bytes", "ags_spawn", "ags_view_stats_update", "ags_prune_scratch_bytes",
-           "ags_prune_compact", "ags_view_utility",
+           "ags_prune_compact", "ags_view_utility", "ags_dist_vis_local", "ags_dist_vis_sum", "ags_dist_terms_put",
            "ags_last_error", "ags_version"]
 
 
@@ -162,6 +178,10 @@ def load():
     lib.ags_prune_compact.restype = C.c_int
     lib.ags_view_utility.argtypes = [C.POINTER(UtilityArgs)]
     lib.ags_view_utility.restype = C.c_int
+    for name, typ in [("ags_dist_vis_local", DistVisArgs), ("ags_dist_vis_sum", DistVisArgs),
+                      ("ags_dist_terms_put", DistTermsArgs)]:
+        getattr(lib, name).argtypes = [C.POINTER(typ)]
+        getattr(lib, name).restype = C.c_int
     lib.ags_dist_adam_step.argtypes = [C.POINTER(DistAdamArgs)]
     lib.ags_dist_adam_step.restype = C.c_int
     lib.ags_postprocess.argtypes = [C.c_int32] * 3 + [C.c_void_p] * 7

@@ -94,6 +94,8 @@ def build_workload(dev, rank, world, seed_base=1000 + CONFIG_IDX):
     T = B_PER_GPU * world
     state = syn.make_room_scene(N, box=box, seed=seed_base)
     ext, K = syn.make_cameras(T, box=box, H=H, W=W, seed=seed_base + 1000)
+    if os.environ.get("AGS_BENCH_PERIODIC"):          # experiment: every rank sees the N=1 camera set
+        ext = ext[:B_PER_GPU].repeat(world, 1, 1)
     cfg = default_gaussian_map_config()
     cfg.sampler.batch_size = T
     gm = GaussianMap(cfg, dev)
@@ -229,6 +231,8 @@ def run_ours(args, rank, world, local_rank):
         # fused NVLink reduce-scatter -> Adam -> all-gather kernel by default; AGS_DIST=nccl selects the
         # NCCL all-reduce + replicated Adam baseline path
         shard = FrameShard(fused=os.environ.get("AGS_DIST", "fused") != "nccl")
+        if os.environ.get("AGS_DIST_MC"):                 # experiment switch: force the NVLS multimem path on/off
+            shard.use_multicast = os.environ["AGS_DIST_MC"] != "0"
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()                      # nvidia-smi takes a moment to start: launch it early
@@ -258,6 +262,8 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     clocks.mark_end()
     ms = e0.elapsed_time(e1)
+    if ctx.eng.marks is not None:
+        print(f"[rank {rank}] segments us:", ctx.eng.segment_times(), file=sys.stderr, flush=True)
     inst = int(np.mean([l[2] for l in ctx.log[-args.steps:]]))
     vis = int(np.mean([l[3] for l in ctx.log[-args.steps:]]))
     loss_first, loss_last = ctx.log[0][0], ctx.log[-1][0]

@@ -44,7 +44,9 @@ extern "C" {
 #define AGS_STAT_INSTANCES 0   /* stats[0]: instances the batch needs */
 #define AGS_STAT_OVERFLOW 1    /* stats[1]: 1 if instances > inst_cap (nothing rendered) */
 #define AGS_STAT_VISIBLE 2     /* stats[2]: sum over views of visible Gaussians */
-#define AGS_NUM_STATS 8
+#define AGS_STAT_VIEW0 8       /* stats[8 + v]: instances of view v (v < 64): the per-frame cost the
+                                  frame-sharded loop balances the ranks with */
+#define AGS_NUM_STATS 72
 
 /* parameter interpretation */
 #define AGS_PARAMS_ACTIVATED 0 /* boundary semantics: inputs are the activated tensors of get_attr() */
@@ -210,6 +212,40 @@ typedef struct AgsDistAdamArgs {
     void* stream;
 } AgsDistAdamArgs;
 int ags_dist_adam_step(const AgsDistAdamArgs* args);
+
+/* The two small exchanges of the frame-sharded iteration over NVLink peer memory (new; csrc/dist_loss.cu).
+ * Visibility count of quirk Q1 (mapping/gaussian_map.py:116-117) summed over the frames of ALL ranks:
+ *   ags_dist_vis_local  counts this rank's B frames (opacity > 1e-3) into its symmetric plane vis_local;
+ *   -- cross-GPU barrier on the stream --
+ *   ags_dist_vis_sum    vis_count[p] = sum over ranks of their planes (multimem.ld_reduce if
+ *                       vis_multicast != NULL, else one load per peer); feed it to AgsLossArgs.vis_count. */
+typedef struct AgsDistVisArgs {
+    int32_t world, rank;
+    int32_t B, H, W;
+    const float* opacity;                       /* (B,1,H,W) this rank's rendered opacity */
+    int32_t* vis_local;                         /* symmetric (H*W) int32, this rank's copy */
+    const int32_t* vis_peers[AGS_MAX_PEERS];    /* the same buffer on every rank */
+    const int32_t* vis_multicast;               /* NVLS multicast address of it, or NULL */
+    int32_t* vis_count;                         /* local (H,W) output of ags_dist_vis_sum */
+    void* stream;
+} AgsDistVisArgs;
+int ags_dist_vis_local(const AgsDistVisArgs* args);
+int ags_dist_vis_sum(const AgsDistVisArgs* args);
+
+/* All-gather of the per-rank loss terms / per-frame performance (the sampler on every rank needs all
+ * of them, mapping/utils.py:206-218) plus (instances, overflow) of the forward: rank r stores its
+ * nterm floats into slot r of every rank's gather buffer; a cross-GPU barrier must follow. */
+typedef struct AgsDistTermsArgs {
+    int32_t world, rank;
+    int32_t nterm;                              /* floats per rank: terms | nview view costs | instances, overflow */
+    int32_t nview;                              /* views of this rank (per-view instance counts gathered too) */
+    const float* terms;                         /* local (nterm - nview - 2) */
+    const int32_t* stats;                       /* local AgsRenderArgs.stats */
+    float* gather_peers[AGS_MAX_PEERS];         /* symmetric (world*nterm) float buffer on every rank */
+    float* gather_multicast;                    /* its NVLS multicast address or NULL */
+    void* stream;
+} AgsDistTermsArgs;
+int ags_dist_terms_put(const AgsDistTermsArgs* args);
 
 /* Per-iteration camera staging (new; replaces the per-view host work of GaussianRenderer.__init__,
  * utils/operations.py:748-762, inside the training loop): gathers the camera blocks of the sampled

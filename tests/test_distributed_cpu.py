@@ -44,6 +44,21 @@ def _worker(rank, world, port, ret):
     assert torch.allclose(pf, torch.tensor([0.25, 0.5, 1.25, 1.5]))
     with pytest.raises(ValueError):
         sh.local_batch(7)
+    # load-balanced partition: same answer on every rank, a permutation of the sampled ids, the active
+    # keyframes at their pinned slots, and a smaller maximum load than the contiguous split
+    cost = {int(i): float(1000 + 900 * (int(i) % 5)) for i in range(16) if i != 3}     # id 3 unknown -> mean
+    bal = sh.balance(ids, len(sampler.active_ids), cost)
+    dist.all_gather_object(gathered, bal.tolist())
+    assert all(g == bal.tolist() for g in gathered)
+    assert sorted(bal.tolist()) == sorted(ids.tolist())
+    b = len(ids) // world
+    for j, fid in enumerate(sampler.active_ids):
+        r, k = sh.pinned_slot(j)
+        assert bal[r * b + k] == fid
+    mean = np.mean(list(cost.values()))
+    load = lambda order: max(sum(cost.get(int(i), mean) for i in order[r * b:(r + 1) * b]) for r in range(world))
+    assert load(bal) <= load(ids)
+    assert sh.balance(ids, len(sampler.active_ids), {}).tolist() == sh.balance(ids, len(sampler.active_ids), {}).tolist()
     dist.barrier()
     dist.destroy_process_group()
     ret[rank] = True
