@@ -488,9 +488,74 @@ view_utility_kernel(AgsUtilityArgs a) {
     }
 }
 
+// =================================================================================================
+// low-confidence voxels (ags_voxel_roi)
+__global__ void __launch_bounds__(MO_THREADS)
+voxel_roi_scatter_kernel(AgsVoxelRoiArgs a) {
+    const int i = blockIdx.x * MO_THREADS + threadIdx.x;
+    if (i >= a.N) return;
+    if (!(__ldg(a.confidences + i) < a.confidence_thres)) return;
+    const float o = __ldg(a.opacities + i);
+    if (!(1.f / (1.f + expf(-o)) > a.opacity_thres)) return;
+    int v[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        v[k] = (int)floorf((__ldg(a.means + 3 * (size_t)i + k) - a.bbox_min[k]) / a.voxel_size[k]);
+        if (v[k] < 0 || v[k] >= a.dim[k]) return;
+    }
+    const size_t lin = ((size_t)v[0] * a.dim[1] + v[1]) * a.dim[2] + v[2];
+    const float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + i);
+    const float qn = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+    const float r = q.x / qn, x = q.y / qn, y = q.z / qn, z = q.w / qn;
+    float nx = 2.f * (x * z + r * y), ny = 2.f * (y * z - r * x), nz = 1.f - 2.f * (x * x + y * y);
+    const float nn = fmaxf(sqrtf(nx * nx + ny * ny + nz * nz), 1e-12f);
+    atomicAdd(a.voxel_count + lin, 1);
+    atomicAdd(a.voxel_normal + 3 * lin + 0, nx / nn);
+    atomicAdd(a.voxel_normal + 3 * lin + 1, ny / nn);
+    atomicAdd(a.voxel_normal + 3 * lin + 2, nz / nn);
+}
+
+__global__ void __launch_bounds__(MO_THREADS)
+voxel_roi_finish_kernel(AgsVoxelRoiArgs a, int M) {
+    const int m = blockIdx.x * MO_THREADS + threadIdx.x;
+    if (m >= M) return;
+    const int c = a.voxel_count[m];
+    const bool upd = c > a.min_gaussian_per_voxel;
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    if (upd) {
+        nx = a.voxel_normal[3 * (size_t)m] / (float)c;
+        ny = a.voxel_normal[3 * (size_t)m + 1] / (float)c;
+        nz = a.voxel_normal[3 * (size_t)m + 2] / (float)c;
+        const float nn = fmaxf(sqrtf(nx * nx + ny * ny + nz * nz), 1e-12f);
+        nx /= nn; ny /= nn; nz /= nn;
+    }
+    a.voxel_normal[3 * (size_t)m] = nx; a.voxel_normal[3 * (size_t)m + 1] = ny; a.voxel_normal[3 * (size_t)m + 2] = nz;
+    a.update_mask[m] = upd ? 1 : 0;
+}
+
 }  // namespace
 
 // =================================================================================================
+extern "C" int ags_voxel_roi(const AgsVoxelRoiArgs* a) {
+    AGS_CHECK_ARG(a != nullptr, "args is NULL");
+    AGS_CHECK_ARG(a->N >= 0, "negative N");
+    AGS_CHECK_ARG(a->dim[0] > 0 && a->dim[1] > 0 && a->dim[2] > 0 &&
+                  (long long)a->dim[0] * a->dim[1] * a->dim[2] < (1ll << 30), "bad voxel grid %d x %d x %d",
+                  a->dim[0], a->dim[1], a->dim[2]);
+    AGS_CHECK_ARG(a->voxel_size[0] > 0.f && a->voxel_size[1] > 0.f && a->voxel_size[2] > 0.f, "voxel size must be positive");
+    AGS_CHECK_ARG(a->voxel_count && a->voxel_normal && a->update_mask, "NULL output");
+    AGS_CHECK_ARG(a->N == 0 || (a->means && a->rotations && a->opacities && a->confidences), "NULL input");
+    AGS_CHECK_ARG(((uintptr_t)a->rotations & 15) == 0, "rotations must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)a->stream;
+    const int M = a->dim[0] * a->dim[1] * a->dim[2];
+    AGS_CHECK_CUDA(cudaMemsetAsync(a->voxel_count, 0, (size_t)M * 4, st));
+    AGS_CHECK_CUDA(cudaMemsetAsync(a->voxel_normal, 0, (size_t)M * 12, st));
+    if (a->N > 0) voxel_roi_scatter_kernel<<<(a->N + MO_THREADS - 1) / MO_THREADS, MO_THREADS, 0, st>>>(*a);
+    voxel_roi_finish_kernel<<<(M + MO_THREADS - 1) / MO_THREADS, MO_THREADS, 0, st>>>(*a, M);
+    AGS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" size_t ags_spawn_scratch_bytes(int32_t H, int32_t W) {
     if (H <= 0 || W <= 0) return 0;
     return spawn_carve(nullptr, H, W).total;

@@ -128,6 +128,15 @@ class UtilityArgs(C.Structure):
     ]
 
 
+class VoxelRoiArgs(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("means", _f), ("rotations", _f), ("opacities", _f), ("confidences", _f),
+        ("bbox_min", C.c_float * 3), ("voxel_size", C.c_float * 3), ("dim", C.c_int32 * 3),
+        ("confidence_thres", C.c_float), ("opacity_thres", C.c_float), ("min_gaussian_per_voxel", C.c_int32),
+        ("voxel_count", _f), ("voxel_normal", _f), ("update_mask", _f), ("stream", _f),
+    ]
+
+
 _lib = None
 
 EXPORTS = ["ags_scratch_bytes", "ags_render_forward", "ags_render_backward", "ags_render_stage",
@@ -135,6 +144,7 @@ EXPORTS = ["ags_scratch_bytes", "ags_render_forward", "ags_render_backward", "ag
            "ags_dist_adam_step", "ags_smooth_depth", "ags_stage_cameras",
            "ags_spawn_scratch_bytes", "ags_spawn", "ags_view_stats_update", "ags_prune_scratch_bytes",
            "ags_prune_compact", "ags_view_utility", "ags_dist_vis_local", "ags_dist_vis_sum", "ags_dist_terms_put",
+           "ags_voxel_roi",
            "ags_last_error", "ags_version"]
 
 
@@ -182,6 +192,8 @@ def load():
                       ("ags_dist_terms_put", DistTermsArgs)]:
         getattr(lib, name).argtypes = [C.POINTER(typ)]
         getattr(lib, name).restype = C.c_int
+    lib.ags_voxel_roi.argtypes = [C.POINTER(VoxelRoiArgs)]
+    lib.ags_voxel_roi.restype = C.c_int
     lib.ags_dist_adam_step.argtypes = [C.POINTER(DistAdamArgs)]
     lib.ags_dist_adam_step.restype = C.c_int
     lib.ags_postprocess.argtypes = [C.c_int32] * 3 + [C.c_void_p] * 7

@@ -213,3 +213,33 @@ def view_utility(depth, confidence, voxel_centers, unexplored, w2c, K, depth_ran
     a.stream = L.current_stream(dev)
     L.check(lib.ags_view_utility(C.byref(a)), "ags_view_utility")
     return explore, exploit
+
+
+def voxel_roi(means, rotations_raw, opacities_raw, confidences, bbox_min, voxel_size, dim, *,
+              confidence_thres=0.3, opacity_thres=0.7, min_gaussian_per_voxel=5):
+    """ags_voxel_roi (mapping/voxel_map.py:70-113): per voxel of the (dim) grid the number of opaque
+    low-confidence Gaussians, the normalised mean normal where that number exceeds
+    min_gaussian_per_voxel (else 0) and the corresponding bool mask.  Returns (count (M,) int32,
+    normal (M,3), mask (M,) bool)."""
+    lib = L.load()
+    dev = means.device
+    N = means.shape[0]
+    dim = [int(d) for d in dim]
+    M = dim[0] * dim[1] * dim[2]
+    a = L.VoxelRoiArgs()
+    a.N = N
+    keep = [means.float().contiguous(), rotations_raw.float().contiguous(), opacities_raw.float().contiguous(),
+            confidences.float().contiguous()]
+    a.means, a.rotations, a.opacities, a.confidences = [L.ptr(t) for t in keep]
+    a.bbox_min = (C.c_float * 3)(*[float(x) for x in bbox_min])
+    a.voxel_size = (C.c_float * 3)(*[float(x) for x in voxel_size])
+    a.dim = (C.c_int32 * 3)(*dim)
+    a.confidence_thres, a.opacity_thres = float(confidence_thres), float(opacity_thres)
+    a.min_gaussian_per_voxel = int(min_gaussian_per_voxel)
+    count = torch.empty(M, dtype=torch.int32, device=dev)
+    normal = torch.empty(M, 3, dtype=torch.float32, device=dev)
+    mask = torch.empty(M, dtype=torch.uint8, device=dev)
+    a.voxel_count, a.voxel_normal, a.update_mask = L.ptr(count), L.ptr(normal), L.ptr(mask)
+    a.stream = L.current_stream(dev)
+    L.check(lib.ags_voxel_roi(C.byref(a)), "ags_voxel_roi")
+    return count, normal, mask.bool()

@@ -81,3 +81,16 @@ class Exploration(_UtilityBase):
     def cal_utility(self, gaussian_map, voxel_map, candidates, simulator):
         explore, _, t = self._utilities(gaussian_map, voxel_map, candidates, simulator)
         return explore, t
+
+
+def low_confidence_voxels(voxel_map, gaussian_map, confidence_thres=0.3):
+    """The Gaussian half of VoxelMap.update_utility (mapping/voxel_map.py:70-113) in one scatter kernel
+    (the reference: 4 activation passes, 6 boolean-index compactions, 2 scatter_adds): returns
+    (voxel_normal (M,3), update_mask (M,) bool) for `self.voxel_normal` / `raw_roi_mask += update_mask`.
+    `voxel_map` needs bbox (2,3), size (3,), dim (3,), min_gaussian_per_voxel."""
+    gm = gaussian_map
+    _, normal, mask = ops.voxel_roi(gm.get_means.detach(), gm._rotations.detach(), gm._opacities.detach(),
+                                    gm.get_confidences.detach(), voxel_map.bbox[0].tolist(), voxel_map.size.tolist(),
+                                    [int(d) for d in voxel_map.dim], confidence_thres=confidence_thres,
+                                    min_gaussian_per_voxel=voxel_map.min_gaussian_per_voxel)
+    return normal, mask

@@ -357,6 +357,32 @@ typedef struct AgsUtilityArgs {
 } AgsUtilityArgs;
 int ags_view_utility(const AgsUtilityArgs* args);
 
+/* ags_voxel_roi   mapping/voxel_map.py:70-113 (the Gaussian half of VoxelMap.update_utility): voxels that
+ *             hold more than min_gaussian_per_voxel opaque (sigmoid(opacity) > opacity_thres) but
+ *             low-confidence (confidence < confidence_thres) Gaussians, and their mean surfel normal.
+ *             Activations are applied here (raw rotations / opacities; `confidences` already activated,
+ *             GaussianMap.get_confidences).  voxel index = floor((mean - bbox_min) / voxel_size) per
+ *             axis (fp32 division, like the reference), linear index x*dim_y*dim_z + y*dim_z + z
+ *             (:185-194).  voxel_count / voxel_normal are outputs AND the accumulators (zeroed here). */
+typedef struct AgsVoxelRoiArgs {
+    int32_t N;
+    const float* means;            /* (N,3) */
+    const float* rotations;        /* (N,4) raw */
+    const float* opacities;        /* (N) raw (logit) */
+    const float* confidences;      /* (N) activated */
+    float bbox_min[3];
+    float voxel_size[3];
+    int32_t dim[3];
+    float confidence_thres;        /* 0.3 */
+    float opacity_thres;           /* 0.7 */
+    int32_t min_gaussian_per_voxel;
+    int32_t* voxel_count;          /* (M) selected Gaussians per voxel, M = dim[0]*dim[1]*dim[2] */
+    float* voxel_normal;           /* (M,3) normalised mean normal where update_mask, else 0 */
+    uint8_t* update_mask;          /* (M) voxel_count > min_gaussian_per_voxel */
+    void* stream;
+} AgsVoxelRoiArgs;
+int ags_voxel_roi(const AgsVoxelRoiArgs* args);
+
 const char* ags_last_error(void);
 int ags_version(void);
 

@@ -480,3 +480,27 @@ def view_utilities(depth, confidence, voxel_centers, unexplored, extrinsics, int
     explore[torch.isnan(explore)] = 0.0
     exploit[torch.isnan(exploit)] = 0.0
     return explore, exploit
+
+
+def low_confidence_voxels(state, bbox_min, size, dim, min_gaussian_per_voxel=5, confidence_thres=0.3,
+                          opacity_thres=0.7, scale_factor=0.01):
+    """mapping/voxel_map.py:70-113 (the Gaussian half of VoxelMap.update_utility): per voxel the number
+    of opaque (> opacity_thres) low-confidence (< confidence_thres) Gaussians whose mean falls in it,
+    update_mask = count > min_gaussian_per_voxel, voxel_normal = normalised mean of their normals
+    (0 elsewhere).  Returns (count (M,) int64, voxel_normal (M,3), update_mask (M,) bool)."""
+    means, _, opac, conf, _, rot = activate(state["means"], state["scales"], state["rotations"], state["opacities"],
+                                            state["harmonics"], state["view_scores"], state["view_supports"],
+                                            state["view_means"], scale_factor)
+    normals = F.normalize(rr.quat_to_rotmat(rot)[:, :3, 2])
+    dim = torch.as_tensor(dim).int()
+    idx = torch.floor((means - bbox_min) / size).int()
+    ok = torch.all(idx >= 0, dim=1) & torch.all(idx < dim, dim=1) & (conf < confidence_thres) & (opac > opacity_thres)
+    idx, normals = idx[ok].long(), normals[ok]
+    lin = idx[:, 0] * int(dim[1] * dim[2]) + idx[:, 1] * int(dim[2]) + idx[:, 2]
+    M = int(torch.prod(dim))
+    count = torch.zeros(M, dtype=torch.int64).scatter_add(0, lin, torch.ones_like(lin))
+    nsum = torch.zeros(M, 3).scatter_add(0, lin[:, None].expand(-1, 3), normals)
+    upd = count > min_gaussian_per_voxel
+    vn = torch.zeros(M, 3)
+    vn[upd] = F.normalize(nsum[upd] / count[upd, None], dim=-1)
+    return count, vn, upd

@@ -143,6 +143,14 @@ def main():
         dv[dv < 0.001] = 10000
         dv = torch.clamp(dv, min=sim.depth_range[0], max=sim.depth_range[1])
         vis.append(vm.cal_visible_mask(cand_ext[i], cand_K[i], dv))
+    # ---- VoxelMap.update_utility (mapping/voxel_map.py:62-116): voxels with many opaque low-confidence surfels
+    vcfg2 = ns(min_gaussian_per_voxel=3, map_resolution=[0.25, 0.25, 0.25], safety_margin=0.3)
+    vm2 = vmod.VoxelMap(vcfg2, bbox, "cpu")
+    gm.view_scores = gm.view_scores * 0.25                     # most surfels below the 0.3 confidence threshold
+    vm2.update_utility(gm, use_confidence=True)
+    G["voxel_roi"] = dict(state=mg.dump_state(gm), bbox=vm2.bbox.clone(), size=vm2.size.clone(), dim=vm2.dim.clone(),
+                          min_gaussian_per_voxel=3, confidence_thres=0.3, voxel_normal=vm2.voxel_normal.clone())
+    gm.view_scores = gm.view_scores * 4.0
     map_state = mg.dump_state(gm)
     G["planner"] = dict(state=map_state, ext=cand_ext, K=cand_K, hw=(32, 32), depth_range=sim.depth_range,
                         voxel_centers=vm.voxel_centers.clone(), unexplored=vm.unexplored_mask.clone(),
@@ -155,6 +163,7 @@ def main():
     print("first: candidates", new0["means"].shape[0], "of", hw[0] * hw[1], "| second:", new1["means"].shape[0],
           "| voxel filter kept", G["voxel"]["n_new"], "of", cap2["points"].shape[0],
           "| coarse kept", G["voxel_coarse"]["selected"].numel())
+    print("voxel roi: voxels flagged", int((G["voxel_roi"]["voxel_normal"].norm(dim=1) > 0).sum()), "of", G["voxel_roi"]["voxel_normal"].shape[0])
     print("utility (confidence)", util, "\nutility (exploration)", util_e, "visible voxels", G["planner"]["visible"].sum(1))
 
 

@@ -249,3 +249,28 @@ def test_planner_mirror_matches_reference_planner_outputs(gold):
     assert float((u_e - g["utility_exploration"]).abs().max()) <= 4.5 / M
     assert torch.allclose(u_c, g["utility_confidence"], atol=2e-2, rtol=1e-3)
     assert int(torch.argmax(u_c)) == int(torch.argmax(g["utility_confidence"]))
+
+
+def test_voxel_roi_matches_oracle_and_reference_fixture(gold):
+    """ags_voxel_roi / planning.low_confidence_voxels vs VoxelMap.update_utility's voxel_normal (fixture)"""
+    from types import SimpleNamespace as ns
+    from active_gs_b200 import planning
+    from active_gs_b200.config import default_gaussian_map_config
+    from active_gs_b200.gaussian_map import GaussianMap
+    from oracle import host_ref as hr
+    dev = _dev()
+    g = gold["voxel_roi"]
+    gm = GaussianMap(default_gaussian_map_config(), dev)
+    for k, v in g["state"].items():
+        setattr(gm, k if k.startswith("view_") else "_" + k, v.clone().to(dev))
+    vm = ns(bbox=g["bbox"], size=g["size"], dim=g["dim"], min_gaussian_per_voxel=g["min_gaussian_per_voxel"])
+    normal, mask = planning.low_confidence_voxels(vm, gm, g["confidence_thres"])
+    count_ref, vn_ref, upd_ref = hr.low_confidence_voxels(g["state"], g["bbox"][0], g["size"], g["dim"],
+                                                          g["min_gaussian_per_voxel"], g["confidence_thres"])
+    assert torch.equal(mask.cpu(), upd_ref)
+    assert torch.allclose(normal.cpu(), vn_ref, atol=1e-5)
+    assert torch.allclose(normal.cpu(), g["voxel_normal"], atol=1e-5)
+    from active_gs_b200 import ops
+    count, _, _ = ops.voxel_roi(gm._means, gm._rotations, gm._opacities, gm.get_confidences, g["bbox"][0].tolist(),
+                                g["size"].tolist(), g["dim"].tolist(), min_gaussian_per_voxel=g["min_gaussian_per_voxel"])
+    assert torch.equal(count.cpu().long(), count_ref)

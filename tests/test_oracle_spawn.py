@@ -82,3 +82,12 @@ def test_planner_utilities(gold):
     assert torch.allclose(explore, g["utility_exploration"], atol=1e-7)
     assert torch.allclose(g["explore_weight"] * explore + exploit, g["utility_confidence"], atol=1e-6)
     assert float(exploit.min()) > 0
+
+
+def test_low_confidence_voxels(gold):
+    g = gold["voxel_roi"]
+    count, vn, upd = hr.low_confidence_voxels(g["state"], g["bbox"][0], g["size"], g["dim"], g["min_gaussian_per_voxel"],
+                                              g["confidence_thres"])
+    assert int(upd.sum()) > 20
+    assert torch.equal(upd, g["voxel_normal"].norm(dim=1) > 0)
+    assert torch.allclose(vn, g["voxel_normal"], atol=1e-6)
