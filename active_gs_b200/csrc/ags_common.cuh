@@ -33,7 +33,7 @@ struct AgsWorkspace {
     int32_t* tile_count;   // (B*tiles)
     int32_t* tile_offset;  // (B*tiles)
     int32_t* tile_fill;    // (B*tiles)
-    int32_t* counters;     // (8) [0] = instance allocator, [1] = visible pairs
+    int32_t* counters;     // (8) [0] = instance allocator, [1] = visible pairs, [2] = tiles above AGS_FUSED_SORT_MAX
     uint64_t* inst_key;    // (inst_cap) depth_bits<<32 | gaussian id, grouped per tile
     uint64_t* inst_key_alt;// (inst_cap) ping-pong buffer for oversize tiles
     int32_t* inst_sorted;  // (inst_cap) gaussian ids, front-to-back per tile

@@ -43,6 +43,7 @@ alloc_kernel(AgsWorkspace w, int n_tiles_total, int tiles_per_view, int inst_cap
             atomicAdd(stats + AGS_STAT_VIEW0 + v, c);
         }
     }
+    if (c > AGS_FUSED_SORT_MAX) atomicAdd(w.counters + 2, 1);      // tile_sort_kernel has work to do
     int incl = c;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -113,11 +114,8 @@ __device__ __forceinline__ void bitonic_smem(uint64_t* s, int m) {
     }
 }
 
-__global__ void __launch_bounds__(SORT_THREADS)
-tile_sort_kernel(AgsWorkspace w, int inst_cap) {
-    __shared__ uint64_t s[SORT_CHUNK];
-    if (w.counters[0] > inst_cap) return;
-    const int t = blockIdx.x;
+// one oversize tile (more than AGS_FUSED_SORT_MAX instances): chunk sort + rank merges
+__device__ void sort_oversize_tile(const AgsWorkspace& w, int t, uint64_t* s) {
     const int n = w.tile_count[t];
     if (n <= AGS_FUSED_SORT_MAX) return;     // sorted in the prologue of composite_fwd
     const int off = w.tile_offset[t];
@@ -165,6 +163,19 @@ tile_sort_kernel(AgsWorkspace w, int inst_cap) {
     for (int k = threadIdx.x; k < n; k += SORT_THREADS) out[k] = (int32_t)(src[k] & 0xffffffffu);
 }
 
+// Oversize tiles are rare (none at all in the BASELINE workloads): the binning pass counts them in
+// counters[2], and a small persistent grid returns at once when there is nothing to do -- one block per
+// tile cost ~10 us per iteration in block scheduling alone.
+__global__ void __launch_bounds__(SORT_THREADS)
+tile_sort_kernel(AgsWorkspace w, int n_tiles_total, int inst_cap) {
+    __shared__ uint64_t s[SORT_CHUNK];
+    if (w.counters[2] == 0 || w.counters[0] > inst_cap) return;
+    for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x) {
+        sort_oversize_tile(w, t, s);
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 int ags_launch_binning(const AgsRenderArgs& a, const AgsWorkspace& w) {
@@ -181,7 +192,7 @@ int ags_launch_binning(const AgsRenderArgs& a, const AgsWorkspace& w) {
     }
     // only tiles with more than AGS_FUSED_SORT_MAX instances are sorted here (chunk sort + merge);
     // all others are sorted in the prologue of composite_fwd
-    tile_sort_kernel<<<nt, SORT_THREADS, 0, st>>>(w, a.inst_cap);
+    tile_sort_kernel<<<nt < 148 * 2 ? nt : 148 * 2, SORT_THREADS, 0, st>>>(w, nt, a.inst_cap);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
