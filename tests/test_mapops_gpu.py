@@ -274,3 +274,49 @@ def test_voxel_roi_matches_oracle_and_reference_fixture(gold):
     count, _, _ = ops.voxel_roi(gm._means, gm._rotations, gm._opacities, gm.get_confidences, g["bbox"][0].tolist(),
                                 g["size"].tolist(), g["dim"].tolist(), min_gaussian_per_voxel=g["min_gaussian_per_voxel"])
     assert torch.equal(count.cpu().long(), count_ref)
+
+
+def test_map_store_external_tensors_public_prune_and_growth(tmp_path):
+    """GaussianMap keeps the reference's attribute surface on top of the capacity buffers: tensors
+    assigned from outside (load(), tests) are adopted, prune(mask) ORs the opacity test into the caller's
+    mask in place (quirk Q5, mapping/gaussian_map.py:234-246), add_gaussians appends without touching the
+    existing rows, and old references are not silently resized."""
+    from active_gs_b200.config import default_gaussian_map_config
+    from active_gs_b200.gaussian_map import GaussianMap
+    dev = _dev()
+    state = syn.make_room_scene(3000, seed=31)
+    gm = GaussianMap(default_gaussian_map_config(), dev)
+    for k, v in state.items():
+        setattr(gm, k if k.startswith("view_") else "_" + k, v.clone().to(dev))
+    gm.save(str(tmp_path), "t")
+    gm2 = GaussianMap(default_gaussian_map_config(), dev)
+    gm2.load(str(tmp_path / "map_t.th"))
+    # public prune with a caller-owned mask
+    g = torch.Generator().manual_seed(1)
+    mask = (torch.rand(3000, generator=g) < 0.3).to(dev)
+    want_drop = mask.cpu() | (torch.sigmoid(state["opacities"]) < 0.1)
+    before = {k: getattr(gm2, k if k.startswith("view_") else "_" + k).clone() for k in state}
+    gm2.prune(mask)
+    assert torch.equal(mask.cpu(), want_drop)
+    n = int((~want_drop).sum())
+    for k in state:
+        t = getattr(gm2, k if k.startswith("view_") else "_" + k)
+        assert t.shape[0] == n and torch.equal(t.cpu(), before[k].cpu()[~want_drop]), k
+    assert gm2._harmonics.shape == (n, 1, 3)
+    # spawn appends after the surviving rows
+    f = _plane_frame(48, 64, 9)
+    old_means = gm2._means
+    kept = gm2._means.clone()
+    torch.manual_seed(3)
+    gm2.add_gaussians(f)
+    n2 = gm2._means.shape[0]
+    assert n2 > n and old_means.shape[0] == n
+    assert torch.equal(gm2._means[:n], kept)
+    assert torch.equal(gm2._scales[n:].cpu(), torch.tensor([0.0, 0.0, -1e10]).expand(n2 - n, 3))
+    assert len(gm2.training_data) == 1 and gm2.training_performance.shape[0] == 1
+    # externally replaced tensors (different length) are adopted by the next call
+    for k, v in state.items():
+        setattr(gm2, k if k.startswith("view_") else "_" + k, v[:500].clone().to(dev))
+    gm2.add_gaussians(_plane_frame(48, 64, 10))
+    assert gm2._means.shape[0] > 500 and torch.equal(gm2._means[:500].cpu(), state["means"][:500])
+    assert gm2.get_attr()[0].shape[0] == gm2.view_scores.shape[0] == gm2._means.shape[0]
