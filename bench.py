@@ -85,6 +85,28 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(inside)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run on (and, by first touch, allocate pinned host memory from) the NUMA node
+    the GPU hangs off, so the per-step keyframe uploads of the end-to-end arm do not cross the socket
+    interconnect.  Best effort (sysfs); returns a description for the log."""
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return f"gpu {bdf}: no NUMA information"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return f"gpu {bdf}: NUMA node {node}, {len(cpus)} cpus"
+    except Exception as e:                                      # containers without sysfs access etc.
+        return f"NUMA binding skipped: {e}"
+
+
 def build_workload(dev, rank, world, seed_base=1000 + CONFIG_IDX):
     """Scene + 8*world keyframes (rendered from the generating scene with our own renderer, then
     depth noise) + the perturbed start state.  Deterministic; identical on every rank."""
@@ -220,6 +242,9 @@ def algorithmic_bytes(N, B, P, I, V, tiles):
 def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa = bind_to_gpu_numa_node(local_rank)
+    if world > 1:
+        print(f"[rank {rank}] {numa}", file=sys.stderr, flush=True)
     shard = None
     if world > 1:
         import torch.distributed as dist
