@@ -32,6 +32,8 @@ from active_gs_b200.config import default_gaussian_map_config  # noqa: E402
 CONFIG_IDX = 2          # BASELINE.json config[1] (the headline workload); --config 3 / 5 select the
 B_PER_GPU = 8           # larger parity configurations (not the headline line)
 METRIC, UNIT = "train_mpix_per_s", "Mpix/s"
+WORKLOAD_C2 = ("BASELINE config[1]: office0-shaped room, 200k Gaussian surfels, 640x480, "
+               "train-loop iteration (render 8 keyframes fwd+bwd, 4-term loss, Adam)")
 
 
 def measured_peaks():
@@ -323,8 +325,7 @@ def run_ours(args, rank, world, local_rank):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "iters_per_s": args.steps / (ms / 1e3),
-        "config": {"workload": ("BASELINE config[1]: office0-shaped room, 200k Gaussian surfels, 640x480, "
-                                "train-loop iteration (render 8 keyframes fwd+bwd, 4-term loss, Adam)") if CONFIG_IDX == 2
+        "config": {"workload": WORKLOAD_C2 if CONFIG_IDX == 2
                                else f"SURVEY 8d config {CONFIG_IDX}: {N} surfels, {W}x{H}, {B} keyframes per step",
                    "gaussians": N, "H": H, "W": W, "keyframes_per_gpu": B, "global_batch": Bg,
                    "parallelism": f"frame-shard x{world}" + ("" if world == 1 else
@@ -426,9 +427,11 @@ def run_reference(args, rank, world):
     return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world,
             "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["seconds"] / steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE config[1]: one training iteration over the 8-keyframe batch per step "
-                                   "(CPU oracle port; steps capped at 3)", "gaussians": N, "H": H, "W": W,
-                       "keyframes_per_step": len(frames)},
+            # the same workload keys as our arm; what the CPU run sampled of it is in cpu_baseline.sample
+            "config": {"workload": WORKLOAD_C2 if CONFIG_IDX == 2 else
+                                   f"SURVEY 8d config {CONFIG_IDX}: {N} surfels, {W}x{H}, {len(frames)} keyframes per step",
+                       "gaussians": N, "H": H, "W": W, "keyframes_per_gpu": len(frames), "global_batch": len(frames),
+                       "parallelism": "host cores (CPU oracle port), steps capped at 3"},
             "cpu_baseline": cb, "gpu_launches": 0,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 

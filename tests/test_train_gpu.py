@@ -123,11 +123,15 @@ def test_train_c1_vs_reference_fixture(golden):
     assert abs(p_ours - p_ref) <= 0.05
 
 
-def test_train_multiframe_prune_vs_reference_fixture(golden):
-    """T=6 keyframes, 48x32 (non-square: quirk Q2), B=6 (quirk Q1), sampler draw, prune at the end."""
+@pytest.mark.parametrize("post_chunk", [16, 4])
+def test_train_multiframe_prune_vs_reference_fixture(golden, post_chunk):
+    """T=6 keyframes, 48x32 (non-square: quirk Q2), B=6 (quirk Q1), sampler draw, prune at the end.
+    post_chunk=4 renders the six keyframes of the prune pass in two launches (the chunked path long
+    missions take, GaussianMap.POST_CHUNK) and must reach the same state."""
     dev = _dev()
     g = golden["train_multi"]
     gm = make_map(g["start"], g["frames"], dev, perf0=g["perf0"], prune_interval=g["prune_interval"])
+    gm.POST_CHUNK = post_chunk
     np.random.seed(g["np_seed"])
     gm.train(steps=3)
     torch.cuda.synchronize()
