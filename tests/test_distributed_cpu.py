@@ -76,3 +76,35 @@ def test_frame_shard_world2_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert all(ret.get(r) for r in range(world))
+
+
+def test_balance_partition_properties_all_world_sizes():
+    """FrameShard.balance without a process group: permutation, B frames per rank, pinned active
+    keyframes, never worse than the contiguous split by more than one frame's cost, and usually better."""
+    from active_gs_b200.distributed import FrameShard
+    rng = np.random.default_rng(0)
+    better = worse = 0
+    for world in (2, 3, 4, 8):
+        for trial in range(40):
+            b = int(rng.integers(1, 9))
+            n_active = int(rng.integers(0, min(3, world * b) + 1))
+            ids = rng.permutation(200)[:world * b]
+            cost = {int(i): float(rng.uniform(2e4, 1.2e5)) for i in ids if rng.random() < 0.9}
+            outs = []
+            for rank in range(world):
+                sh = FrameShard.__new__(FrameShard)
+                sh.world, sh.rank = world, rank
+                outs.append(sh.balance(ids, n_active, cost))
+            assert all(np.array_equal(outs[0], o) for o in outs)          # rank-independent
+            bal = outs[0]
+            assert sorted(bal.tolist()) == sorted(ids.tolist()) and len(bal) == world * b
+            for j in range(n_active):
+                r, k = sh.pinned_slot(j)
+                assert bal[r * b + k] == ids[j]
+            mean = np.mean(list(cost.values())) if cost else 0.0
+            c = lambda i: cost.get(int(i), mean)
+            load = lambda order: max(sum(c(i) for i in order[r * b:(r + 1) * b]) for r in range(world))
+            assert load(bal) <= load(ids) + max(c(i) for i in ids) + 1e-6
+            better += load(bal) < load(ids) - 1e-6
+            worse += load(bal) > load(ids) + 1e-6
+    assert better > 100 and worse < 10
