@@ -10,7 +10,6 @@ sampled keyframe batch.  Exchanges per iteration:
 The sampler draw uses numpy's global RNG with the same seed on every rank, so the ids agree without
 a broadcast.  Loss normalisers use the global batch size (AgsLossArgs.B_total).
 """
-import ctypes as C
 import numpy as np
 import torch
 import torch.distributed as dist

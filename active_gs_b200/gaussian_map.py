@@ -13,7 +13,6 @@ traffic per iteration is the (B,) keyframe ids up and (B + stats) floats down fo
 loss-weighted sampler, exactly the dependency the reference has (mapping/utils.py:206-218).
 """
 import ctypes as C
-import math
 import os
 import numpy as np
 import torch

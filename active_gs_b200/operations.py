@@ -18,7 +18,6 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from . import lib as L
 from . import ops
 from .rasterizer import RenderBatch
 

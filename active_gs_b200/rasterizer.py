@@ -5,7 +5,7 @@
 kwargs, 8 returned tensors), so `render_cuda_core` runs unchanged on top of libags_b200.so.
 `RenderBatch` is the B-view form used by the fused training loop (active_gs_b200.gaussian_map).
 """
-from typing import NamedTuple, Optional
+from typing import NamedTuple
 import ctypes as C
 import torch
 

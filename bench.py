@@ -13,7 +13,6 @@ its own 8 keyframes of an 8N-keyframe batch; gradients are all-reduced).  One JS
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
