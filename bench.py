@@ -335,10 +335,11 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * P * 16 + B * 36 * 4,
                 "d2h_bytes_per_step": (4 + 2 * B) * 4 + 32, "ms_per_step": ms_e2e / args.steps,
                 "what": "GaussianMap.train(steps=K) incl. engine set-up and post_processing, keyframes in pinned host memory"},
-        # our kernels per step: stage_cameras, project_fwd, alloc, scatter, composite_fwd, loss_vis_count,
-        # loss_pass_a, loss_pass_b, composite_bwd, zero_grads, project_bwd, adam (N>1: + vis local/sum,
-        # terms put, dist_adam instead of adam); torch's own stack/memset launches are not counted
-        "gpu_launches": (12 if world == 1 else 15) * args.steps,
+        # our kernels per step: stage_cameras, project_fwd, alloc, scatter, tile_sort, composite_fwd,
+        # loss_vis_count, loss_pass_a, loss_pass_b, composite_bwd, zero_grads, project_bwd, adam (N>1: + vis
+        # local/sum, terms put, dist_adam instead of adam); torch's own stack/memset/barrier launches are
+        # not counted
+        "gpu_launches": (13 if world == 1 else 16) * args.steps,
         "clocks": clk,
     }
     if stages is not None:
