@@ -43,7 +43,7 @@ for rep in range(3):
 for rep in range(3):
     t = [T()]
     gm._make_contiguous(); t.append(T())
-    fovs, views, projs, tanfovs = gm._camera_table(); t.append(T())
-    eng = _TrainEngine(gm, 8, H, W, None); t.append(T())
+    rows = gm._camera_rows(range(len(gm.training_data))); t.append(T())
+    eng = _TrainEngine(gm, 8, H, W, None, cam_table=rows.to(dev)); t.append(T())
     print("setup parts ms:", {n: round(1e3 * (b - a), 2) for n, a, b in zip(["contiguous", "camera table", "engine init"], t[:-1], t[1:])})
     del eng
