@@ -117,10 +117,10 @@ extern "C" int ags_adam_step(const AgsAdamArgs* a) {
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks < 1) blocks = 1;
     dim3 grid((unsigned)blocks, a->num_groups);
-    adam_kernel<<<grid, threads, 0, st>>>(P, total);
+    ags_note_launch(); adam_kernel<<<grid, threads, 0, st>>>(P, total);
     AGS_CHECK_CUDA(cudaGetLastError());
     if (a->step_dev) {
-        tick_kernel<<<1, 1, 0, st>>>(a->step_dev, a->skip_flag);
+        ags_note_launch(); tick_kernel<<<1, 1, 0, st>>>(a->step_dev, a->skip_flag);
         AGS_CHECK_CUDA(cudaGetLastError());
     }
     return 0;

@@ -91,6 +91,9 @@ void ags_set_error(const char* fmt, ...);
         }                                                                           \
     } while (0)
 
+// every kernel launch of the library is counted (bench.py reports the number it saw inside the timed region)
+void ags_note_launch();
+
 // kernel launchers implemented in the individual .cu files
 int ags_launch_project_fwd(const AgsRenderArgs& a, const AgsWorkspace& w, bool for_backward);
 int ags_launch_binning(const AgsRenderArgs& a, const AgsWorkspace& w);

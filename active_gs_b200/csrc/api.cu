@@ -13,6 +13,10 @@ void ags_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;   // host-side, one mapper thread per process (SURVEY 8b threading)
+void ags_note_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+extern "C" unsigned long long ags_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 extern "C" const char* ags_last_error(void) { return g_err; }
 extern "C" int ags_version(void) { return 100; }
 

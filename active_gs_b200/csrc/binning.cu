@@ -182,17 +182,17 @@ int ags_launch_binning(const AgsRenderArgs& a, const AgsWorkspace& w) {
     cudaStream_t st = (cudaStream_t)a.stream;
     const int tiles = ((a.W + TILE - 1) / TILE) * ((a.H + TILE - 1) / TILE);
     const int nt = a.B * tiles;
-    alloc_kernel<<<(nt + 255) / 256, 256, 0, st>>>(w, nt, tiles, a.inst_cap, a.stats);
+    ags_note_launch(); alloc_kernel<<<(nt + 255) / 256, 256, 0, st>>>(w, nt, tiles, a.inst_cap, a.stats);
     AGS_CHECK_CUDA(cudaGetLastError());
     if (a.N > 0) {
         long long blocks = ((long long)a.N * a.B + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
-        scatter_kernel<<<(int)blocks, 256, 0, st>>>(a, w);
+        ags_note_launch(); scatter_kernel<<<(int)blocks, 256, 0, st>>>(a, w);
         AGS_CHECK_CUDA(cudaGetLastError());
     }
     // only tiles with more than AGS_FUSED_SORT_MAX instances are sorted here (chunk sort + merge);
     // all others are sorted in the prologue of composite_fwd
-    tile_sort_kernel<<<nt < 148 * 2 ? nt : 148 * 2, SORT_THREADS, 0, st>>>(w, nt, a.inst_cap);
+    ags_note_launch(); tile_sort_kernel<<<nt < 148 * 2 ? nt : 148 * 2, SORT_THREADS, 0, st>>>(w, nt, a.inst_cap);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -597,7 +597,7 @@ composite_bwd_px2_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) 
 int ags_launch_composite_fwd(const AgsRenderArgs& a, const AgsWorkspace& w) {
     dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE, a.B);
     dim3 block(TILE * TILE);
-    composite_fwd_kernel<<<grid, block, 0, (cudaStream_t)a.stream>>>(a, w);
+    ags_note_launch(); composite_fwd_kernel<<<grid, block, 0, (cudaStream_t)a.stream>>>(a, w);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -605,10 +605,10 @@ int ags_launch_composite_fwd(const AgsRenderArgs& a, const AgsWorkspace& w) {
 int ags_launch_composite_bwd(const AgsRenderArgs& a, const AgsRenderGradArgs& g, const AgsWorkspace& w) {
     dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE, a.B);
 #if AGS_BWD_PX2
-    composite_bwd_px2_kernel<<<grid, 128, 0, (cudaStream_t)a.stream>>>(a, g, w);
+    ags_note_launch(); composite_bwd_px2_kernel<<<grid, 128, 0, (cudaStream_t)a.stream>>>(a, g, w);
 #else
     dim3 block(TILE * TILE);
-    composite_bwd_kernel<<<grid, block, 0, (cudaStream_t)a.stream>>>(a, g, w);
+    ags_note_launch(); composite_bwd_kernel<<<grid, block, 0, (cudaStream_t)a.stream>>>(a, g, w);
 #endif
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;

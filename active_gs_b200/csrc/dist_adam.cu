@@ -181,7 +181,7 @@ extern "C" int ags_dist_adam_step(const AgsDistAdamArgs* a) {
     long long blocks = (n4 + 255) / 256;
     if (blocks > 148 * 2) blocks = 148 * 2;          // one wave (see the kernel's note)
     if (blocks < 1) blocks = 1;
-    dist_adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)a->stream>>>(P);
+    ags_note_launch(); dist_adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)a->stream>>>(P);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

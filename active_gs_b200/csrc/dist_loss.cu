@@ -98,7 +98,7 @@ extern "C" int ags_dist_vis_local(const AgsDistVisArgs* a) {
     int rc = fill_vis(a, P, false);
     if (rc) return rc;
     AGS_CHECK_ARG(a->opacity != nullptr, "NULL opacity");
-    dist_vis_local_kernel<<<(P.P + 255) / 256, 256, 0, (cudaStream_t)a->stream>>>(P);
+    ags_note_launch(); dist_vis_local_kernel<<<(P.P + 255) / 256, 256, 0, (cudaStream_t)a->stream>>>(P);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -108,7 +108,7 @@ extern "C" int ags_dist_vis_sum(const AgsDistVisArgs* a) {
     int rc = fill_vis(a, P, true);
     if (rc) return rc;
     AGS_CHECK_ARG(a->vis_count != nullptr, "NULL vis_count");
-    dist_vis_sum_kernel<<<(P.P + 255) / 256, 256, 0, (cudaStream_t)a->stream>>>(P);
+    ags_note_launch(); dist_vis_sum_kernel<<<(P.P + 255) / 256, 256, 0, (cudaStream_t)a->stream>>>(P);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -127,7 +127,7 @@ extern "C" int ags_dist_terms_put(const AgsDistTermsArgs* a) {
         P.peers[r] = r < a->world ? a->gather_peers[r] : nullptr;
         if (!a->gather_multicast && r < a->world) AGS_CHECK_ARG(a->gather_peers[r] != nullptr, "NULL peer pointer %d", r);
     }
-    dist_terms_put_kernel<<<1, ((a->nterm + 31) / 32) * 32, 0, (cudaStream_t)a->stream>>>(P);
+    ags_note_launch(); dist_terms_put_kernel<<<1, ((a->nterm + 31) / 32) * 32, 0, (cudaStream_t)a->stream>>>(P);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

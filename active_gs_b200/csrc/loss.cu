@@ -330,7 +330,7 @@ extern "C" int ags_postprocess(int32_t B, int32_t H, int32_t W, const float* nor
     AGS_CHECK_ARG(B > 0 && H > 0 && W > 0, "bad sizes");
     AGS_CHECK_ARG(normal && depth && opacity && fov && normal_unit && d2n, "NULL pointer");
     dim3 grid((unsigned)(((size_t)H * W + 255) / 256), B);
-    postprocess_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(B, H, W, normal, depth, opacity, fov,
+    ags_note_launch(); postprocess_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(B, H, W, normal, depth, opacity, fov,
                                                               normal_unit, d2n);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -358,11 +358,11 @@ extern "C" int ags_loss_forward_backward(const AgsLossArgs* a) {
     float* nb = (float*)a->workspace;                     // (B,4,H,W) neighbour contributions
     float* msum_plane = nb + (size_t)a->B * 4 * P;        // (H,W) visibility count (quirk Q1)
     dim3 grid((a->W + 31) / 32, (a->H + 7) / 8, a->B), block(32, 8);
-    loss_vis_count<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(*a, msum_plane);
+    ags_note_launch(); loss_vis_count<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(*a, msum_plane);
     AGS_CHECK_CUDA(cudaGetLastError());
-    loss_pass_a<<<grid, block, 0, st>>>(*a, nb, msum_plane);
+    ags_note_launch(); loss_pass_a<<<grid, block, 0, st>>>(*a, nb, msum_plane);
     AGS_CHECK_CUDA(cudaGetLastError());
-    loss_pass_b<<<grid, block, 0, st>>>(*a, nb, msum_plane);
+    ags_note_launch(); loss_pass_b<<<grid, block, 0, st>>>(*a, nb, msum_plane);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -34,7 +34,7 @@ extern "C" int ags_stage_cameras(const float* table, int32_t T, const int32_t* i
         ids.id[b] = ids_host[b];
     }
     const int n = B * AGS_CAM_ROW;
-    stage_cameras_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(table, ids, B, viewmatrix, projmatrix, tanfov);
+    ags_note_launch(); stage_cameras_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(table, ids, B, viewmatrix, projmatrix, tanfov);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -550,8 +550,8 @@ extern "C" int ags_voxel_roi(const AgsVoxelRoiArgs* a) {
     const int M = a->dim[0] * a->dim[1] * a->dim[2];
     AGS_CHECK_CUDA(cudaMemsetAsync(a->voxel_count, 0, (size_t)M * 4, st));
     AGS_CHECK_CUDA(cudaMemsetAsync(a->voxel_normal, 0, (size_t)M * 12, st));
-    if (a->N > 0) voxel_roi_scatter_kernel<<<(a->N + MO_THREADS - 1) / MO_THREADS, MO_THREADS, 0, st>>>(*a);
-    voxel_roi_finish_kernel<<<(M + MO_THREADS - 1) / MO_THREADS, MO_THREADS, 0, st>>>(*a, M);
+    if (a->N > 0) { ags_note_launch(); voxel_roi_scatter_kernel<<<(a->N + MO_THREADS - 1) / MO_THREADS, MO_THREADS, 0, st>>>(*a); }
+    ags_note_launch(); voxel_roi_finish_kernel<<<(M + MO_THREADS - 1) / MO_THREADS, MO_THREADS, 0, st>>>(*a, M);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -584,11 +584,11 @@ extern "C" int ags_spawn(const AgsSpawnArgs* a) {
     AGS_CHECK_CUDA(cudaMemsetAsync(w.keys, 0xff, (size_t)(w.table_mask + 1) * 8, st));
     AGS_CHECK_CUDA(cudaMemsetAsync(w.vals, 0, (size_t)(w.table_mask + 1) * 8, st));
     AGS_CHECK_CUDA(cudaMemsetAsync(a->counters, 0, 4 * sizeof(int32_t), st));
-    spawn_candidates_kernel<<<nblk, MO_THREADS, 0, st>>>(*a, cam, w);
-    spawn_count_kernel<<<nblk, MO_THREADS, 0, st>>>(*a, w);
-    scan_counts_kernel<<<1, 1024, 0, st>>>(w.blk_count, w.blk_offset, nblk, a->counters, a->counters + 2,
+    ags_note_launch(); spawn_candidates_kernel<<<nblk, MO_THREADS, 0, st>>>(*a, cam, w);
+    ags_note_launch(); spawn_count_kernel<<<nblk, MO_THREADS, 0, st>>>(*a, w);
+    ags_note_launch(); scan_counts_kernel<<<1, 1024, 0, st>>>(w.blk_count, w.blk_offset, nblk, a->counters, a->counters + 2,
                                            a->capacity - a->n_old);
-    spawn_append_kernel<<<nblk, MO_THREADS, 0, st>>>(*a, w);
+    ags_note_launch(); spawn_append_kernel<<<nblk, MO_THREADS, 0, st>>>(*a, w);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -600,7 +600,7 @@ extern "C" int ags_view_stats_update(int32_t N, const int32_t* count_last, const
     if (N == 0) return 0;
     AGS_CHECK_ARG(count_last && means && rotations_raw && view_supports && view_means && view_scores, "NULL argument");
     AGS_CHECK_ARG(((uintptr_t)rotations_raw & 15) == 0, "rotations must be 16-byte aligned");
-    view_stats_kernel<<<(N + MO_THREADS - 1) / MO_THREADS, MO_THREADS, 0, (cudaStream_t)stream>>>(
+    ags_note_launch(); view_stats_kernel<<<(N + MO_THREADS - 1) / MO_THREADS, MO_THREADS, 0, (cudaStream_t)stream>>>(
         N, count_last, means, rotations_raw, cam_x, cam_y, cam_z, depth_max, use_view_distribution, view_supports,
         view_means, view_scores);
     AGS_CHECK_CUDA(cudaGetLastError());
@@ -626,9 +626,9 @@ extern "C" int ags_prune_compact(const AgsPruneArgs* a) {
     AGS_CHECK_ARG(a->workspace_bytes >= ags_prune_scratch_bytes(a->N), "workspace too small");
     PruneWs w = prune_carve(a->workspace, a->N);
     const int nblk = (a->N + MO_THREADS - 1) / MO_THREADS;
-    prune_flag_kernel<<<nblk, MO_THREADS, 0, st>>>(*a, w);
-    scan_counts_kernel<<<1, 1024, 0, st>>>(w.blk_count, w.blk_offset, nblk, a->n_kept, nullptr, -1);
-    prune_scatter_kernel<<<nblk, MO_THREADS, 0, st>>>(*a, w);
+    ags_note_launch(); prune_flag_kernel<<<nblk, MO_THREADS, 0, st>>>(*a, w);
+    ags_note_launch(); scan_counts_kernel<<<1, 1024, 0, st>>>(w.blk_count, w.blk_offset, nblk, a->n_kept, nullptr, -1);
+    ags_note_launch(); prune_scatter_kernel<<<nblk, MO_THREADS, 0, st>>>(*a, w);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -639,7 +639,7 @@ extern "C" int ags_view_utility(const AgsUtilityArgs* a) {
     AGS_CHECK_ARG(a->depth && a->confidence && a->w2c && a->K && a->explore && a->exploit, "NULL argument");
     AGS_CHECK_ARG(a->M == 0 || (a->voxel_centers && a->unexplored), "NULL voxel arrays");
     AGS_CHECK_ARG(a->depth_hi > 0.f, "depth_hi must be positive");
-    view_utility_kernel<<<a->V, UT_THREADS, 0, (cudaStream_t)a->stream>>>(*a);
+    ags_note_launch(); view_utility_kernel<<<a->V, UT_THREADS, 0, (cudaStream_t)a->stream>>>(*a);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -484,7 +484,7 @@ project_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
 int ags_launch_project_fwd(const AgsRenderArgs& a, const AgsWorkspace& w, bool for_backward) {
     if (a.N == 0) return 0;
     dim3 grid((a.N + K1_PAIRS - 1) / K1_PAIRS, a.B);
-    project_fwd_kernel<<<grid, K1_THREADS, 0, (cudaStream_t)a.stream>>>(a, w, for_backward ? 1 : 0);
+    ags_note_launch(); project_fwd_kernel<<<grid, K1_THREADS, 0, (cudaStream_t)a.stream>>>(a, w, for_backward ? 1 : 0);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -494,10 +494,10 @@ int ags_launch_project_bwd(const AgsRenderArgs& a, const AgsRenderGradArgs& g, c
     const int threads = 128;
     cudaStream_t st = (cudaStream_t)a.stream;
     if (!g.accumulate) {
-        zero_grads_kernel<<<148 * 4, threads, 0, st>>>(g, a.N, a.B);
+        ags_note_launch(); zero_grads_kernel<<<148 * 4, threads, 0, st>>>(g, a.N, a.B);
         AGS_CHECK_CUDA(cudaGetLastError());
     }
-    project_bwd_kernel<<<148 * 8, threads, 0, st>>>(a, g, w);
+    ags_note_launch(); project_bwd_kernel<<<148 * 8, threads, 0, st>>>(a, g, w);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

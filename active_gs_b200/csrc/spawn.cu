@@ -100,11 +100,11 @@ extern "C" int ags_smooth_depth(int32_t H, int32_t W, const float* depth, float*
     unsigned* mm = (unsigned*)scratch;
     const unsigned init[2] = {0x7f7fffffu /* FLT_MAX */, 0u};
     AGS_CHECK_CUDA(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    depth_minmax_kernel<<<148, 256, 0, st>>>(depth, H * W, mm);
+    ags_note_launch(); depth_minmax_kernel<<<148, 256, 0, st>>>(depth, H * W, mm);
     AGS_CHECK_CUDA(cudaGetLastError());
     const int span = BF_TILE + 2 * radius;
     dim3 grid((W + BF_TILE - 1) / BF_TILE, (H + BF_TILE - 1) / BF_TILE), block(BF_TILE, BF_TILE);
-    bilateral_kernel<<<grid, block, (size_t)span * span * sizeof(float), st>>>(
+    ags_note_launch(); bilateral_kernel<<<grid, block, (size_t)span * span * sizeof(float), st>>>(
         depth, out, H, W, radius, -0.5f / (sigma_color * sigma_color), -0.5f / (sigma_space * sigma_space), mm);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -21,7 +21,7 @@ import torch.nn.functional as F
 from . import lib as L
 from . import ops
 from . import operations as O
-from .rasterizer import RenderBatch
+from .rasterizer import RenderBatch, views_per_chunk
 
 
 class WeightedSampler:
@@ -628,8 +628,9 @@ class GaussianMap:
         N = self._means.shape[0]
         seen = None                                   # (1,N) int32: times counted over all views but the last chunk
         last = None
-        for c0 in range(0, len(ids), self.POST_CHUNK):
-            chunk = ids[c0:c0 + self.POST_CHUNK]
+        step = views_per_chunk(N, H, W, per_gaussian=self._cap_per_gaussian, cap=self.POST_CHUNK)
+        for c0 in range(0, len(ids), step):
+            chunk = ids[c0:c0 + step]
             dgt = torch.stack([self.training_data[i]["depth"] for i in chunk]).to(self.device)
             rb = self._render_raw(chunk, H, W, render_mask=(dgt > 0.0).float(), require_importance=True,
                                   front_only=True)
@@ -705,11 +706,14 @@ class GaussianMap:
 
     # ------------------------------------------------------------------ :491-527 (.th dict format kept)
     def save(self, save_path, index="final"):
+        # the map tensors are [:N] views of capacity buffers (or of the symmetric flat buffer of the
+        # multi-GPU engine): torch.save would serialise the whole underlying storage, so clone
+        c = lambda t: t.detach().clone()
         torch.save({
-            "means": self._means.detach(), "scales": self._scales.detach(),
-            "harmonics": self._harmonics.detach(), "opacities": self._opacities.detach(),
-            "rotations": self._rotations.detach(), "view_scores": self.view_scores.detach(),
-            "view_supports": self.view_supports.detach(), "view_means": self.view_means.detach(),
+            "means": c(self._means), "scales": c(self._scales),
+            "harmonics": c(self._harmonics), "opacities": c(self._opacities),
+            "rotations": c(self._rotations), "view_scores": c(self.view_scores),
+            "view_supports": c(self.view_supports), "view_means": c(self.view_means),
             "near": self.scene_near, "far": self.scene_far,
             "use_view_direction": self.use_view_distribution,
             "background_color": self.background_color, "scale_factor": self.scale_factor,

@@ -145,7 +145,7 @@ EXPORTS = ["ags_scratch_bytes", "ags_render_forward", "ags_render_backward", "ag
            "ags_spawn_scratch_bytes", "ags_spawn", "ags_view_stats_update", "ags_prune_scratch_bytes",
            "ags_prune_compact", "ags_view_utility", "ags_dist_vis_local", "ags_dist_vis_sum", "ags_dist_terms_put",
            "ags_voxel_roi",
-           "ags_last_error", "ags_version"]
+           "ags_last_error", "ags_version", "ags_launch_count"]
 
 
 def load():
@@ -199,6 +199,8 @@ def load():
     lib.ags_postprocess.argtypes = [C.c_int32] * 3 + [C.c_void_p] * 7
     lib.ags_postprocess.restype = C.c_int
     lib.ags_last_error.restype = C.c_char_p
+    lib.ags_launch_count.restype = C.c_ulonglong
+    lib.ags_launch_count.argtypes = []
     for name in ["ags_render_forward", "ags_render_backward", "ags_loss_forward_backward",
                  "ags_adam_step", "ags_version"]:
         getattr(lib, name).restype = C.c_int

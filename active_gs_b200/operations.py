@@ -171,7 +171,6 @@ class _RenderAll(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_rgb, d_normal, d_depth, d_opacity, d_conf, *_):
         dm, ds, dr, do, dc, _ = ctx.rb.backward(d_rgb, d_normal, d_depth, d_opacity, d_conf)
-        ctx.rb = None
         return dm, dc, do, ds, dr, None, None
 
 

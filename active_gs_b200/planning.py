@@ -15,10 +15,18 @@ import torch
 
 from . import ops
 from . import operations as O
+from .rasterizer import views_per_chunk
 
 
 class _UtilityBase:
-    CHUNK = 128            # candidate views per rasterizer launch
+    CHUNK = 128            # candidate views per rasterizer launch (upper bound; see _chunk)
+    WORKSPACE_BUDGET = 2 << 30
+
+    def _chunk(self, gaussian_map, h, w):
+        """views per launch from a workspace byte budget: 128 views over a 1 M-surfel map would ask
+        for > 10 GB of per-(view, Gaussian) scratch before any visibility is known"""
+        return views_per_chunk(gaussian_map.get_means.shape[0], h, w, self.WORKSPACE_BUDGET,
+                               device_index=self.device.index or 0, cap=self.CHUNK)
 
     def __init__(self, cfg, device):
         self.device = torch.device(device)
@@ -27,8 +35,9 @@ class _UtilityBase:
     def _render(self, gaussian_map, extrinsics, intrinsics, h, w):
         depth, conf = [], []
         attrs = gaussian_map.get_attr()
-        for c0 in range(0, extrinsics.shape[0], self.CHUNK):
-            out = O.GaussianRenderer(extrinsics[c0:c0 + self.CHUNK], intrinsics[c0:c0 + self.CHUNK], attrs,
+        chunk = self._chunk(gaussian_map, h, w)
+        for c0 in range(0, extrinsics.shape[0], chunk):
+            out = O.GaussianRenderer(extrinsics[c0:c0 + chunk], intrinsics[c0:c0 + chunk], attrs,
                                      gaussian_map.background_color, (gaussian_map.scene_near, gaussian_map.scene_far),
                                      (h, w), self.device).render_view_all()
             depth.append(out[1][:, 0])

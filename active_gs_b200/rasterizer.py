@@ -31,6 +31,16 @@ class GaussianRasterizationSettings(NamedTuple):
 
 
 _cap_hint = {}          # device -> instances-per-Gaussian estimate that was enough last time
+INT32_MAX = 2 ** 31 - 1
+
+
+def views_per_chunk(N, H, W, budget_bytes=2 << 30, per_gaussian=None, device_index=0, cap=128):
+    """How many views one RenderBatch may take so that its workspace stays within `budget_bytes`
+    (planner candidates and the post-processing re-render come in chunks of this many views).  The
+    per-pair part of the workspace is 140 B, an instance costs 20 B (csrc/ags_common.cuh)."""
+    per = per_gaussian if per_gaussian is not None else _cap_hint.get(device_index, 4.0)
+    per_view = 140 * max(N, 1) + 20 * per * max(N, 1) + 8 * H * W + 4096
+    return int(max(1, min(cap, budget_bytes // per_view, (INT32_MAX - 1) // max(N, 1))))
 
 
 def _f32c(t):
@@ -83,7 +93,7 @@ class RenderBatch:
         if inst_cap is None:
             per = _cap_hint.get(dev.index, 4.0)
             inst_cap = int(per * N * B) + 4096
-        self.inst_cap = int(inst_cap)
+        self.inst_cap = min(int(inst_cap), INT32_MAX)          # AgsRenderArgs.inst_cap is an int32
         self.workspace = None
         self.pool = pool                 # optional callable(nbytes) -> uint8 tensor with >= nbytes (reused across calls)
         self._alloc(lib)
@@ -130,7 +140,7 @@ class RenderBatch:
             st = self.stats.tolist()
             need = st[L.STAT_INSTANCES]
             if st[L.STAT_OVERFLOW]:
-                self.inst_cap = int(need * 1.25) + 4096
+                self.inst_cap = min(int(need * 1.25) + 4096, INT32_MAX)
                 self._alloc(lib)
                 L.check(lib.ags_render_forward(C.byref(self._args())), "ags_render_forward")
             if self.N * self.B > 0:
@@ -183,7 +193,8 @@ class _Rasterize(torch.autograd.Function):
         un = lambda t: None if t is None else t.unsqueeze(0)
         dm, ds, dr, do, dc, dm2 = rb.backward(un(d_rgb), un(d_normal), un(d_depth), un(d_opacity),
                                               un(d_conf), want_means2D=True)
-        ctx.rb = None
+        # ctx.rb stays: the backward consumed-and-cleared the gradient records (clear_records=1), so a
+        # second backward over the same graph (retain_graph=True) starts from zero again
         return dm, dm2[0], do.reshape(ctx.opac_shape), None, dc, ds, dr, None
 
 

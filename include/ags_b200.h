@@ -385,6 +385,9 @@ int ags_voxel_roi(const AgsVoxelRoiArgs* args);
 
 const char* ags_last_error(void);
 int ags_version(void);
+/* (new) number of kernels this library has launched in the calling process so far (bench.py's
+ * `gpu_launches` is the difference over the timed region; no reference counterpart) */
+unsigned long long ags_launch_count(void);
 
 #ifdef __cplusplus
 }
