@@ -67,3 +67,42 @@ def test_c_oracle_runs_the_restated_train_loop(golden):
                         rasterize_fn=c_ref.rasterize)
     for k in ["means", "opacities", "harmonics"]:
         torch.testing.assert_close(state[k], g["end"][k], rtol=2e-4, atol=2e-5)
+
+
+def test_flip_aware_report_accepts_fp32_noise_and_rejects_confined_bugs():
+    """tests/parity_util.py (the GPU parity criterion) on the CPU: the float32 C oracle must pass against
+    the float64 arbiter with shifted thresholds, and an error confined to 0.1 % of the elements -- which
+    the round-1 criterion let through with any magnitude -- must fail."""
+    from parity_util import flip_report, int_flip_report, SHIFT
+    from active_gs_b200 import synthetic as syn
+    box = (6.0, 4.5, 2.7)
+    state = syn.make_room_scene(20000, box=box, seed=1002)
+    state["scales"][:, :2] += 1.2
+    H, W = 120, 160
+    ext, K = syn.make_cameras(1, box=box, H=H, W=W, seed=2002)
+    means, harm, opac, conf, scales, rots = hr.activate(
+        state["means"], state["scales"], state["rotations"], state["opacities"], state["harmonics"],
+        state["view_scores"], state["view_supports"], state["view_means"])
+    A = (means, harm[:, 0, :], opac, conf, scales, rots)
+    fovs, view, proj, _ = hr.camera_setup(ext, K, (0.001, 10.0))
+    tan = (0.5 * fovs[0]).tan()
+    g = torch.Generator().manual_seed(0)
+    ups = [torch.randn(c, H, W, generator=g) for c in (3, 3, 1, 1, 1)]
+    run = lambda **kw: c_ref.forward_backward(A, view[0], proj[0], tan, (H, W), ups, require_importance=True, **kw)
+    (o0, g0), (op, gp), (om, gm) = run(), run(threshold_shift=SHIFT), run(threshold_shift=-SHIFT)
+    o32, g32 = run(dtype=torch.float32)
+    for k in range(6):
+        assert flip_report(f"out{k}", o32[k], o0[k], op[k], om[k], max_flip_frac=0.10 if k == 5 else 0.03)
+    assert int_flip_report("count", o32[6], o0[6], op[6], om[6], max_flip_frac=0.10)
+    assert int_flip_report("radii", o32[7], o0[7], op[7], om[7])
+    for k in range(6):
+        assert flip_report(f"grad{k}", g32[k], g0[k], gp[k], gm[k])
+    # a bug confined to 0.1 % of the pixels / Gaussians, 1 % of the scale: must be rejected
+    bad = o32[0].clone().reshape(-1)
+    idx = torch.randperm(bad.numel(), generator=g)[:bad.numel() // 1000]
+    bad[idx] += 0.01 * float(o0[0].abs().max())
+    assert not flip_report("rgb+bug", bad.reshape(o32[0].shape), o0[0], op[0], om[0], quiet=True)
+    badg = g32[0].clone().reshape(-1)
+    idx = torch.randperm(badg.numel(), generator=g)[:badg.numel() // 1000]
+    badg[idx] += 0.01 * float(g0[0].abs().max())
+    assert not flip_report("grad+bug", badg.reshape(g32[0].shape), g0[0], gp[0], gm[0], quiet=True)

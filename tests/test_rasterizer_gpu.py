@@ -1,18 +1,20 @@
 """GPU parity: libags_b200.so (through the C ABI / drop-in module) vs the oracle.
 
-Tolerance (BASELINE.json north_star): 1e-4 relative, fp32.  'Relative' is measured against the
-tensor's scale (max |ref|): err = max|got-ref| / max|ref|, and as a 2-norm ratio.  The compositing
-rule has hard thresholds (alpha<1/255, T<1e-4, power>0, integer radius) where two fp32 evaluation
-orders can legitimately fall on different sides, so a small fraction of outlier elements is
-tolerated for images; the norm-wise error must still pass.
+Tolerance (BASELINE.json north_star): 1e-4 relative, fp32, flip-aware (tests/parity_util.py): the
+float64 C oracle (cross-checked against the torch-autograd oracle to 1e-12 in tests/test_oracle_c.py) is
+the arbiter; it is also evaluated with every hard threshold of the specification shifted by +-SHIFT,
+which marks the elements whose value hinges on a comparison fp32 rounding can flip.  Nothing is removed
+from the error norm except those provably flip-prone elements, and there the deviation is bounded by
+what the shift itself does.  The float32 C oracle gives the fp32 evaluation-noise floor.
 """
 import math
 import numpy as np
 import pytest
 import torch
 
-from oracle import rasterizer_ref as rr, host_ref as hr
+from oracle import c_ref, rasterizer_ref as rr, host_ref as hr
 from active_gs_b200 import synthetic as syn
+from parity_util import flip_report, int_flip_report, SHIFT
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -24,24 +26,6 @@ def _dev():
     return torch.device("cuda:0")
 
 
-def report(name, got, ref, tol=TOL, outlier_frac=0.0):
-    got = got.detach().double().cpu()
-    ref = ref.detach().double().cpu()
-    assert got.shape == ref.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
-    scale = max(ref.abs().max().item(), 1e-12)
-    diff = (got - ref).abs()
-    emax = diff.max().item() / scale if diff.numel() else 0.0
-    outl = diff > tol * scale
-    frac = outl.double().mean().item() if diff.numel() else 0.0
-    # threshold flips (alpha<1/255, T<1e-4 ...) put a whole pixel / Gaussian on the other side of a
-    # discontinuity: the norm-wise error is taken over the non-outlier elements, whose share is bounded
-    keep = ~outl if outlier_frac > 0 else torch.ones_like(outl)
-    l2 = ((got - ref) * keep).norm().item() / max(ref.norm().item(), 1e-12)
-    ok = (l2 <= tol) and (frac <= outlier_frac if outlier_frac > 0 else emax <= tol)
-    print(f"  {name:12s} max_rel={emax:.3e} l2_rel={l2:.3e} frac_out={frac:.2e} {'ok' if ok else 'FAIL'}")
-    return ok
-
-
 def setup_case(state, ext, K, hw, dev):
     attrs = hr.activate(state["means"], state["scales"], state["rotations"], state["opacities"],
                         state["harmonics"], state["view_scores"], state["view_supports"],
@@ -51,10 +35,9 @@ def setup_case(state, ext, K, hw, dev):
 
 
 def run_both(attrs, fovs, view, proj, hw, dev, vi=0, bg=None, render_mask=None,
-             require_importance=False, front_only=False, upstream_seed=0, check_grad=True,
-             ref_dtype=torch.float32, only_ref=False):
-    """Render view `vi` with the oracle (CPU, `ref_dtype`) and the drop-in module (GPU) and return
-    outputs+grads."""
+             require_importance=False, front_only=False, upstream_seed=0, check_grad=True):
+    """Render view `vi` with the C oracle (CPU: float64, float64 at +-SHIFT, float32) and with the drop-in
+    module (GPU).  Returns (oracle dict, outputs, grads)."""
     from diff_gaussian_rasterization_2d import GaussianRasterizationSettings, GaussianRasterizer
     means, harm, opac, conf, scales, rots = attrs
     H, W = hw
@@ -62,28 +45,18 @@ def run_both(attrs, fovs, view, proj, hw, dev, vi=0, bg=None, render_mask=None,
     bg = torch.zeros(4) if bg is None else bg
     g = torch.Generator().manual_seed(upstream_seed)
     ups = [torch.randn(c, H, W, generator=g) for c in (3, 3, 1, 1, 1)]
-
-    def leafs(device, dtype=torch.float32):
-        return [t.detach().clone().to(device=device, dtype=dtype).requires_grad_(check_grad)
-                for t in (means, opac[:, None], harm[:, 0, :], scales, rots)]
-
-    # oracle
-    m, o, c, s, r = leafs("cpu", ref_dtype)
-    m2 = torch.zeros_like(m, requires_grad=check_grad)
-    ups_ref = [u.to(ref_dtype) for u in ups]
-    out_ref = rr.rasterize(m, m2, o, conf.to(ref_dtype), c, s, r, image_height=H, image_width=W,
-                           tanfovx=float(tan[0]), tanfovy=float(tan[1]), bg=bg, viewmatrix=view[vi],
-                           projmatrix=proj[vi], render_mask=render_mask, weight_thres=0.03,
-                           require_importance=require_importance, front_only=front_only)
-    grads_ref = None
-    if check_grad:
-        loss = sum((u * x).sum() for u, x in zip(ups_ref, out_ref[:5]))
-        loss.backward()
-        grads_ref = [m.grad, m2.grad, o.grad, c.grad, s.grad, r.grad]
-    if only_ref:
-        return out_ref, grads_ref
+    A = (means, harm[:, 0, :], opac, conf, scales, rots)
+    kw = dict(bg=bg, render_mask=render_mask, require_importance=require_importance, front_only=front_only)
+    U = ups if check_grad else None
+    ora = {
+        "f64": c_ref.forward_backward(A, view[vi], proj[vi], tan, hw, U, **kw),
+        "plus": c_ref.forward_backward(A, view[vi], proj[vi], tan, hw, U, threshold_shift=SHIFT, **kw),
+        "minus": c_ref.forward_backward(A, view[vi], proj[vi], tan, hw, U, threshold_shift=-SHIFT, **kw),
+        "f32": c_ref.forward_backward(A, view[vi], proj[vi], tan, hw, U, dtype=torch.float32, **kw),
+    }
     # CUDA through the reference-facing module
-    m, o, c, s, r = leafs(dev)
+    m, o, c, s, r = [t.detach().clone().to(device=dev, dtype=torch.float32).requires_grad_(check_grad)
+                     for t in (means, opac[:, None], harm[:, 0, :], scales, rots)]
     m2 = torch.zeros_like(m, requires_grad=check_grad)
     settings = GaussianRasterizationSettings(
         image_height=H, image_width=W, tanfovx=float(tan[0]), tanfovy=float(tan[1]), bg=bg.to(dev),
@@ -99,43 +72,41 @@ def run_both(attrs, fovs, view, proj, hw, dev, vi=0, bg=None, render_mask=None,
     if check_grad:
         loss = sum((u.to(dev) * x).sum() for u, x in zip(ups, out[:5]))
         loss.backward()
-        grads = [m.grad, m2.grad, o.grad, c.grad, s.grad, r.grad]
-    return out_ref, grads_ref, out, grads
+        grads = [m.grad, m2.grad, o.grad.reshape(-1), c.grad, s.grad, r.grad]
+    return ora, out, grads
 
 
 OUT_NAMES = ["rgb", "normal", "depth", "opacity", "confidence", "importance", "count", "radii"]
 GRAD_NAMES = ["d_means3D", "d_means2D", "d_opacity", "d_colors", "d_scales", "d_rotations"]
 
 
-def l2_rel(a, b):
-    a, b = a.detach().double().cpu(), b.detach().double().cpu()
-    return (a - b).norm().item() / max(b.norm().item(), 1e-300)
-
-
-def compare_all(out_ref, grads_ref, out, grads, img_outliers=2e-3, grad_tol=TOL, grads_floor=None):
-    """grads_floor: gradients of the SAME semantics evaluated in fp32 by the oracle; when given,
-    `grads_ref` is the fp64 arbiter and a gradient passes if its error vs the arbiter is within
-    max(tol, 2 x the fp32 oracle's own error) -- i.e. no worse than fp32 evaluation noise."""
+def compare_all(ora, out, grads):
+    (o0, g0), (op, gp), (om, gm), (o32, g32) = ora["f64"], ora["plus"], ora["minus"], ora["f32"]
     ok = True
-    for k in range(5):
-        ok &= report(OUT_NAMES[k], out[k], out_ref[k], outlier_frac=img_outliers)
-    ok &= report("importance", out[5], out_ref[5], tol=1e-3, outlier_frac=5e-3)
-    cnt_diff = (out[6].cpu() - out_ref[6]).abs()
-    print(f"  count        max_abs_diff={int(cnt_diff.max()) if cnt_diff.numel() else 0} "
-          f"frac_diff={(cnt_diff > 0).float().mean().item() if cnt_diff.numel() else 0:.2e}")
-    ok &= (cnt_diff > 0).float().mean().item() <= 5e-3 if cnt_diff.numel() else True
-    rad_diff = (out[7].cpu() - out_ref[7]).abs()
-    print(f"  radii        frac_diff={(rad_diff > 0).float().mean().item() if rad_diff.numel() else 0:.2e}")
-    ok &= (rad_diff > 0).float().mean().item() <= 1e-3 if rad_diff.numel() else True
+    # importance / count: a Gaussian's value moves if ANY of its pixels sits at the weight threshold, so
+    # the flip-prone share is per-Gaussian high for large splats (bounded at 10 %)
+    for k in range(6):
+        ok &= flip_report(OUT_NAMES[k], out[k], o0[k], op[k], om[k], floor=o32[k], max_flip_frac=0.10 if k == 5 else 0.03)
+    ok &= int_flip_report("count", out[6], o0[6], op[6], om[6], max_flip_frac=0.10)
+    ok &= int_flip_report("radii", out[7], o0[7], op[7], om[7])
     if grads is not None:
-        for k, (n, a, b) in enumerate(zip(GRAD_NAMES, grads, grads_ref)):
-            tol = grad_tol
-            if grads_floor is not None:
-                fl = l2_rel(grads_floor[k], b)
-                tol = max(grad_tol, 2.0 * fl)
-                print(f"  {n:12s} fp32-oracle-vs-fp64 l2_rel={fl:.3e} -> tol {tol:.2e}")
-            ok &= report(n, a, b, tol=tol, outlier_frac=2e-3)
+        for k, n in enumerate(GRAD_NAMES):
+            ok &= flip_report(n, grads[k], g0[k], gp[k], gm[k], floor=g32[k])
     return ok
+
+
+def test_torch_oracle_agrees_with_c_oracle_on_the_gpu_box():
+    """the arbiter used here (C, float64) against the autograd oracle, on the box the parity runs on"""
+    state, ext, K = syn.make_c1_scene()
+    attrs, fovs, view, proj, _ = setup_case(state, ext, K, (64, 64), None)
+    means, harm, opac, conf, scales, rots = [t.double() for t in attrs]
+    tan = (0.5 * fovs[0]).tan()
+    ref = rr.rasterize(means, torch.zeros_like(means), opac[:, None], conf, harm[:, 0, :], scales, rots,
+                       image_height=64, image_width=64, tanfovx=float(tan[0]), tanfovy=float(tan[1]),
+                       bg=torch.zeros(4).double(), viewmatrix=view[0].double(), projmatrix=proj[0].double())
+    got, _ = c_ref.forward_backward((means, harm[:, 0, :], opac, conf, scales, rots), view[0], proj[0], tan, (64, 64))
+    for k in range(5):
+        assert float((got[k] - ref[k]).abs().max()) < 1e-10
 
 
 def test_c1_forward_backward():
@@ -157,11 +128,7 @@ def test_room_cut_20k_160x120():
     ext, K = syn.make_cameras(2, box=box, H=120, W=160, seed=2002)
     attrs, fovs, view, proj, _ = setup_case(state, ext, K, (120, 160), dev)
     for vi in range(2):
-        # fp64 oracle = arbiter; fp32 oracle gives the evaluation-noise floor of the gradients
-        out64, g64, out, g = run_both(attrs, fovs, view, proj, (120, 160), dev, vi=vi,
-                                      ref_dtype=torch.float64)
-        _, g32 = run_both(attrs, fovs, view, proj, (120, 160), dev, vi=vi, only_ref=True)
-        assert compare_all(out64, g64, out, g, grads_floor=g32)
+        assert compare_all(*run_both(attrs, fovs, view, proj, (120, 160), dev, vi=vi))
 
 
 def test_ragged_image_and_masked_counts():
