@@ -14,6 +14,7 @@
 // per-Gaussian partial gradients across the warp through a shared-memory transposition (36
 // instructions instead of 150 for a plain shuffle tree) and issues one 15-lane vector RED per
 // (warp, Gaussian) into a 64 B gradient record.
+#include <stdlib.h>
 #include "ags_common.cuh"
 
 namespace {
@@ -94,8 +95,8 @@ __device__ __forceinline__ bool bbox_hits(const float4 bb, const WarpBlock& b) {
 #ifndef AGS_RANKSORT
 #define AGS_RANKSORT 1        // single-batch tiles: rank sort fused with the staging (0 = bitonic prologue)
 #endif
-#ifndef AGS_BWD_PX2
-#define AGS_BWD_PX2 0         // 1 = experimental two-pixels-per-lane backward (composite_bwd_px2_kernel)
+#ifndef AGS_BWD_PX_DEFAULT
+#define AGS_BWD_PX_DEFAULT 1  // pixels per lane of the backward (composite_bwd_kernel<PX>)
 #endif
 #ifndef AGS_FWD_MINB
 #define AGS_FWD_MINB 6
@@ -309,155 +310,21 @@ __device__ __forceinline__ float warp_reduce15(const float (&v)[15], unsigned st
     return r;
 }
 
-__global__ void __launch_bounds__(256, AGS_BWD_MINB)
-composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
-    __shared__ SplatRec s_rec[BATCH];
-    __shared__ int s_id[BATCH];
-    __shared__ int s_max_last;
-    __shared__ __align__(16) float s_red[8][15 * RED_STRIDE];   // per-warp transposition buffer
-    const int v = blockIdx.z;
-    const int tiles_x = gridDim.x, tiles_y = gridDim.y;
-    const int tile = blockIdx.y * tiles_x + blockIdx.x;
-    const size_t gt = (size_t)v * tiles_x * tiles_y + tile;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const WarpBlock wb = warp_block(blockIdx.x, blockIdx.y, tid);
-    const int px = wb.px, py = wb.py;
-    const bool inside = (px < a.W) && (py < a.H);
-    const float pxf = (float)px, pyf = (float)py;
-    if (w.counters[0] > a.inst_cap) return;
-    const int n = w.tile_count[gt];
-    if (n == 0) return;
-    const int off = w.tile_offset[gt];
-    const size_t vN = (size_t)v * a.N;
-    const size_t P = (size_t)a.H * a.W;
-    const size_t pix = (size_t)py * a.W + px;
-    const size_t vp = (size_t)v * P + pix;
-
-    // per-pixel upstream gradients and the "remaining" sum
-    float gC0 = 0.f, gC1 = 0.f, gC2 = 0.f, gN0 = 0.f, gN1 = 0.f, gN2 = 0.f, gD = 0.f, gCf = 0.f;
-    float rem = 0.f;
-    int my_last = 0;
-    if (inside) {
-        my_last = w.n_contrib[vp];
-        const float Tf = w.final_T[vp];
-        const float A = 1.f - Tf;
-        if (gr.d_rgb) { const float* p = gr.d_rgb + (size_t)v * 3 * P + pix; gC0 = p[0]; gC1 = p[P]; gC2 = p[2 * P]; }
-        if (gr.d_normal) { const float* p = gr.d_normal + (size_t)v * 3 * P + pix; gN0 = p[0]; gN1 = p[P]; gN2 = p[2 * P]; }
-        const float gdep = gr.d_depth ? gr.d_depth[vp] : 0.f;
-        float gA = gr.d_opacity ? gr.d_opacity[vp] : 0.f;
-        if (gr.d_confidence) gCf = gr.d_confidence[vp];
-        const float depth_out = a.out_depth[vp];
-        if (A > 0.f) { gD = gdep / A; gA -= gdep * depth_out / A; }
-        const float bg0 = __ldg(a.bg), bg1 = __ldg(a.bg + 1), bg2 = __ldg(a.bg + 2);
-        const float* c = a.out_rgb + (size_t)v * 3 * P + pix;
-        const float* nn = a.out_normal + (size_t)v * 3 * P + pix;
-        const float bgdot = gC0 * bg0 + gC1 * bg1 + gC2 * bg2;
-        const float S_all = gC0 * (c[0] - Tf * bg0) + gC1 * (c[P] - Tf * bg1) + gC2 * (c[2 * P] - Tf * bg2)
-                          + gN0 * nn[0] + gN1 * nn[P] + gN2 * nn[2 * P]
-                          + gD * (depth_out * A) + gCf * a.out_confidence[vp];
-        rem = S_all + Tf * (bgdot - gA);
-    }
-    if (tid == 0) s_max_last = 0;
-    __syncthreads();
-    if (my_last > 0) atomicMax(&s_max_last, my_last);
-    __syncthreads();
-    const int n_eff = min(n, s_max_last);
-
-    const int warp_last = __reduce_max_sync(0xffffffffu, my_last);
-    // loop-invariant shared-space addresses of this lane's slots in the warp's transposition buffer
-    const unsigned red_st = (unsigned)__cvta_generic_to_shared(&s_red[tid >> 5][lane]);
-    const unsigned red_ld = (unsigned)__cvta_generic_to_shared(
-        &s_red[tid >> 5][(lane >> 1) * RED_STRIDE + (lane & 1) * 16]);
-    float* const dsplat_lane = w.dsplat + vN * 16 + (lane >> 1);
-    float T = 1.f;
-    for (int base = 0; base < n_eff; base += BATCH) {
-        __syncthreads();
-        const int j = base + tid;
-        if (j < n_eff) {
-            const int id = w.inst_sorted[off + j];
-            const size_t idx = vN + id;
-            const float4 g0 = ldg4(w.geom0 + idx), g1 = ldg4(w.geom1 + idx);
-            s_id[tid] = id;
-            SplatRec& r = s_rec[tid];
-            r.g0 = make_float4(g0.x, g0.y, g0.z * AGS_LOG2E, g0.w * AGS_LOG2E);   // conic * log2(e)
-            r.g1 = make_float4(g1.x * AGS_LOG2E, g1.y, g1.z, g1.w);
-            r.f0 = ldg4(w.feat0 + idx);
-            r.f1 = ldg4(w.feat1 + idx);
-            r.bb = splat_bbox(g0, g1);
-        }
-        __syncthreads();
-        const int cnt = min(BATCH, min(n_eff, warp_last) - base);   // nothing beyond the warp's last contributor
-        for (int c = 0; c < cnt; c += 32) {
-            const int jj = c + lane;
-            unsigned mask = __ballot_sync(0xffffffffu, jj < cnt && bbox_hits(s_rec[jj].bb, wb));
-            while (mask) {
-                const int k = c + __ffs(mask) - 1;
-                mask &= mask - 1;
-                const SplatRec& rec = s_rec[k];
-                const float4 g0 = rec.g0, g1 = rec.g1;
-                const SplatEval e = eval_alpha(g0, g1, pxf, pyf);
-                const bool active = (base + k < my_last) && !e.skip;
-                if (__ballot_sync(0xffffffffu, active) == 0u) continue;
-                // branch-free: an inactive lane runs the same arithmetic with alpha = G = 0, which
-                // leaves its T / rem untouched and makes all fifteen partials exactly zero
-                const float4 f0 = rec.f0, f1 = rec.f1;
-                const float alpha = active ? e.alpha : 0.f;
-                const float G = active ? e.G : 0.f;
-                const float wgt = alpha * T;
-                const float one_m = 1.f - alpha;
-                const float dpix = f0.w - g1.z * e.dx - g1.w * e.dy;
-                const float sdot = gC0 * f0.x + gC1 * f0.y + gC2 * f0.z + gN0 * f1.x + gN1 * f1.y + gN2 * f1.z
-                                 + gD * dpix + gCf * f1.w;
-                rem -= wgt * sdot;
-                const float dalpha = T * sdot - rem * rcp_approx(one_m);       // one_m >= 0.01
-                T *= one_m;
-                // alpha = min(0.99, o*G): clamped -> no gradient.  dpower is w.r.t. the NATURAL exponent;
-                // the staged conic is scaled by log2(e), hence the 1/log2(e) on the position terms.
-                const bool unclamped = (g1.y * G <= AGS_ALPHA_MAX);
-                const float dpower = unclamped ? alpha * dalpha : 0.f;
-                const float dps = dpower * (1.f / AGS_LOG2E);
-                const float wgD = wgt * gD;
-                float val[15];
-                val[0] = dps * (-g0.z * e.dx - g0.w * e.dy) - wgD * g1.z;       // d x
-                val[1] = dps * (-g1.x * e.dy - g0.w * e.dx) - wgD * g1.w;       // d y
-                val[2] = -0.5f * e.dx * e.dx * dpower;                          // d conic a
-                val[3] = -e.dx * e.dy * dpower;                                 // d conic b
-                val[4] = -0.5f * e.dy * e.dy * dpower;                          // d conic c
-                val[5] = unclamped ? G * dalpha : 0.f;                          // d opacity
-                val[6] = wgt * gC0; val[7] = wgt * gC1; val[8] = wgt * gC2;     // d rgb
-                val[9] = wgt * gN0; val[10] = wgt * gN1; val[11] = wgt * gN2;   // d normal
-                val[12] = wgD;                                                  // d depth
-                val[13] = -wgD * e.dx;                                          // d slope x
-                val[14] = -wgD * e.dy;                                          // d slope y
-                const float r = warp_reduce15(val, red_st, red_ld, lane);
-                if ((lane & 1) == 0 && lane < 30) atomicAdd(dsplat_lane + (size_t)s_id[k] * 16, r);
-            }
-        }
-    }
-}
-
-#if AGS_BWD_PX2
-// K5, two pixels per lane (EXPERIMENT, off by default): the backward is limited
-// by instruction issue AND by the shared-memory data pipe, and 31 of the ~36 shared-memory wavefronts per
-// (warp, splat) pair are the 15-value warp reduction.  Here a CTA of 128 threads owns the 16x16 tile,
-// every warp an 8x8 pixel block, every lane the pixels (x, y) and (x, y + 4): the two pixels' partials are
-// added in registers before ONE reduction, so a splat costs one reduction per 8x8 block instead of one
-// per 8x4 block (-30 % pairs for a 12-pixel splat).  Same arithmetic per pixel as composite_bwd_kernel.
-struct PixState {
+// Per-pixel state of the backward walk.
+struct BwdPix {
     float gC0, gC1, gC2, gN0, gN1, gN2, gD, gCf, rem, T, pyf;
-    int my_last;
+    int last;
 };
 
-__device__ __forceinline__ void px2_load_pixel(PixState& s, const AgsRenderArgs& a, const AgsRenderGradArgs& gr,
+__device__ __forceinline__ void bwd_load_pixel(BwdPix& s, const AgsRenderArgs& a, const AgsRenderGradArgs& gr,
                                                const AgsWorkspace& w, int v, int px, int py) {
     s.gC0 = s.gC1 = s.gC2 = s.gN0 = s.gN1 = s.gN2 = s.gD = s.gCf = 0.f;
-    s.rem = 0.f; s.T = 1.f; s.my_last = 0; s.pyf = (float)py;
+    s.rem = 0.f; s.T = 1.f; s.last = 0; s.pyf = (float)py;
     if (px >= a.W || py >= a.H) return;
     const size_t P = (size_t)a.H * a.W;
     const size_t pix = (size_t)py * a.W + px;
     const size_t vp = (size_t)v * P + pix;
-    s.my_last = w.n_contrib[vp];
+    s.last = w.n_contrib[vp];
     const float Tf = w.final_T[vp];
     const float A = 1.f - Tf;
     if (gr.d_rgb) { const float* p = gr.d_rgb + (size_t)v * 3 * P + pix; s.gC0 = p[0]; s.gC1 = p[P]; s.gC2 = p[2 * P]; }
@@ -477,43 +344,60 @@ __device__ __forceinline__ void px2_load_pixel(PixState& s, const AgsRenderArgs&
     s.rem = S_all + Tf * (bgdot - gA);
 }
 
-// one pixel's contribution to the 15 partials of the splat (added into val); branch-free like the
-// one-pixel kernel: an inactive pixel runs with alpha = G = 0
-__device__ __forceinline__ void px2_accumulate(float (&val)[15], PixState& s, const float4 g0, const float4 g1,
-                                               const float4 f0, const float4 f1, const SplatEval& e, bool active) {
-    const float alpha = active ? e.alpha : 0.f;
-    const float G = active ? e.G : 0.f;
+// One pixel's contribution to the 15 per-splat partials.  Branch-free: an inactive pixel runs the same
+// arithmetic with alpha = G = 0, which leaves its T / rem untouched and adds exact zeros.
+// The partials are the RAW MOMENTS of the pixel gradients (the chain rule through the conic, the centre
+// and the plane slopes is linear in them and is applied once per splat in project_bwd):
+//   [0] sum dpower*dx   [1] sum dpower*dy   [2] sum dpower*dx^2   [3] sum dpower*dx*dy   [4] sum dpower*dy^2
+//   [5] sum G*dalpha (d opacity)   [6..8] sum w*gC   [9..11] sum w*gN   [12] sum w*gD   [13] sum w*gD*dx
+//   [14] sum w*gD*dy        (dpower = dL/d(natural exponent), w = alpha*T, dx = x_splat - x_pixel)
+template <bool FIRST, bool HAS_CONF>
+__device__ __forceinline__ void bwd_accumulate(float (&val)[15], BwdPix& s, const float4 g1, const float4 f0,
+                                               const float4 f1, float dx, float dy, float e_alpha, float e_G,
+                                               bool active) {
+    const float alpha = active ? e_alpha : 0.f;
+    const float G = active ? e_G : 0.f;
     const float wgt = alpha * s.T;
     const float one_m = 1.f - alpha;
-    const float dpix = f0.w - g1.z * e.dx - g1.w * e.dy;
-    const float sdot = s.gC0 * f0.x + s.gC1 * f0.y + s.gC2 * f0.z + s.gN0 * f1.x + s.gN1 * f1.y + s.gN2 * f1.z
-                     + s.gD * dpix + s.gCf * f1.w;
+    const float dpix = f0.w - g1.z * dx - g1.w * dy;
+    float sdot = s.gC0 * f0.x + s.gC1 * f0.y + s.gC2 * f0.z + s.gN0 * f1.x + s.gN1 * f1.y + s.gN2 * f1.z + s.gD * dpix;
+    if (HAS_CONF) sdot += s.gCf * f1.w;
     s.rem -= wgt * sdot;
-    const float dalpha = s.T * sdot - s.rem * rcp_approx(one_m);
+    const float dalpha = s.T * sdot - s.rem * rcp_approx(one_m);         // one_m >= 0.01
     s.T *= one_m;
+    // alpha = min(0.99, o*G): clamped -> no gradient
     const bool unclamped = (g1.y * G <= AGS_ALPHA_MAX);
     const float dpower = unclamped ? alpha * dalpha : 0.f;
-    const float dps = dpower * (1.f / AGS_LOG2E);
+    const float dop = unclamped ? G * dalpha : 0.f;
     const float wgD = wgt * s.gD;
-    val[0] += dps * (-g0.z * e.dx - g0.w * e.dy) - wgD * g1.z;
-    val[1] += dps * (-g1.x * e.dy - g0.w * e.dx) - wgD * g1.w;
-    val[2] += -0.5f * e.dx * e.dx * dpower;
-    val[3] += -e.dx * e.dy * dpower;
-    val[4] += -0.5f * e.dy * e.dy * dpower;
-    val[5] += unclamped ? G * dalpha : 0.f;
-    val[6] += wgt * s.gC0; val[7] += wgt * s.gC1; val[8] += wgt * s.gC2;
-    val[9] += wgt * s.gN0; val[10] += wgt * s.gN1; val[11] += wgt * s.gN2;
-    val[12] += wgD;
-    val[13] += -wgD * e.dx;
-    val[14] += -wgD * e.dy;
+    const float pdx = dpower * dx, pdy = dpower * dy;
+    if (FIRST) {
+        val[0] = pdx; val[1] = pdy; val[2] = pdx * dx; val[3] = pdx * dy; val[4] = pdy * dy; val[5] = dop;
+        val[6] = wgt * s.gC0; val[7] = wgt * s.gC1; val[8] = wgt * s.gC2;
+        val[9] = wgt * s.gN0; val[10] = wgt * s.gN1; val[11] = wgt * s.gN2;
+        val[12] = wgD; val[13] = wgD * dx; val[14] = wgD * dy;
+    } else {
+        val[0] += pdx; val[1] += pdy; val[2] += pdx * dx; val[3] += pdx * dy; val[4] += pdy * dy; val[5] += dop;
+        val[6] += wgt * s.gC0; val[7] += wgt * s.gC1; val[8] += wgt * s.gC2;
+        val[9] += wgt * s.gN0; val[10] += wgt * s.gN1; val[11] += wgt * s.gN2;
+        val[12] += wgD; val[13] += wgD * dx; val[14] += wgD * dy;
+    }
 }
 
-__global__ void __launch_bounds__(128, 6)
-composite_bwd_px2_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
+// K5.  CTA = one 16x16 tile of one view, 256 / PX threads: every warp owns a block of 8 x (4*PX) pixels,
+// every lane PX pixels of one column (rows y, y+4, ...).  The partials of a lane's pixels are summed in
+// registers BEFORE the cross-lane reduction, so a splat costs one reduction + one 15-lane RED per
+// (warp block, splat) -- with PX = 4 half as many as with 8x4 blocks -- and the loop control, the record
+// loads and the bounding-box test are shared by the PX pixels.  Sub-blocks of 8x4 pixels the splat's
+// cutoff box does not reach are skipped warp-uniformly.
+template <int PX, bool HAS_CONF>
+__global__ void __launch_bounds__(256 / PX, PX == 1 ? AGS_BWD_MINB : (PX == 2 ? 6 : 8))
+composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
+    constexpr int THREADS = 256 / PX, WARPS = 8 / PX;
     __shared__ SplatRec s_rec[BATCH];
     __shared__ int s_id[BATCH];
     __shared__ int s_max_last;
-    __shared__ __align__(16) float s_red[4][15 * RED_STRIDE];   // per-warp transposition buffer
+    __shared__ __align__(16) float s_red[WARPS][15 * RED_STRIDE];   // per-warp transposition buffer
     const int v = blockIdx.z;
     const int tiles_x = gridDim.x, tiles_y = gridDim.y;
     const int tile = blockIdx.y * tiles_x + blockIdx.x;
@@ -525,30 +409,33 @@ composite_bwd_px2_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) 
     if (n == 0) return;
     const int off = w.tile_offset[gt];
     const size_t vN = (size_t)v * a.N;
-    // warp block: 8x8 pixels; lane -> (x, y) and (x, y + 4)
-    const int bx = blockIdx.x * TILE + (wid & 1) * 8, by = blockIdx.y * TILE + (wid >> 1) * 8;
+    const int bx = blockIdx.x * TILE + (wid & 1) * 8, by = blockIdx.y * TILE + (wid >> 1) * 4 * PX;
     WarpBlock wb;
     wb.px = bx + (lane & 7); wb.py = by + (lane >> 3);
-    wb.x0 = (float)bx; wb.x1 = (float)(bx + 7); wb.y0 = (float)by; wb.y1 = (float)(by + 7);
+    wb.x0 = (float)bx; wb.x1 = (float)(bx + 7); wb.y0 = (float)by; wb.y1 = (float)(by + 4 * PX - 1);
     const float pxf = (float)wb.px;
-    PixState s0, s1;
-    px2_load_pixel(s0, a, gr, w, v, wb.px, wb.py);
-    px2_load_pixel(s1, a, gr, w, v, wb.px, wb.py + 4);
-    const int lane_last = max(s0.my_last, s1.my_last);
+    BwdPix s[PX];
+    int lane_last = 0;
+#pragma unroll
+    for (int j = 0; j < PX; ++j) {
+        bwd_load_pixel(s[j], a, gr, w, v, wb.px, wb.py + 4 * j);
+        lane_last = max(lane_last, s[j].last);
+    }
     if (tid == 0) s_max_last = 0;
     __syncthreads();
     if (lane_last > 0) atomicMax(&s_max_last, lane_last);
     __syncthreads();
     const int n_eff = min(n, s_max_last);
     const int warp_last = __reduce_max_sync(0xffffffffu, lane_last);
+    // loop-invariant shared-space addresses of this lane's slots in the warp's transposition buffer
     const unsigned red_st = (unsigned)__cvta_generic_to_shared(&s_red[wid][lane]);
     const unsigned red_ld = (unsigned)__cvta_generic_to_shared(&s_red[wid][(lane >> 1) * RED_STRIDE + (lane & 1) * 16]);
     float* const dsplat_lane = w.dsplat + vN * 16 + (lane >> 1);
     for (int base = 0; base < n_eff; base += BATCH) {
         __syncthreads();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {                       // 128 threads stage 256 records
-            const int t = tid + h * 128;
+        for (int h = 0; h < PX; ++h) {                       // THREADS threads stage BATCH records
+            const int t = tid + h * THREADS;
             const int j = base + t;
             if (j < n_eff) {
                 const int id = w.inst_sorted[off + j];
@@ -556,7 +443,7 @@ composite_bwd_px2_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) 
                 const float4 g0 = ldg4(w.geom0 + idx), g1 = ldg4(w.geom1 + idx);
                 s_id[t] = id;
                 SplatRec& r = s_rec[t];
-                r.g0 = make_float4(g0.x, g0.y, g0.z * AGS_LOG2E, g0.w * AGS_LOG2E);
+                r.g0 = make_float4(g0.x, g0.y, g0.z * AGS_LOG2E, g0.w * AGS_LOG2E);   // conic * log2(e)
                 r.g1 = make_float4(g1.x * AGS_LOG2E, g1.y, g1.z, g1.w);
                 r.f0 = ldg4(w.feat0 + idx);
                 r.f1 = ldg4(w.feat1 + idx);
@@ -564,7 +451,7 @@ composite_bwd_px2_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) 
             }
         }
         __syncthreads();
-        const int cnt = min(BATCH, min(n_eff, warp_last) - base);
+        const int cnt = min(BATCH, min(n_eff, warp_last) - base);   // nothing beyond the warp's last contributor
         for (int c = 0; c < cnt; c += 32) {
             const int jj = c + lane;
             unsigned mask = __ballot_sync(0xffffffffu, jj < cnt && bbox_hits(s_rec[jj].bb, wb));
@@ -573,24 +460,45 @@ composite_bwd_px2_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) 
                 mask &= mask - 1;
                 const SplatRec& rec = s_rec[k];
                 const float4 g0 = rec.g0, g1 = rec.g1;
-                const SplatEval e0 = eval_alpha(g0, g1, pxf, s0.pyf);
-                const SplatEval e1 = eval_alpha(g0, g1, pxf, s1.pyf);
-                const bool act0 = (base + k < s0.my_last) && !e0.skip;
-                const bool act1 = (base + k < s1.my_last) && !e1.skip;
-                if (__ballot_sync(0xffffffffu, act0 || act1) == 0u) continue;
+                const float dx = g0.x - pxf;
+                // evaluate alpha for the lane's pixels; a sub-block (8x4) nobody is active in costs nothing more
+                float eA[PX], eG[PX], eDy[PX];
+                bool act[PX];
+                unsigned any = 0u;
+                float bz = 0.f, bw = 0.f;
+                if (PX > 1) { const float4 bb = rec.bb; bz = bb.z; bw = bb.w; }
+#pragma unroll
+                for (int j = 0; j < PX; ++j) {
+                    act[j] = false; eA[j] = 0.f; eG[j] = 0.f; eDy[j] = 0.f;
+                    if (PX > 1 && !((bz <= wb.y0 + (float)(4 * j + 3)) && (bw >= wb.y0 + (float)(4 * j)))) continue;
+                    const float dy = g0.y - s[j].pyf;
+                    const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+                    const float G = ex2_approx(power);
+                    const float alpha = fminf(AGS_ALPHA_MAX, g1.y * G);
+                    const bool skip = (power > 0.f) || (alpha < AGS_ALPHA_MIN);
+                    act[j] = (base + k < s[j].last) && !skip;
+                    eA[j] = alpha; eG[j] = G; eDy[j] = dy;
+                    if (__ballot_sync(0xffffffffu, act[j])) any |= 1u << j;
+                }
+                if (any == 0u) continue;
                 const float4 f0 = rec.f0, f1 = rec.f1;
                 float val[15];
+                if (PX == 1) {
+                    bwd_accumulate<true, HAS_CONF>(val, s[0], g1, f0, f1, dx, eDy[0], eA[0], eG[0], act[0]);
+                } else {
 #pragma unroll
-                for (int q = 0; q < 15; ++q) val[q] = 0.f;
-                px2_accumulate(val, s0, g0, g1, f0, f1, e0, act0);
-                px2_accumulate(val, s1, g0, g1, f0, f1, e1, act1);
+                    for (int q = 0; q < 15; ++q) val[q] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < PX; ++j)
+                        if (any & (1u << j))
+                            bwd_accumulate<false, HAS_CONF>(val, s[j], g1, f0, f1, dx, eDy[j], eA[j], eG[j], act[j]);
+                }
                 const float r = warp_reduce15(val, red_st, red_ld, lane);
                 if ((lane & 1) == 0 && lane < 30) atomicAdd(dsplat_lane + (size_t)s_id[k] * 16, r);
             }
         }
     }
 }
-#endif  // AGS_BWD_PX2
 
 }  // namespace
 
@@ -602,14 +510,32 @@ int ags_launch_composite_fwd(const AgsRenderArgs& a, const AgsWorkspace& w) {
     return 0;
 }
 
+// Pixels per lane of the backward (1, 2 or 4; see composite_bwd_kernel).  AGS_BWD_PX in the environment
+// overrides the default for tuning runs (read once).
+static int bwd_px() {
+    static int px = -1;
+    if (px < 0) {
+        const char* e = getenv("AGS_BWD_PX");
+        px = e ? atoi(e) : AGS_BWD_PX_DEFAULT;
+        if (px != 1 && px != 2 && px != 4) px = AGS_BWD_PX_DEFAULT;
+    }
+    return px;
+}
+
+template <int PX>
+static void launch_bwd(const AgsRenderArgs& a, const AgsRenderGradArgs& g, const AgsWorkspace& w, dim3 grid) {
+    ags_note_launch();
+    if (g.d_confidence) composite_bwd_kernel<PX, true><<<grid, 256 / PX, 0, (cudaStream_t)a.stream>>>(a, g, w);
+    else composite_bwd_kernel<PX, false><<<grid, 256 / PX, 0, (cudaStream_t)a.stream>>>(a, g, w);
+}
+
 int ags_launch_composite_bwd(const AgsRenderArgs& a, const AgsRenderGradArgs& g, const AgsWorkspace& w) {
     dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE, a.B);
-#if AGS_BWD_PX2
-    ags_note_launch(); composite_bwd_px2_kernel<<<grid, 128, 0, (cudaStream_t)a.stream>>>(a, g, w);
-#else
-    dim3 block(TILE * TILE);
-    ags_note_launch(); composite_bwd_kernel<<<grid, block, 0, (cudaStream_t)a.stream>>>(a, g, w);
-#endif
+    switch (bwd_px()) {
+        case 1: launch_bwd<1>(a, g, w, grid); break;
+        case 2: launch_bwd<2>(a, g, w, grid); break;
+        default: launch_bwd<4>(a, g, w, grid); break;
+    }
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

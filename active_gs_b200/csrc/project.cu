@@ -336,12 +336,17 @@ project_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             dr[0] = z; dr[1] = z; dr[2] = z; dr[3] = z;
         }
-        const float dxg = d0.x, dyg = d0.y, dca = d0.z, dcb = d0.w;
-        const float dcc = d1.x;
+        // the record holds the raw moments accumulated by composite_bwd (composite.cu, bwd_accumulate);
+        // the chain rule through the conic, the centre and the plane slopes is applied here, once per splat:
+        //   power = -0.5 (a dx^2 + c dy^2) - b dx dy,  dx = x_splat - x_pixel,  depth(pix) = z - sx dx - sy dy
+        const float M0 = d0.x, M1 = d0.y, M20 = d0.z, M11 = d0.w, M02 = d1.x;
         const float d_o = d1.y;
         const float dcol[3] = {d1.z, d1.w, d2.x};
         float dnv[3] = {d2.y, d2.z, d2.w};
-        const float dz = d3.x, dsx = d3.y, dsy = d3.z;
+        const float dz = d3.x, dsx = -d3.y, dsy = -d3.z;
+        const float dxg = -(p.ca * M0 + p.cb * M1) - p.sx * dz;
+        const float dyg = -(p.cc * M1 + p.cb * M0) - p.sy * dz;
+        const float dca = -0.5f * M20, dcb = -M11, dcc = -0.5f * M02;
         if (gr.d_means2D) { gr.d_means2D[idx * 3 + 0] = dxg; gr.d_means2D[idx * 3 + 1] = dyg; }
         const float* V = cam.V;
         const float* M = cam.M;
