@@ -13,7 +13,7 @@ k=d['kernels']
 print('px$px step %.1f us e2e %.1f us' % (d['ms_per_step']*1e3, d['e2e']['ms_per_step']*1e3), ' '.join('%s=%.0f' % (n[:11], k[n]['ms']*1e3) for n in k), 'launches', d['gpu_launches'])
 PY
 done
-ncu --set full --clock-control none --import-source on -k regex:"composite|project|scatter|loss|alloc|adam|tile_sort" -s 72 -c 13 -o gpurun_out/${tag}_ncu_step \
+ncu --set full --clock-control none --import-source on -k regex:"composite|project|scatter|loss|alloc|adam|tile_sort" -s 73 -c 11 -o gpurun_out/${tag}_ncu_step \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2> gpurun_out/${tag}_ncu.err
 ncu -i gpurun_out/${tag}_ncu_step.ncu-rep --page raw --csv > gpurun_out/${tag}_ncu_step_raw.csv 2>&1
 ls -la gpurun_out | tail -12
