@@ -11,7 +11,7 @@ namespace {
 
 struct AdamParams {
     float* p[AGS_ADAM_GROUPS];
-    const float* g[AGS_ADAM_GROUPS];
+    float* g[AGS_ADAM_GROUPS];
     float* m[AGS_ADAM_GROUPS];
     float* v[AGS_ADAM_GROUPS];
     long long end[AGS_ADAM_GROUPS];   // exclusive prefix of numel
@@ -21,6 +21,7 @@ struct AdamParams {
     int step;
     const int* step_dev;
     const int* skip_flag;
+    int zero_grad;
 };
 
 // grid = (blocks, groups): blockIdx.y selects the parameter group, every thread owns quads of four
@@ -43,7 +44,8 @@ adam_kernel(AdamParams P, long long total) {
     const long long n = P.end[grp] - (grp ? P.end[grp - 1] : 0);
     const float step_size = P.lr[grp] * s_c[1];
     float* __restrict__ p = P.p[grp];
-    const float* __restrict__ g = P.g[grp];
+    float* __restrict__ g = P.g[grp];
+    const bool zg = P.zero_grad != 0;
     float* __restrict__ m = P.m[grp];
     float* __restrict__ v = P.v[grp];
     const float b1 = P.b1, b2 = P.b2, eps = P.eps;
@@ -52,7 +54,7 @@ adam_kernel(AdamParams P, long long total) {
     const bool aligned = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
     if (aligned) {
         for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + q);
+            const float4 g4 = reinterpret_cast<const float4*>(g)[q];
             float4 m4 = reinterpret_cast<float4*>(m)[q], v4 = reinterpret_cast<float4*>(v)[q];
             float4 p4 = reinterpret_cast<float4*>(p)[q];
             const float* gg = &g4.x; float* mm = &m4.x; float* vv = &v4.x; float* pp = &p4.x;
@@ -65,6 +67,7 @@ adam_kernel(AdamParams P, long long total) {
             reinterpret_cast<float4*>(m)[q] = m4;
             reinterpret_cast<float4*>(v)[q] = v4;
             reinterpret_cast<float4*>(p)[q] = p4;
+            if (zg) reinterpret_cast<float4*>(g)[q] = make_float4(0.f, 0.f, 0.f, 0.f);   // consumed: ready for the next backward
         }
     }
     const long long tail_from = aligned ? (nq << 2) : 0;
@@ -74,6 +77,7 @@ adam_kernel(AdamParams P, long long total) {
         const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
         m[i] = mi; v[i] = vi;
         p[i] -= step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
+        if (zg) g[i] = 0.f;
     }
 }
 
@@ -97,7 +101,7 @@ extern "C" int ags_adam_step(const AgsAdamArgs* a) {
             total += a->numel[k];
         }
         P.p[k] = k < a->num_groups ? a->param[k] : nullptr;
-        P.g[k] = k < a->num_groups ? a->grad[k] : nullptr;
+        P.g[k] = k < a->num_groups ? const_cast<float*>(a->grad[k]) : nullptr;
         P.m[k] = k < a->num_groups ? a->exp_avg[k] : nullptr;
         P.v[k] = k < a->num_groups ? a->exp_avg_sq[k] : nullptr;
         P.lr[k] = k < a->num_groups ? a->lr[k] : 0.f;
@@ -106,6 +110,7 @@ extern "C" int ags_adam_step(const AgsAdamArgs* a) {
     P.groups = a->num_groups;
     P.b1 = a->beta1; P.b2 = a->beta2; P.eps = a->eps;
     P.step = a->step; P.step_dev = a->step_dev; P.skip_flag = a->skip_flag;
+    P.zero_grad = a->zero_grad;
     AGS_CHECK_ARG(a->step_dev != nullptr || a->step >= 1, "step must be >= 1");
     if (total == 0) return 0;
     cudaStream_t st = (cudaStream_t)a->stream;

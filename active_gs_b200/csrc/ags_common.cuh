@@ -16,7 +16,7 @@
 #define AGS_T_EPS 1e-4f
 #define AGS_SLOPE_COS_MIN 0.1f
 // tiles with at most this many instances are depth-sorted inside composite_fwd's prologue (keys alias
-// the 20 KB staging buffer); larger tiles go through tile_sort_kernel first
+// the 20 KB staging buffer); larger tiles are chunk-sorted and merged by the same CTA (sort_oversize_tile)
 #define AGS_FUSED_SORT_MAX 2048
 
 // ------------------------------------------------------------------------------------------------
@@ -33,7 +33,7 @@ struct AgsWorkspace {
     int32_t* tile_count;   // (B*tiles)
     int32_t* tile_offset;  // (B*tiles)
     int32_t* tile_fill;    // (B*tiles)
-    int32_t* counters;     // (8) [0] = instance allocator, [1] = visible pairs, [2] = tiles above AGS_FUSED_SORT_MAX
+    int32_t* counters;     // (8) [0] = instance allocator, [1] = visible pairs, [2] = unused
     uint64_t* inst_key;    // (inst_cap) depth_bits<<32 | gaussian id, grouped per tile
     uint64_t* inst_key_alt;// (inst_cap) ping-pong buffer for oversize tiles
     int32_t* inst_sorted;  // (inst_cap) gaussian ids, front-to-back per tile

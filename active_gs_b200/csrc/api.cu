@@ -25,6 +25,50 @@ extern "C" size_t ags_scratch_bytes(int32_t N, int32_t B, int32_t H, int32_t W, 
     return ags_carve(nullptr, N, B, H, W, inst_cap).total;
 }
 
+// One launch zeroes everything the forward accumulates into: the per-tile tables + device counters (contiguous
+// in the workspace), the statistics and -- when present -- the importance / count outputs.
+__global__ void __launch_bounds__(256)
+clear_kernel(int4* tiles, size_t tile_quads, int32_t* stats, int4* imp, int4* cnt, size_t bn_quads, int bn_tail,
+             int32_t* imp_tail, int32_t* cnt_tail) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int4 z = make_int4(0, 0, 0, 0);
+    for (size_t i = t0; i < tile_quads; i += stride) tiles[i] = z;
+    if (t0 < AGS_NUM_STATS) stats[t0] = 0;
+    if (imp) for (size_t i = t0; i < bn_quads; i += stride) imp[i] = z;
+    if (cnt) for (size_t i = t0; i < bn_quads; i += stride) cnt[i] = z;
+    if ((int)t0 < bn_tail) {
+        if (imp_tail) imp_tail[t0] = 0;
+        if (cnt_tail) cnt_tail[t0] = 0;
+    }
+}
+
+static int launch_clear(const AgsRenderArgs* a, const AgsWorkspace& w) {
+    cudaStream_t st = (cudaStream_t)a->stream;
+    const size_t zero_bytes = (char*)w.inst_key - (char*)w.tile_count;        // multiple of 256
+    const size_t bn = a->N > 0 ? (size_t)a->B * a->N : 0;
+    const bool aligned = (((uintptr_t)a->importance | (uintptr_t)a->count) & 15) == 0;
+    const size_t quads = aligned ? bn / 4 : 0;
+    const int tail = (int)(bn - quads * 4);
+    if (!aligned && bn) {      // unaligned caller buffers (never from torch): plain memsets
+        if (a->importance) AGS_CHECK_CUDA(cudaMemsetAsync(a->importance, 0, bn * 4, st));
+        if (a->count) AGS_CHECK_CUDA(cudaMemsetAsync(a->count, 0, bn * 4, st));
+    }
+    size_t work = zero_bytes / 16;
+    if ((a->importance || a->count) && quads > work) work = quads;
+    long long blocks = (long long)((work + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    ags_note_launch();
+    clear_kernel<<<(int)blocks, 256, 0, st>>>((int4*)w.tile_count, zero_bytes / 16, a->stats,
+                                              aligned ? (int4*)a->importance : nullptr, aligned ? (int4*)a->count : nullptr, quads,
+                                              aligned ? tail : 0,
+                                              (aligned && a->importance) ? (int32_t*)a->importance + quads * 4 : nullptr,
+                                              (aligned && a->count) ? a->count + quads * 4 : nullptr);
+    AGS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static int check_render_args(const AgsRenderArgs* a) {
     AGS_CHECK_ARG(a != nullptr, "args is NULL");
     AGS_CHECK_ARG(a->N >= 0 && a->B > 0 && a->H > 0 && a->W > 0, "bad sizes N=%d B=%d H=%d W=%d", a->N, a->B, a->H, a->W);
@@ -52,16 +96,10 @@ static int check_render_args(const AgsRenderArgs* a) {
 static int render_forward_impl(const AgsRenderArgs* a, bool for_backward) {
     int rc = check_render_args(a);
     if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)a->stream;
     AgsWorkspace w = ags_carve(a->workspace, a->N, a->B, a->H, a->W, a->inst_cap);
-    // tile_count, tile_offset, tile_fill and the counters are contiguous in the workspace
-    const size_t zero_bytes = (char*)w.inst_key - (char*)w.tile_count;
-    AGS_CHECK_CUDA(cudaMemsetAsync(w.tile_count, 0, zero_bytes, st));
-    AGS_CHECK_CUDA(cudaMemsetAsync(a->stats, 0, AGS_NUM_STATS * sizeof(int32_t), st));
-    if (a->N > 0) {   // importance / count are all-zero unless config[3]; optional outputs
-        if (a->importance) AGS_CHECK_CUDA(cudaMemsetAsync(a->importance, 0, (size_t)a->B * a->N * 4, st));
-        if (a->count) AGS_CHECK_CUDA(cudaMemsetAsync(a->count, 0, (size_t)a->B * a->N * 4, st));
-    }
+    // tile_count, tile_offset, tile_fill and the counters are contiguous in the workspace; importance /
+    // count are all-zero unless config[3] (optional outputs)
+    if ((rc = launch_clear(a, w))) return rc;
     if ((rc = ags_launch_project_fwd(*a, w, for_backward))) return rc;
     if ((rc = ags_launch_binning(*a, w))) return rc;
     if ((rc = ags_launch_composite_fwd(*a, w))) return rc;
@@ -74,19 +112,9 @@ extern "C" int ags_render_forward(const AgsRenderArgs* a) { return render_forwar
 extern "C" int ags_render_stage(const AgsRenderArgs* a, const AgsRenderGradArgs* g, int stage) {
     int rc = check_render_args(a);
     if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)a->stream;
     AgsWorkspace w = ags_carve(a->workspace, a->N, a->B, a->H, a->W, a->inst_cap);
     switch (stage) {
-        case AGS_STAGE_CLEAR: {
-            const size_t zero_bytes = (char*)w.inst_key - (char*)w.tile_count;
-            AGS_CHECK_CUDA(cudaMemsetAsync(w.tile_count, 0, zero_bytes, st));
-            AGS_CHECK_CUDA(cudaMemsetAsync(a->stats, 0, AGS_NUM_STATS * sizeof(int32_t), st));
-            if (a->N > 0) {
-                if (a->importance) AGS_CHECK_CUDA(cudaMemsetAsync(a->importance, 0, (size_t)a->B * a->N * 4, st));
-                if (a->count) AGS_CHECK_CUDA(cudaMemsetAsync(a->count, 0, (size_t)a->B * a->N * 4, st));
-            }
-            return 0;
-        }
+        case AGS_STAGE_CLEAR: return launch_clear(a, w);
         case AGS_STAGE_PROJECT_FWD: return ags_launch_project_fwd(*a, w, true);
         case AGS_STAGE_BINNING: return ags_launch_binning(*a, w);
         case AGS_STAGE_COMPOSITE_FWD: return ags_launch_composite_fwd(*a, w);

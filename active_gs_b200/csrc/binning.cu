@@ -7,19 +7,16 @@
 //      -> tile_offset (segments are contiguous per tile; their order in memory is irrelevant)
 //   3. scatter_kernel: every visible (view, Gaussian) writes key = depth_bits<<32 | id into its
 //      tiles' segments (slot claimed with an atomic)                       -> inst_key
-//   4. depth sort per tile (bitonic on 64-bit keys in shared memory; unique keys => deterministic, ties
-//      in depth resolved by Gaussian id exactly like the stable radix sort of the lineage).  Tiles with
-//      <= AGS_FUSED_SORT_MAX instances are sorted in the PROLOGUE of composite_fwd (composite.cu), where
-//      the barrier latency hides behind other CTAs' compositing; tile_sort_kernel only handles larger
-//      tiles: chunk sort + rank-by-binary-search merges through a ping-pong buffer.   -> inst_sorted
+//   4. depth sort per tile in the PROLOGUE of composite_fwd (composite.cu), where the barrier latency
+//      hides behind other CTAs' compositing: rank sort / bitonic network on 64-bit keys in shared memory
+//      (unique keys => deterministic, ties in depth resolved by Gaussian id exactly like the stable radix
+//      sort of the lineage); tiles above AGS_FUSED_SORT_MAX instances: chunk sort + rank-by-binary-search
+//      merges through a ping-pong buffer, by the same CTA.                            -> inst_sorted
 // Everything is sized by device-side counters; when the batch needs more than inst_cap instances the
 // overflow flag is raised and all later kernels render empty tiles.
 #include "ags_common.cuh"
 
 namespace {
-
-constexpr int SORT_CHUNK = 4096;
-constexpr int SORT_THREADS = 256;
 
 __global__ void __launch_bounds__(256)
 alloc_kernel(AgsWorkspace w, int n_tiles_total, int tiles_per_view, int inst_cap, int32_t* stats) {
@@ -43,7 +40,6 @@ alloc_kernel(AgsWorkspace w, int n_tiles_total, int tiles_per_view, int inst_cap
             atomicAdd(stats + AGS_STAT_VIEW0 + v, c);
         }
     }
-    if (c > AGS_FUSED_SORT_MAX) atomicAdd(w.counters + 2, 1);      // tile_sort_kernel has work to do
     int incl = c;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -70,6 +66,11 @@ alloc_kernel(AgsWorkspace w, int n_tiles_total, int tiles_per_view, int inst_cap
     if (t < n_tiles_total) w.tile_offset[t] = block_base + warp_excl + incl - c;
 }
 
+// Warp-cooperative scatter: a warp takes 32 visible (view, Gaussian) pairs, scans their tile counts and
+// then emits the union of their instances 32 at a time (lane j of a round finds its source pair with a
+// 5-step shuffle search over the scan).  Every round issues 32 independent slot-claiming atomics, so the
+// number of dependent round trips per warp is instances/32 (about 3) instead of the largest tile count
+// among its 32 pairs (one thread per pair serialised ~16 atomics behind the warp's biggest splat).
 __global__ void __launch_bounds__(256)
 scatter_kernel(AgsRenderArgs a, AgsWorkspace w) {
     const int total = w.counters[0];
@@ -80,99 +81,53 @@ scatter_kernel(AgsRenderArgs a, AgsWorkspace w) {
     const int nvis = w.counters[1];
     if (blockIdx.x == 0 && threadIdx.x == 0) a.stats[AGS_STAT_VISIBLE] = nvis;
     const int tiles_x = (a.W + TILE - 1) / TILE, tiles_y = (a.H + TILE - 1) / TILE;
-    const int stride = gridDim.x * blockDim.x;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nvis; e += stride) {
-        const size_t idx = (size_t)w.vis_list[e];
-        const int v = (int)(idx / a.N);
-        const uint32_t i = (uint32_t)(idx - (size_t)v * a.N);
-        const uint2 r = w.rect[idx];
-        const int minx = r.x & 0xffff, maxx = r.x >> 16, miny = r.y & 0xffff, maxy = r.y >> 16;
-        const size_t tbase = (size_t)v * tiles_x * tiles_y;
-        const float depth = w.feat0[idx].w;
-        const uint64_t key = ((uint64_t)__float_as_uint(depth) << 32) | i;
-        for (int ty = miny; ty < maxy; ++ty)
-            for (int tx = minx; tx < maxx; ++tx) {
-                const size_t t = tbase + (size_t)ty * tiles_x + tx;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int e0 = warp * 32; e0 < nvis; e0 += nwarps * 32) {
+        const int e = e0 + lane;
+        int minx = 0, miny = 0, wx = 0, cnt = 0, tbase = 0;
+        unsigned key_hi = 0u, key_lo = 0u;
+        if (e < nvis) {
+            const size_t idx = (size_t)w.vis_list[e];
+            const int v = (int)(idx / a.N);
+            key_lo = (uint32_t)(idx - (size_t)v * a.N);
+            const uint2 r = w.rect[idx];
+            minx = r.x & 0xffff; miny = r.y & 0xffff;
+            wx = (int)(r.x >> 16) - minx;
+            cnt = wx * ((int)(r.y >> 16) - miny);
+            tbase = v * tiles_x * tiles_y;
+            key_hi = __float_as_uint(w.feat0[idx].w);
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        const int total_w = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl = incl - cnt;
+        for (int j0 = 0; j0 < total_w; j0 += 32) {
+            const int j = j0 + lane;
+            // source lane = number of lanes whose inclusive count is <= j
+            int src = 0;
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const int t = __shfl_sync(0xffffffffu, incl, min(src + step - 1, 31));
+                if (t <= j) src += step;
+            }
+            src = min(src, 31);
+            const int local = j - __shfl_sync(0xffffffffu, excl, src);
+            const int sminx = __shfl_sync(0xffffffffu, minx, src), sminy = __shfl_sync(0xffffffffu, miny, src);
+            const int swx = __shfl_sync(0xffffffffu, wx, src), stb = __shfl_sync(0xffffffffu, tbase, src);
+            const unsigned khi = __shfl_sync(0xffffffffu, key_hi, src), klo = __shfl_sync(0xffffffffu, key_lo, src);
+            if (j < total_w) {
+                const int ty = sminy + local / swx, tx = sminx + local - (local / swx) * swx;
+                const size_t t = (size_t)stb + (size_t)ty * tiles_x + tx;
                 const int slot = w.tile_offset[t] + atomicAdd(w.tile_fill + t, 1);
-                w.inst_key[slot] = key;
+                w.inst_key[slot] = ((uint64_t)khi << 32) | klo;
             }
-    }
-}
-
-__device__ __forceinline__ void bitonic_smem(uint64_t* s, int m) {
-    for (int k = 2; k <= m; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (m >> 1); t += SORT_THREADS) {
-                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int hi = lo | j;
-                const bool asc = ((lo & k) == 0);
-                const uint64_t x = s[lo], y = s[hi];
-                if ((x > y) == asc) { s[lo] = y; s[hi] = x; }
-            }
-            __syncthreads();
         }
-    }
-}
-
-// one oversize tile (more than AGS_FUSED_SORT_MAX instances): chunk sort + rank merges
-__device__ void sort_oversize_tile(const AgsWorkspace& w, int t, uint64_t* s) {
-    const int n = w.tile_count[t];
-    if (n <= AGS_FUSED_SORT_MAX) return;     // sorted in the prologue of composite_fwd
-    const int off = w.tile_offset[t];
-    uint64_t* keys = w.inst_key + off;
-    int32_t* out = w.inst_sorted + off;
-    // phase 1: sort chunks of SORT_CHUNK in shared memory
-    for (int cbase = 0; cbase < n; cbase += SORT_CHUNK) {
-        const int cn = min(SORT_CHUNK, n - cbase);
-        int m = 2;
-        while (m < cn) m <<= 1;
-        for (int k = threadIdx.x; k < m; k += SORT_THREADS) s[k] = (k < cn) ? keys[cbase + k] : ~0ull;
-        __syncthreads();
-        bitonic_smem(s, m);
-        if (n <= SORT_CHUNK) {
-            for (int k = threadIdx.x; k < cn; k += SORT_THREADS) out[k] = (int32_t)(s[k] & 0xffffffffu);
-            return;
-        }
-        for (int k = threadIdx.x; k < cn; k += SORT_THREADS) keys[cbase + k] = s[k];
-        __syncthreads();
-    }
-    // phase 2: pairwise merges through the ping-pong buffer (keys are unique)
-    uint64_t* src = keys;
-    uint64_t* dst = w.inst_key_alt + off;
-    for (int run = SORT_CHUNK; run < n; run <<= 1) {
-        for (int e = threadIdx.x; e < n; e += SORT_THREADS) {
-            const int r = e / run;
-            const int pr = r ^ 1;
-            const int ps = pr * run;
-            const uint64_t key = src[e];
-            int dest = e;
-            if (ps < n) {
-                const int pe = min(ps + run, n);
-                int lo = ps, hi = pe;                       // first partner element > key
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (src[mid] < key) lo = mid + 1; else hi = mid;
-                }
-                dest = min(r, pr) * run + (e - r * run) + (lo - ps);
-            }
-            dst[dest] = key;
-        }
-        __syncthreads();
-        uint64_t* tmp = src; src = dst; dst = tmp;
-    }
-    for (int k = threadIdx.x; k < n; k += SORT_THREADS) out[k] = (int32_t)(src[k] & 0xffffffffu);
-}
-
-// Oversize tiles are rare (none at all in the BASELINE workloads): the binning pass counts them in
-// counters[2], and a small persistent grid returns at once when there is nothing to do -- one block per
-// tile cost ~10 us per iteration in block scheduling alone.
-__global__ void __launch_bounds__(SORT_THREADS)
-tile_sort_kernel(AgsWorkspace w, int n_tiles_total, int inst_cap) {
-    __shared__ uint64_t s[SORT_CHUNK];
-    if (w.counters[2] == 0 || w.counters[0] > inst_cap) return;
-    for (int t = blockIdx.x; t < n_tiles_total; t += gridDim.x) {
-        sort_oversize_tile(w, t, s);
-        __syncthreads();
     }
 }
 
@@ -190,9 +145,6 @@ int ags_launch_binning(const AgsRenderArgs& a, const AgsWorkspace& w) {
         ags_note_launch(); scatter_kernel<<<(int)blocks, 256, 0, st>>>(a, w);
         AGS_CHECK_CUDA(cudaGetLastError());
     }
-    // only tiles with more than AGS_FUSED_SORT_MAX instances are sorted here (chunk sort + merge);
-    // all others are sorted in the prologue of composite_fwd
-    ags_note_launch(); tile_sort_kernel<<<nt < 148 * 2 ? nt : 148 * 2, SORT_THREADS, 0, st>>>(w, nt, a.inst_cap);
-    AGS_CHECK_CUDA(cudaGetLastError());
+    // the depth sort of every tile happens in the prologue of composite_fwd (composite.cu)
     return 0;
 }

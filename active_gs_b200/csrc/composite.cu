@@ -91,12 +91,76 @@ __device__ __forceinline__ bool bbox_hits(const float4 bb, const WarpBlock& b) {
     return (bb.x <= b.x1) && (bb.y >= b.x0) && (bb.z <= b.y1) && (bb.w >= b.y0);
 }
 
+// Depth sort of an OVERSIZE tile (more than AGS_FUSED_SORT_MAX instances; none in the BASELINE workloads)
+// by the tile's own CTA: bitonic sort of chunks of SORT_CHUNK keys in the 20 KB staging buffer, then
+// rank-by-binary-search merges through the ping-pong key buffer (keys are unique).  256 threads.
+constexpr int SORT_CHUNK = AGS_FUSED_SORT_MAX;
+
+__device__ __forceinline__ void bitonic_cta(uint64_t* s, int m, int tid) {
+    for (int k = 2; k <= m; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (m >> 1); t += 256) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int hi = lo | j;
+                const bool asc = ((lo & k) == 0);
+                const uint64_t x = s[lo], y = s[hi];
+                if ((x > y) == asc) { s[lo] = y; s[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ void sort_oversize_tile(const AgsWorkspace& w, int n, int off, uint64_t* s, int tid) {
+    uint64_t* keys = w.inst_key + off;
+    int32_t* out = w.inst_sorted + off;
+    for (int cbase = 0; cbase < n; cbase += SORT_CHUNK) {
+        const int cn = min(SORT_CHUNK, n - cbase);
+        int m = 2;
+        while (m < cn) m <<= 1;
+        for (int k = tid; k < m; k += 256) s[k] = (k < cn) ? keys[cbase + k] : ~0ull;
+        __syncthreads();
+        bitonic_cta(s, m, tid);
+        for (int k = tid; k < cn; k += 256) keys[cbase + k] = s[k];
+        __syncthreads();
+    }
+    uint64_t* src = keys;
+    uint64_t* dst = w.inst_key_alt + off;
+    for (int run = SORT_CHUNK; run < n; run <<= 1) {
+        __threadfence_block();
+        for (int e = tid; e < n; e += 256) {
+            const int r = e / run;
+            const int pr = r ^ 1;
+            const int ps = pr * run;
+            const uint64_t key = src[e];
+            int dest = e;
+            if (ps < n) {
+                const int pe = min(ps + run, n);
+                int lo = ps, hi = pe;                       // first partner element > key
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (src[mid] < key) lo = mid + 1; else hi = mid;
+                }
+                dest = min(r, pr) * run + (e - r * run) + (lo - ps);
+            }
+            dst[dest] = key;
+        }
+        __syncthreads();
+        uint64_t* tmp = src; src = dst; dst = tmp;
+    }
+    for (int k = tid; k < n; k += 256) out[k] = (int32_t)(src[k] & 0xffffffffu);
+    __syncthreads();
+}
+
 // K4 ---------------------------------------------------------------------------------------------
 #ifndef AGS_RANKSORT
 #define AGS_RANKSORT 1        // single-batch tiles: rank sort fused with the staging (0 = bitonic prologue)
 #endif
 #ifndef AGS_BWD_PX_DEFAULT
 #define AGS_BWD_PX_DEFAULT 1  // pixels per lane of the backward (composite_bwd_kernel<PX>)
+#endif
+#ifndef AGS_BWD_RED_DEFAULT
+#define AGS_BWD_RED_DEFAULT 0 // cross-lane reduction variant of the backward (see bwd_red())
 #endif
 #ifndef AGS_FWD_MINB
 #define AGS_FWD_MINB 6
@@ -127,7 +191,7 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
     // ---- prologue: depth sort of this tile's instance keys (K3 fused here: its barrier latency hides
     // behind the compositing of the other resident CTAs).  Keys (depth_bits<<32 | id) are unique, so
     // the bitonic network is deterministic; ids go to inst_sorted for the batches below and for the
-    // backward.  Tiles above the shared-memory capacity were sorted by tile_sort_kernel beforehand.
+    // backward.  Tiles above the shared-memory capacity: sort_oversize_tile (chunk sort + merges).
     int32_t first_id = -1;
     bool prestaged = false;
     const size_t vN = (size_t)v * a.N;
@@ -206,6 +270,8 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
         if (tid < n) first_id = (int32_t)(s_keys[tid] & 0xffffffffu);
         for (int k = tid; k < n; k += 256) w.inst_sorted[off + k] = (int32_t)(s_keys[k] & 0xffffffffu);
         __syncthreads();            // ids visible to the whole CTA; s_raw free for the records
+    } else if (n > FUSED_SORT_MAX) {
+        sort_oversize_tile(w, n, off, s_keys, tid);     // ids in inst_sorted (global), visible after its barrier
     }
     const size_t P = (size_t)a.H * a.W;
     const size_t pix = (size_t)py * a.W + px;
@@ -233,7 +299,7 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
             r.f1 = ldg4(w.feat1 + idx);
             r.bb = splat_bbox(g0, g1);
         }
-        __syncthreads();
+        if (!(prestaged && base == 0)) __syncthreads();   // (the rank-sorted first batch was ordered by the barrier above)
         const int cnt = min(BATCH, n - base);
         for (int c = 0; c < cnt && !warp_done; c += 32) {
             const int jj = c + lane;
@@ -308,6 +374,56 @@ __device__ __forceinline__ float warp_reduce15(const float (&v)[15], unsigned st
     r += __shfl_xor_sync(0xffffffffu, r, 1);
     __syncwarp();
     return r;
+}
+
+// Variant 1: ONE register butterfly step first (lanes l and l^16 exchange half of their values), then
+// the transposition runs on 8 values per lane over two half-warps: half the shared-memory bytes
+// (8 STS.32 + 2 LDS.128 per lane instead of 15 + 4) for 8 SHFL + 16 SEL more.  Layout per warp: row =
+// value (stride 24 floats), column = lane & 15, rows 8..15 shifted by 16 floats: conflict-free stores and
+// quarter-warp-phased 128-bit loads (checked exhaustively offline).
+constexpr int RED1_STRIDE = 24, RED1_HALF = 16, RED1_FLOATS = 16 * RED1_STRIDE + RED1_HALF;
+
+__device__ __forceinline__ float warp_reduce15_half(const float (&v)[15], unsigned st_addr, unsigned ld_addr, int lane) {
+    const bool upper = (lane & 16) != 0;
+    float r8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float lo = v[i], hi = (i < 7) ? v[i + 8] : 0.f;
+        const float send = upper ? lo : hi, keep = upper ? hi : lo;
+        r8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#define AGS_RED_ST(q) asm volatile("st.shared.f32 [%0+%1], %2;" :: "r"(st_addr), "n"((q) * RED1_STRIDE * 4), "f"(r8[q]) : "memory")
+    AGS_RED_ST(0); AGS_RED_ST(1); AGS_RED_ST(2); AGS_RED_ST(3); AGS_RED_ST(4); AGS_RED_ST(5); AGS_RED_ST(6); AGS_RED_ST(7);
+#undef AGS_RED_ST
+    __syncwarp();
+    float r = 0.f;
+    if (lane < 30) {
+        float4 x0, x1;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x0.x), "=f"(x0.y), "=f"(x0.z), "=f"(x0.w) : "r"(ld_addr) : "memory");
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+32];" : "=f"(x1.x), "=f"(x1.y), "=f"(x1.z), "=f"(x1.w) : "r"(ld_addr) : "memory");
+        r = ((x0.x + x0.y) + (x0.z + x0.w)) + ((x1.x + x1.y) + (x1.z + x1.w));
+    }
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    __syncwarp();
+    return r;
+}
+
+// Variant 2: the full register butterfly (no shared memory): 16 SHFL + 15 FADD + 30 SEL.
+__device__ __forceinline__ float warp_reduce15_shfl(const float (&v)[15], int lane) {
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) a[i] = v[i];
+    a[15] = 0.f;
+#pragma unroll
+    for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+        const bool upper = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < w; ++i) {
+            const float send = upper ? a[i] : a[i + w], keep = upper ? a[i + w] : a[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    return a[0] + __shfl_xor_sync(0xffffffffu, a[0], 1);
 }
 
 // Per-pixel state of the backward walk.
@@ -390,14 +506,15 @@ __device__ __forceinline__ void bwd_accumulate(float (&val)[15], BwdPix& s, cons
 // (warp block, splat) -- with PX = 4 half as many as with 8x4 blocks -- and the loop control, the record
 // loads and the bounding-box test are shared by the PX pixels.  Sub-blocks of 8x4 pixels the splat's
 // cutoff box does not reach are skipped warp-uniformly.
-template <int PX, bool HAS_CONF>
+template <int PX, bool HAS_CONF, int RED>
 __global__ void __launch_bounds__(256 / PX, PX == 1 ? AGS_BWD_MINB : (PX == 2 ? 6 : 8))
 composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
     constexpr int THREADS = 256 / PX, WARPS = 8 / PX;
+    constexpr int RED_FLOATS = RED == 0 ? 15 * RED_STRIDE : (RED == 1 ? RED1_FLOATS : 4);
     __shared__ SplatRec s_rec[BATCH];
     __shared__ int s_id[BATCH];
     __shared__ int s_max_last;
-    __shared__ __align__(16) float s_red[WARPS][15 * RED_STRIDE];   // per-warp transposition buffer
+    __shared__ __align__(16) float s_red[WARPS][RED_FLOATS];   // per-warp transposition buffer
     const int v = blockIdx.z;
     const int tiles_x = gridDim.x, tiles_y = gridDim.y;
     const int tile = blockIdx.y * tiles_x + blockIdx.x;
@@ -428,8 +545,15 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
     const int n_eff = min(n, s_max_last);
     const int warp_last = __reduce_max_sync(0xffffffffu, lane_last);
     // loop-invariant shared-space addresses of this lane's slots in the warp's transposition buffer
-    const unsigned red_st = (unsigned)__cvta_generic_to_shared(&s_red[wid][lane]);
-    const unsigned red_ld = (unsigned)__cvta_generic_to_shared(&s_red[wid][(lane >> 1) * RED_STRIDE + (lane & 1) * 16]);
+    unsigned red_st, red_ld;
+    if (RED == 1) {
+        red_st = (unsigned)__cvta_generic_to_shared(&s_red[wid][(lane >> 4) * (8 * RED1_STRIDE + RED1_HALF) + (lane & 15)]);
+        red_ld = (unsigned)__cvta_generic_to_shared(
+            &s_red[wid][(lane >> 1) * RED1_STRIDE + (lane >> 4) * RED1_HALF + (lane & 1) * 4]);
+    } else {
+        red_st = (unsigned)__cvta_generic_to_shared(&s_red[wid][RED == 0 ? lane : 0]);
+        red_ld = (unsigned)__cvta_generic_to_shared(&s_red[wid][RED == 0 ? (lane >> 1) * RED_STRIDE + (lane & 1) * 16 : 0]);
+    }
     float* const dsplat_lane = w.dsplat + vN * 16 + (lane >> 1);
     for (int base = 0; base < n_eff; base += BATCH) {
         __syncthreads();
@@ -493,7 +617,8 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
                         if (any & (1u << j))
                             bwd_accumulate<false, HAS_CONF>(val, s[j], g1, f0, f1, dx, eDy[j], eA[j], eG[j], act[j]);
                 }
-                const float r = warp_reduce15(val, red_st, red_ld, lane);
+                const float r = RED == 0 ? warp_reduce15(val, red_st, red_ld, lane)
+                              : (RED == 1 ? warp_reduce15_half(val, red_st, red_ld, lane) : warp_reduce15_shfl(val, lane));
                 if ((lane & 1) == 0 && lane < 30) atomicAdd(dsplat_lane + (size_t)s_id[k] * 16, r);
             }
         }
@@ -522,11 +647,32 @@ static int bwd_px() {
     return px;
 }
 
+// Cross-lane reduction of the 15 partials: 0 = shared-memory transposition, 1 = one shuffle step + half
+// transposition, 2 = register butterfly.  AGS_BWD_RED overrides the default for tuning runs.
+static int bwd_red() {
+    static int red = -1;
+    if (red < 0) {
+        const char* e = getenv("AGS_BWD_RED");
+        red = e ? atoi(e) : AGS_BWD_RED_DEFAULT;
+        if (red < 0 || red > 2) red = AGS_BWD_RED_DEFAULT;
+    }
+    return red;
+}
+
+template <int PX, int RED>
+static void launch_bwd2(const AgsRenderArgs& a, const AgsRenderGradArgs& g, const AgsWorkspace& w, dim3 grid) {
+    ags_note_launch();
+    if (g.d_confidence) composite_bwd_kernel<PX, true, RED><<<grid, 256 / PX, 0, (cudaStream_t)a.stream>>>(a, g, w);
+    else composite_bwd_kernel<PX, false, RED><<<grid, 256 / PX, 0, (cudaStream_t)a.stream>>>(a, g, w);
+}
+
 template <int PX>
 static void launch_bwd(const AgsRenderArgs& a, const AgsRenderGradArgs& g, const AgsWorkspace& w, dim3 grid) {
-    ags_note_launch();
-    if (g.d_confidence) composite_bwd_kernel<PX, true><<<grid, 256 / PX, 0, (cudaStream_t)a.stream>>>(a, g, w);
-    else composite_bwd_kernel<PX, false><<<grid, 256 / PX, 0, (cudaStream_t)a.stream>>>(a, g, w);
+    switch (bwd_red()) {
+        case 0: launch_bwd2<PX, 0>(a, g, w, grid); break;
+        case 1: launch_bwd2<PX, 1>(a, g, w, grid); break;
+        default: launch_bwd2<PX, 2>(a, g, w, grid); break;
+    }
 }
 
 int ags_launch_composite_bwd(const AgsRenderArgs& a, const AgsRenderGradArgs& g, const AgsWorkspace& w) {

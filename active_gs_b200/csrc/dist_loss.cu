@@ -19,6 +19,7 @@ struct VisParams {
     int world, B;
     unsigned P;
     const float* opacity;
+    const float* frame_weight;
     int32_t* vis_local;
     const int32_t* peers[AGS_MAX_PEERS];
     const int32_t* mc;
@@ -30,7 +31,10 @@ dist_vis_local_kernel(VisParams a) {
     const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.P) return;
     int c = 0;
-    for (int f = 0; f < a.B; ++f) c += (__ldg(a.opacity + (size_t)f * a.P + p) > 1e-3f) ? 1 : 0;
+    for (int f = 0; f < a.B; ++f) {
+        const bool real = !a.frame_weight || __ldg(a.frame_weight + f) != 0.f;      // padded frames do not count
+        c += (real && __ldg(a.opacity + (size_t)f * a.P + p) > 1e-3f) ? 1 : 0;
+    }
     a.vis_local[p] = c;
 }
 
@@ -83,7 +87,7 @@ int fill_vis(const AgsDistVisArgs* a, VisParams& P, bool need_peers) {
     AGS_CHECK_ARG(a->B > 0 && a->H > 0 && a->W > 0 && (long long)a->H * a->W < (1ll << 31), "bad sizes");
     AGS_CHECK_ARG(a->vis_local != nullptr, "NULL vis_local");
     P.world = a->world; P.B = a->B; P.P = (unsigned)a->H * (unsigned)a->W;
-    P.opacity = a->opacity; P.vis_local = a->vis_local; P.mc = a->vis_multicast; P.out = a->vis_count;
+    P.opacity = a->opacity; P.frame_weight = a->frame_weight; P.vis_local = a->vis_local; P.mc = a->vis_multicast; P.out = a->vis_count;
     for (int r = 0; r < AGS_MAX_PEERS; ++r) {
         P.peers[r] = r < a->world ? a->vis_peers[r] : nullptr;
         if (need_peers && !a->vis_multicast && r < a->world) AGS_CHECK_ARG(a->vis_peers[r] != nullptr, "NULL peer pointer %d", r);

@@ -8,13 +8,17 @@
 //   /root/reference/mapping/gaussian_map.py:132-139  track_performance per-frame means
 // and the autograd backward of all of it down to d rgb / d depth / d normal(raw).
 //
-// Two stencil passes, one thread per (pixel, frame):
-//   pass A: unit normal, d2n, rgb gradient, loss sums, the pixel's own depth gradient (L1 term +
-//           its share of the depth2normal adjoint) and, as four planes, what it contributes to the
-//           depth gradients of its 4 neighbours
-//   pass B: depth gradient += gather of the neighbours' planes; normal gradient (consistency +
-//           gather of the TV terms, then through normalize*mask); TV loss sum
-// HBM roofline: reads 15 planes + writes 13 planes of B*H*W floats (+3 scratch planes twice).
+// ONE tiled kernel (loss_fused_kernel): a CTA owns a 32x8 pixel tile of one frame and stages, in shared
+// memory, depth / opacity mask of the tile + a halo of 2 and the unit normals / visibility sum / depth
+// mask of the tile + a halo of 1.  Phase 1 evaluates depth2normal and its adjoint (the pixel's own depth
+// gradient and what it pushes to its four neighbours) for the tile + halo 1; phase 2 gathers the
+// neighbours' contributions from shared memory, adds the L1 terms and the TV / consistency normal
+// gradient and writes d_rgb / d_depth / d_normal ONCE.  No intermediate planes in global memory, no
+// atomics on images, deterministic.
+// HBM roofline: reads 12 planes (8 predicted + 4 ground truth) + the (H,W) visibility sum, writes 7 planes
+// of B*H*W floats (+6 when the caller wants normal_unit / d2n): 76 B per pixel and frame.  The halo
+// (1.33x / 1.69x of the tile) is served by L2.
+#include <string.h>
 #include "ags_common.cuh"
 
 namespace {
@@ -113,7 +117,10 @@ __device__ __forceinline__ void block_accumulate(float (&v)[K], float* const (&d
 __device__ __forceinline__ float vis_sum(const AgsLossArgs& a, size_t P, int p) {
     if (a.vis_count) return (float)__ldg(a.vis_count + p);
     float m = 0.f;
-    for (int f = 0; f < a.B; ++f) m += (__ldg(a.opacity + (size_t)f * P + p) > 1e-3f) ? 1.f : 0.f;
+    for (int f = 0; f < a.B; ++f) {
+        const float wf = a.frame_weight ? __ldg(a.frame_weight + f) : 1.f;       // padded frames do not count
+        m += (wf != 0.f && __ldg(a.opacity + (size_t)f * P + p) > 1e-3f) ? 1.f : 0.f;
+    }
     return m;
 }
 
@@ -130,89 +137,16 @@ loss_vis_count(AgsLossArgs a, float* __restrict__ msum_plane) {
 #define AGS_LOSS_MINB 4
 #endif
 
-// Addressing: every tensor is indexed as  kernel-parameter pointer + 32-bit unsigned element offset
-// (B*3*H*W < 2^32, checked by the launcher), which lets the compiler use the uniform-base +
-// 32-bit-offset addressing mode instead of 64-bit pointer arithmetic per access.
+constexpr int LT_W = 32, LT_H = 8;                 // output tile
+constexpr int LE_W = LT_W + 2, LE_H = LT_H + 2;    // tile + halo 1 (d2n adjoint, unit normals)
+constexpr int LR_W = LT_W + 4, LR_H = LT_H + 4;    // tile + halo 2 (depth, opacity mask)
+constexpr int LE_N = LE_W * LE_H, LR_N = LR_W * LR_H;
+#define AGS_LOSS_MAX_FRAMES 64
 
-// pass A: one thread per (pixel, frame).  Writes normal_unit, d2n, d_rgb, the pixel's own depth
-// gradient (L1 term + its share of the depth2normal adjoint) and the four contributions it makes
-// to its neighbours' depth gradients as four planes (up, left, bottom, right) that pass B gathers:
-// no atomics, deterministic.
-__global__ void __launch_bounds__(256, AGS_LOSS_MINB)
-loss_pass_a(AgsLossArgs a, float* __restrict__ nb, const float* __restrict__ msum_plane) {
-    const int H = a.H, W = a.W;
-    const unsigned P = (unsigned)H * (unsigned)W;
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    const unsigned f = blockIdx.z;
-    const bool in = (x < W) && (y < H);
-    const unsigned p = (unsigned)y * (unsigned)W + (unsigned)x;
-    const float Bt = (float)a.B_total;
-    const float inv_rgb = 1.f / (Bt * 3.f * (float)P);
-    const float inv_d = 1.f / (Bt * (float)P);
-    const float inv_cons = 1.f / (Bt * Bt * (float)P);
-    float fr_rgb = 0.f, fr_d = 0.f, acc_cons = 0.f;
-    if (in) {
-        const unsigned o1 = f * P + p;             // single-channel planes
-        const unsigned o3 = f * 3u * P + p;        // three-channel planes
-        const unsigned o4 = f * 4u * P + p;        // neighbour planes
-        const float msum = __ldg(msum_plane + p);
-        const float* opac = a.opacity + f * P;     // frame bases for the stencil helpers
-        const float* depth = a.depth + f * P;
-        const float A = __ldg(a.opacity + o1);
-        const float mvis = (A > 1e-3f) ? 1.f : 0.f;
-        const float m2 = (A > 1e-2f) ? 1.f : 0.f;
-        // ---- L1 rgb + gradient
-#pragma unroll
-        for (unsigned c = 0; c < 3; ++c) {
-            const float e = (__ldg(a.rgb + o3 + c * P) - __ldg(a.rgb_gt + o3 + c * P)) * mvis;
-            fr_rgb += fabsf(e);
-            a.d_rgb[o3 + c * P] = (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f)) * mvis * inv_rgb;
-        }
-        // ---- L1 depth + gradient
-        const float dg = __ldg(a.depth_gt + o1);
-        const float md = (dg > 0.f) ? 1.f : 0.f;
-        const float ed = (__ldg(a.depth + o1) - dg) * md;
-        fr_d = fabsf(ed);
-        float dd_self = a.w_depth * (ed > 0.f ? 1.f : (ed < 0.f ? -1.f : 0.f)) * md * inv_d;
-        // ---- unit normal
-        const F3 n = f3(__ldg(a.normal + o3), __ldg(a.normal + o3 + P), __ldg(a.normal + o3 + 2u * P));
-        const F3 nu = n * (m2 * rsqrtf(fmaxf(dot(n, n), 1e-24f)));
-        a.normal_unit[o3] = nu.x; a.normal_unit[o3 + P] = nu.y; a.normal_unit[o3 + 2u * P] = nu.z;
-        // ---- depth2normal
-        const FrameGeom g = frame_geom(a.tanfov, f, H, W);
-        const D2N v = d2n_vectors(depth, opac, g, H, W, y, x);
-        const F3 ns = cross(v.pu, v.pl) + cross(v.pr, v.pu) + cross(v.pb, v.pr) + cross(v.pl, v.pb);
-        const float insn = rsqrtf(fmaxf(dot(ns, ns), 1e-24f));
-        const F3 u = ns * insn;
-        const F3 d2n = u * m2;
-        a.d2n[o3] = d2n.x; a.d2n[o3 + P] = d2n.y; a.d2n[o3 + 2u * P] = d2n.z;
-        // ---- consistency loss; adjoint of the un-normalised d2n vector, pushed to the five depths
-        acc_cons = (1.f - dot(nu, d2n)) * msum;
-        float c_up = 0.f, c_left = 0.f, c_bottom = 0.f, c_right = 0.f;
-        if (m2 > 0.f && msum > 0.f) {
-            const float wc = -a.w_cons * msum * inv_cons;                // dL/d(nu . d2n)
-            const F3 gd = nu * wc;                                       // dL/d u  (d2n = u*m2, m2 = 1)
-            const F3 gq = (gd - u * dot(u, gd)) * insn;
-            const F3 dpu = (cross(v.pl, gq) + cross(gq, v.pr)) * v.mu;
-            const F3 dpl = (cross(gq, v.pu) + cross(v.pb, gq)) * v.ml;
-            const F3 dpb = (cross(v.pr, gq) + cross(gq, v.pl)) * v.mb;
-            const F3 dpr = (cross(v.pu, gq) + cross(gq, v.pb)) * v.mr;
-            const F3 dpc = (dpu + dpl + dpb + dpr) * (-v.mc);
-            const float rx = (x - g.cx) * g.ik00, ry = (y - g.cy) * g.ik11;   // c = depth * (rx, ry, 1)
-            dd_self += dpc.x * rx + dpc.y * ry + dpc.z;
-            c_up = dpu.x * rx + dpu.y * (ry - g.ik11) + dpu.z;          // zero when v.mu == 0
-            c_left = dpl.x * (rx - g.ik00) + dpl.y * ry + dpl.z;
-            c_bottom = dpb.x * rx + dpb.y * (ry + g.ik11) + dpb.z;
-            c_right = dpr.x * (rx + g.ik00) + dpr.y * ry + dpr.z;
-        }
-        a.d_depth[o1] = dd_self;
-        nb[o4] = c_up; nb[o4 + P] = c_left; nb[o4 + 2u * P] = c_bottom; nb[o4 + 3u * P] = c_right;
-    }
-    float v5[5] = {fr_rgb * inv_rgb, fr_d * inv_d, acc_cons * inv_cons, fr_rgb / (3.f * (float)P), fr_d / (float)P};
-    float* const d5[5] = {a.loss_terms + 0, a.loss_terms + 1, a.loss_terms + 2,
-                          a.loss_terms + 4 + 2 * f, a.loss_terms + 4 + 2 * f + 1};
-    block_accumulate<5>(v5, d5);
-}
+struct LossFrames {        // per-frame ground-truth pointers (kernel parameter; NULL list -> stacked tensors)
+    const float* rgb[AGS_LOSS_MAX_FRAMES];
+    const float* depth[AGS_LOSS_MAX_FRAMES];
+};
 
 // TV helper: value and derivative factor of one one-sided difference
 __device__ __forceinline__ void tv_term(F3 np_, F3 nq, float dp, float dq, float md, float inv2s2,
@@ -226,73 +160,179 @@ __device__ __forceinline__ void tv_term(F3 np_, F3 nq, float dp, float dq, float
     coef = gate * e * (1.f - nd * inv2s2);       // d val / d nd
 }
 
-// pass B: one thread per (pixel, frame): depth gradient += the neighbours' planes; normal gradient
-// (consistency + TV gather, through normalize*mask) and the TV loss sum.
+template <bool USE_LIST>
 __global__ void __launch_bounds__(256, AGS_LOSS_MINB)
-loss_pass_b(AgsLossArgs a, const float* __restrict__ nb, const float* __restrict__ msum_plane) {
+loss_fused_kernel(AgsLossArgs a, LossFrames fr, const float* __restrict__ msum_plane) {
+    __shared__ float sD[LR_N], sM[LR_N];                         // depth, d2n mask (opacity > 1e-2); 0 outside
+    __shared__ float sNU[3][LE_N], sMS[LE_N], sMD[LE_N];         // unit normal, visibility sum, depth_gt > 0
+    __shared__ float sDN[3][LE_N];                               // d2n (= u * m2)
+    __shared__ float sAdj[5][LE_N];                              // own, up, left, bottom, right depth adjoints
     const int H = a.H, W = a.W;
     const unsigned P = (unsigned)H * (unsigned)W;
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
     const unsigned f = blockIdx.z;
-    const bool in = (x < W) && (y < H);
-    const unsigned p = (unsigned)y * (unsigned)W + (unsigned)x;
+    const int tid = threadIdx.y * LT_W + threadIdx.x;
+    const int x0 = blockIdx.x * LT_W, y0 = blockIdx.y * LT_H;
+    const float wf = a.frame_weight ? __ldg(a.frame_weight + f) : 1.f;
     const float Bt = (float)a.B_total;
-    const float inv_cons = 1.f / (Bt * Bt * (float)P);
-    const float inv_tv = 1.f / (Bt * 4.f * (float)P);
+    const float inv_rgb = wf / (Bt * 3.f * (float)P);
+    const float inv_d = wf / (Bt * (float)P);
+    const float inv_cons = wf / (Bt * Bt * (float)P);
+    const float inv_tv = wf / (Bt * 4.f * (float)P);
     const float inv2s2 = 1.f / (2.f * 0.3f * 0.3f);
-    float acc_tv = 0.f;
+    const float* depth = a.depth + f * P;
+    const float* opac = a.opacity + f * P;
+    const float* normal = a.normal + f * 3u * P;
+    const float* depth_gt = USE_LIST ? fr.depth[f] : a.depth_gt + f * P;
+    const float* rgb_gt = USE_LIST ? fr.rgb[f] : a.rgb_gt + f * 3u * P;
+    const FrameGeom g = frame_geom(a.tanfov, f, H, W);
+    // ---- stage: depth + mask with halo 2
+    for (int i = tid; i < LR_N; i += 256) {
+        const int ry = i / LR_W, rx = i - ry * LR_W;
+        const int y = y0 - 2 + ry, x = x0 - 2 + rx;
+        float d = 0.f, m = 0.f;
+        if (x >= 0 && x < W && y >= 0 && y < H) {
+            d = __ldg(depth + y * W + x);
+            m = (__ldg(opac + y * W + x) > 1e-2f) ? 1.f : 0.f;
+        }
+        sD[i] = d; sM[i] = m;
+    }
+    // ---- stage: unit normal, visibility sum, depth mask with halo 1
+    for (int i = tid; i < LE_N; i += 256) {
+        const int ey = i / LE_W, ex = i - ey * LE_W;
+        const int y = y0 - 1 + ey, x = x0 - 1 + ex;
+        F3 nu = f3(0.f, 0.f, 0.f);
+        float ms = 0.f, md = 0.f;
+        if (x >= 0 && x < W && y >= 0 && y < H) {
+            const unsigned p = (unsigned)y * W + x;
+            const F3 n = f3(__ldg(normal + p), __ldg(normal + P + p), __ldg(normal + 2u * P + p));
+            const float m2 = (__ldg(opac + p) > 1e-2f) ? 1.f : 0.f;
+            nu = n * (m2 * rsqrtf(fmaxf(dot(n, n), 1e-24f)));
+            ms = __ldg(msum_plane + p);
+            md = (__ldg(depth_gt + p) > 0.f) ? 1.f : 0.f;
+        }
+        sNU[0][i] = nu.x; sNU[1][i] = nu.y; sNU[2][i] = nu.z; sMS[i] = ms; sMD[i] = md;
+    }
+    __syncthreads();
+    // ---- phase 1: depth2normal + adjoint for the tile + halo 1
+    for (int i = tid; i < LE_N; i += 256) {
+        const int ey = i / LE_W, ex = i - ey * LE_W;
+        const int y = y0 - 1 + ey, x = x0 - 1 + ex;
+        F3 d2n = f3(0.f, 0.f, 0.f);
+        float a_own = 0.f, a_up = 0.f, a_left = 0.f, a_bottom = 0.f, a_right = 0.f;
+        if (x >= 0 && x < W && y >= 0 && y < H) {
+            const int r = (ey + 1) * LR_W + (ex + 1);            // same pixel in the halo-2 region
+            const float rx = (x - g.cx) * g.ik00, ry = (y - g.cy) * g.ik11;   // point = depth * (rx, ry, 1)
+            // replicate padding: an out-of-image neighbour equals the pixel itself; with a 0/1 mask its
+            // masked difference is exactly zero, which the zero mask staged outside the image reproduces
+            const float dc = sD[r], mc = sM[r];
+            const float du = sD[r - LR_W], mu = sM[r - LR_W];
+            const float dl = sD[r - 1], ml = sM[r - 1];
+            const float db = sD[r + LR_W], mb = sM[r + LR_W];
+            const float dr = sD[r + 1], mr = sM[r + 1];
+            const F3 pc = f3(rx * dc, ry * dc, dc) * mc;
+            const F3 pu = (f3(rx * du, (ry - g.ik11) * du, du) - pc) * mu;
+            const F3 pl = (f3((rx - g.ik00) * dl, ry * dl, dl) - pc) * ml;
+            const F3 pb = (f3(rx * db, (ry + g.ik11) * db, db) - pc) * mb;
+            const F3 pr = (f3((rx + g.ik00) * dr, ry * dr, dr) - pc) * mr;
+            const F3 ns = cross(pu, pl) + cross(pr, pu) + cross(pb, pr) + cross(pl, pb);
+            const float insn = rsqrtf(fmaxf(dot(ns, ns), 1e-24f));
+            const F3 u = ns * insn;
+            d2n = u * mc;
+            const float msum = sMS[i];
+            if (mc > 0.f && msum > 0.f) {
+                const F3 nu = f3(sNU[0][i], sNU[1][i], sNU[2][i]);
+                const float wc = -a.w_cons * msum * inv_cons;                // dL/d(nu . d2n)
+                const F3 gd = nu * wc;                                       // dL/d u  (d2n = u*m2, m2 = 1)
+                const F3 gq = (gd - u * dot(u, gd)) * insn;
+                const F3 dpu = (cross(pl, gq) + cross(gq, pr)) * mu;
+                const F3 dpl = (cross(gq, pu) + cross(pb, gq)) * ml;
+                const F3 dpb = (cross(pr, gq) + cross(gq, pl)) * mb;
+                const F3 dpr = (cross(pu, gq) + cross(gq, pb)) * mr;
+                const F3 dpc = (dpu + dpl + dpb + dpr) * (-mc);
+                a_own = dpc.x * rx + dpc.y * ry + dpc.z;
+                a_up = dpu.x * rx + dpu.y * (ry - g.ik11) + dpu.z;           // zero when mu == 0
+                a_left = dpl.x * (rx - g.ik00) + dpl.y * ry + dpl.z;
+                a_bottom = dpb.x * rx + dpb.y * (ry + g.ik11) + dpb.z;
+                a_right = dpr.x * (rx + g.ik00) + dpr.y * ry + dpr.z;
+            }
+        }
+        sDN[0][i] = d2n.x; sDN[1][i] = d2n.y; sDN[2][i] = d2n.z;
+        sAdj[0][i] = a_own; sAdj[1][i] = a_up; sAdj[2][i] = a_left; sAdj[3][i] = a_bottom; sAdj[4][i] = a_right;
+    }
+    __syncthreads();
+    // ---- phase 2: one thread per pixel of the tile
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    const bool in = (x < W) && (y < H);
+    float fr_rgb = 0.f, fr_d = 0.f, acc_cons = 0.f, acc_tv = 0.f;
     if (in) {
-        const unsigned b1 = f * P, b3 = f * 3u * P, b4 = f * 4u * P;
-        const float msum = __ldg(msum_plane + p);
-        {   // depth gradient: own term (pass A) + what the four neighbours push to this pixel
-            float dd = 0.f;
-            if (y < H - 1) dd += __ldg(nb + b4 + p + (unsigned)W);              // "up" plane of the pixel below
-            if (x < W - 1) dd += __ldg(nb + b4 + P + p + 1u);                   // "left" plane of the pixel to the right
-            if (y > 0) dd += __ldg(nb + b4 + 2u * P + p - (unsigned)W);         // "bottom" plane of the pixel above
-            if (x > 0) dd += __ldg(nb + b4 + 3u * P + p - 1u);                  // "right" plane of the pixel to the left
-            a.d_depth[b1 + p] += dd;
-        }
-        auto NU = [&](unsigned q) { return f3(__ldg(a.normal_unit + b3 + q), __ldg(a.normal_unit + b3 + P + q),
-                                              __ldg(a.normal_unit + b3 + 2u * P + q)); };
-        // all loads of the 5-point stencil up front (clamped coordinates, validity folded into flags)
-        const unsigned qs[4] = {(unsigned)(y * W + min(x + 1, W - 1)), (unsigned)(y * W + max(x - 1, 0)),
-                                (unsigned)(min(y + 1, H - 1) * W + x), (unsigned)(max(y - 1, 0) * W + x)};
-        const float ok[4] = {x < W - 1 ? 1.f : 0.f, x > 0 ? 1.f : 0.f, y < H - 1 ? 1.f : 0.f, y > 0 ? 1.f : 0.f};
-        const F3 nu = NU(p);
-        F3 nq[4];
-        float dq[4], mdq[4];
+        const unsigned p = (unsigned)y * (unsigned)W + (unsigned)x;
+        const unsigned o1 = f * P + p, o3 = f * 3u * P + p;
+        const int e = (threadIdx.y + 1) * LE_W + (threadIdx.x + 1);
+        const int r = (threadIdx.y + 2) * LR_W + (threadIdx.x + 2);
+        const float msum = sMS[e];
+        const float A = __ldg(opac + p);
+        const float mvis = (A > 1e-3f) ? 1.f : 0.f;
+        const float m2 = sM[r];
+        // ---- L1 rgb + gradient
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            nq[k] = NU(qs[k]);
-            dq[k] = __ldg(a.depth + b1 + qs[k]);
-            mdq[k] = (__ldg(a.depth_gt + b1 + qs[k]) > 0.f) ? ok[k] : 0.f;
+        for (unsigned c = 0; c < 3; ++c) {
+            const float er = (__ldg(a.rgb + o3 + c * P) - __ldg(rgb_gt + p + c * P)) * mvis;
+            fr_rgb += fabsf(er);
+            a.d_rgb[o3 + c * P] = (er > 0.f ? 1.f : (er < 0.f ? -1.f : 0.f)) * mvis * inv_rgb;
         }
-        const float dp = __ldg(a.depth + b1 + p);
-        const float md_p = (__ldg(a.depth_gt + b1 + p) > 0.f) ? 1.f : 0.f;
-        const float m2 = (__ldg(a.opacity + b1 + p) > 1e-2f) ? 1.f : 0.f;
-        F3 gnu = f3(__ldg(a.d2n + b3 + p), __ldg(a.d2n + b3 + P + p), __ldg(a.d2n + b3 + 2u * P + p))
-                 * (-a.w_cons * msum * inv_cons);
-        const F3 n = f3(__ldg(a.normal + b3 + p), __ldg(a.normal + b3 + P + p), __ldg(a.normal + b3 + 2u * P + p));
+        // ---- L1 depth + gradient, plus the depth2normal adjoint gathered from the neighbours
+        const float dp = sD[r];
+        const float md_p = sMD[e];
+        const float ed = (dp - __ldg(depth_gt + p)) * md_p;
+        fr_d = fabsf(ed);
+        float dd = a.w_depth * (ed > 0.f ? 1.f : (ed < 0.f ? -1.f : 0.f)) * md_p * inv_d;
+        dd += sAdj[0][e];
+        dd += sAdj[1][e + LE_W];        // "up" share of the pixel below
+        dd += sAdj[2][e + 1];           // "left" share of the pixel to the right
+        dd += sAdj[3][e - LE_W];        // "bottom" share of the pixel above
+        dd += sAdj[4][e - 1];           // "right" share of the pixel to the left   (zero outside the image)
+        a.d_depth[o1] = dd;
+        // ---- consistency loss + normal gradient (consistency + TV, through normalize*mask)
+        const F3 nu = f3(sNU[0][e], sNU[1][e], sNU[2][e]);
+        const F3 d2n = f3(sDN[0][e], sDN[1][e], sDN[2][e]);
+        acc_cons = (1.f - dot(nu, d2n)) * msum;
+        F3 gnu = d2n * (-a.w_cons * msum * inv_cons);
         const float ctv = a.w_tv * inv_tv;
         // each neighbour q contributes the own one-sided difference (mask of p) and the mirrored
         // difference of q that references p (mask of q)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float val, coef;
-            tv_term(nu, nq[k], dp, dq[k], md_p * ok[k], inv2s2, val, coef);
-            acc_tv += val;
-            gnu = gnu + (nu - nq[k]) * (2.f * coef * ctv);
-            tv_term(nq[k], nu, dq[k], dp, mdq[k], inv2s2, val, coef);
-            gnu = gnu - (nq[k] - nu) * (2.f * coef * ctv);
+#define AGS_TV_NEIGHBOUR(EO, RO, OK)                                                        \
+        {                                                                                   \
+            const float okf = (OK) ? 1.f : 0.f;                                             \
+            const F3 nq = f3(sNU[0][e + (EO)], sNU[1][e + (EO)], sNU[2][e + (EO)]);         \
+            const float dq = sD[r + (RO)];                                                  \
+            const float mdq = sMD[e + (EO)] * okf;                                          \
+            float val, coef;                                                                \
+            tv_term(nu, nq, dp, dq, md_p * okf, inv2s2, val, coef);                         \
+            acc_tv += val;                                                                  \
+            gnu = gnu + (nu - nq) * (2.f * coef * ctv);                                     \
+            tv_term(nq, nu, dq, dp, mdq, inv2s2, val, coef);                                \
+            gnu = gnu - (nq - nu) * (2.f * coef * ctv);                                     \
         }
+        AGS_TV_NEIGHBOUR(1, 1, x < W - 1)
+        AGS_TV_NEIGHBOUR(-1, -1, x > 0)
+        AGS_TV_NEIGHBOUR(LE_W, LR_W, y < H - 1)
+        AGS_TV_NEIGHBOUR(-LE_W, -LR_W, y > 0)
+#undef AGS_TV_NEIGHBOUR
+        const F3 n = f3(__ldg(normal + p), __ldg(normal + P + p), __ldg(normal + 2u * P + p));
         const float inn = rsqrtf(fmaxf(dot(n, n), 1e-24f));
         const F3 uh = n * inn;
         const F3 gn = (gnu - uh * dot(uh, gnu)) * (m2 * inn);
-        a.d_normal[b3 + p] = gn.x; a.d_normal[b3 + P + p] = gn.y; a.d_normal[b3 + 2u * P + p] = gn.z;
+        a.d_normal[o3] = gn.x; a.d_normal[o3 + P] = gn.y; a.d_normal[o3 + 2u * P] = gn.z;
+        if (a.normal_unit) { a.normal_unit[o3] = nu.x; a.normal_unit[o3 + P] = nu.y; a.normal_unit[o3 + 2u * P] = nu.z; }
+        if (a.d2n) { a.d2n[o3] = d2n.x; a.d2n[o3 + P] = d2n.y; a.d2n[o3 + 2u * P] = d2n.z; }
     }
-    float v1[1] = {acc_tv * inv_tv};
-    float* const d1[1] = {a.loss_terms + 3};
-    block_accumulate<1>(v1, d1);
+    // loss sums: every term carries the frame weight through its normaliser; the per-frame performance
+    // (track_performance, gaussian_map.py:132-139) is the plain mean
+    float v6[6] = {fr_rgb * inv_rgb, fr_d * inv_d, acc_cons * inv_cons, acc_tv * inv_tv,
+                   fr_rgb / (3.f * (float)P), fr_d / (float)P};
+    float* const d6[6] = {a.loss_terms + 0, a.loss_terms + 1, a.loss_terms + 2, a.loss_terms + 3,
+                          a.loss_terms + 4 + 2 * f, a.loss_terms + 4 + 2 * f + 1};
+    block_accumulate<6>(v6, d6);
 }
 
 // forward-only post-processing of rendered views (planners / eval / GUI): unit normal + d2n
@@ -338,31 +378,40 @@ extern "C" int ags_postprocess(int32_t B, int32_t H, int32_t W, const float* nor
 
 extern "C" size_t ags_loss_scratch_bytes(int32_t B, int32_t H, int32_t W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
-    return ags_align256(((size_t)B * 4 + 1) * H * W * sizeof(float));
+    return ags_align256((size_t)H * W * sizeof(float));       // the (H,W) visibility-sum plane
 }
 
 extern "C" int ags_loss_forward_backward(const AgsLossArgs* a) {
     AGS_CHECK_ARG(a != nullptr, "args is NULL");
-    AGS_CHECK_ARG(a->B > 0 && a->H > 0 && a->W > 0 && a->B_total >= a->B, "bad sizes B=%d H=%d W=%d B_total=%d",
+    AGS_CHECK_ARG(a->B > 0 && a->H > 0 && a->W > 0 && a->B_total >= 1, "bad sizes B=%d H=%d W=%d B_total=%d",
                   a->B, a->H, a->W, a->B_total);
-    AGS_CHECK_ARG(a->rgb && a->normal && a->depth && a->opacity && a->rgb_gt && a->depth_gt && a->tanfov,
-                  "NULL input");
-    AGS_CHECK_ARG(a->normal_unit && a->d2n && a->d_rgb && a->d_normal && a->d_depth && a->loss_terms,
-                  "NULL output");
+    const bool list = a->rgb_gt_frames_host != nullptr || a->depth_gt_frames_host != nullptr;
+    AGS_CHECK_ARG(a->rgb && a->normal && a->depth && a->opacity && a->tanfov, "NULL input");
+    AGS_CHECK_ARG(list ? (a->rgb_gt_frames_host && a->depth_gt_frames_host) : (a->rgb_gt && a->depth_gt),
+                  "ground truth: pass rgb_gt/depth_gt or both *_frames_host lists");
+    AGS_CHECK_ARG(!list || a->B <= AGS_LOSS_MAX_FRAMES, "at most %d frames with per-frame ground-truth pointers", AGS_LOSS_MAX_FRAMES);
+    AGS_CHECK_ARG(a->d_rgb && a->d_normal && a->d_depth && a->loss_terms, "NULL output");
     AGS_CHECK_ARG(a->workspace && a->workspace_bytes >= ags_loss_scratch_bytes(a->B, a->H, a->W),
                   "loss workspace too small");
     AGS_CHECK_ARG((unsigned long long)a->B * 4ull * a->H * a->W < 4294967295ull, "B*4*H*W exceeds 32-bit indexing");
     cudaStream_t st = (cudaStream_t)a->stream;
     AGS_CHECK_CUDA(cudaMemsetAsync(a->loss_terms, 0, (4 + 2 * (size_t)a->B) * sizeof(float), st));
     const size_t P = (size_t)a->H * a->W;
-    float* nb = (float*)a->workspace;                     // (B,4,H,W) neighbour contributions
-    float* msum_plane = nb + (size_t)a->B * 4 * P;        // (H,W) visibility count (quirk Q1)
-    dim3 grid((a->W + 31) / 32, (a->H + 7) / 8, a->B), block(32, 8);
+    float* msum_plane = (float*)a->workspace;             // (H,W) visibility count (quirk Q1)
+    LossFrames fr;
+    memset(&fr, 0, sizeof(fr));
+    if (list)
+        for (int f = 0; f < a->B; ++f) {
+            AGS_CHECK_ARG(a->rgb_gt_frames_host[f] && a->depth_gt_frames_host[f], "NULL ground-truth frame %d", f);
+            fr.rgb[f] = a->rgb_gt_frames_host[f];
+            fr.depth[f] = a->depth_gt_frames_host[f];
+        }
+    dim3 grid((a->W + LT_W - 1) / LT_W, (a->H + LT_H - 1) / LT_H, a->B), block(LT_W, LT_H);
     ags_note_launch(); loss_vis_count<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(*a, msum_plane);
     AGS_CHECK_CUDA(cudaGetLastError());
-    ags_note_launch(); loss_pass_a<<<grid, block, 0, st>>>(*a, nb, msum_plane);
-    AGS_CHECK_CUDA(cudaGetLastError());
-    ags_note_launch(); loss_pass_b<<<grid, block, 0, st>>>(*a, nb, msum_plane);
+    ags_note_launch();
+    if (list) loss_fused_kernel<true><<<grid, block, 0, st>>>(*a, fr, msum_plane);
+    else loss_fused_kernel<false><<<grid, block, 0, st>>>(*a, fr, msum_plane);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -3,8 +3,8 @@
 // Replaces the per-Gaussian stage of the native extension behind
 // /root/reference/utils/operations.py:701-713 and, in RAW mode, the activations of
 // /root/reference/mapping/gaussian_map.py:529-545 (fused here and in the backward).
-// K1 runs one thread per (Gaussian, view) pair with a conservative early cull; K6 one thread per
-// visible pair (compact list).
+// K1: a CTA owns 512 Gaussians for all views (conservative cull per (Gaussian, view) pair, exact
+// projection on the compacted survivors); K6 one thread per visible pair (compact list).
 //
 // HBM roofline: K1 reads 60 B/Gaussian and writes 72+8 B per (view, Gaussian); K6 reads 64 B grad
 // record + 56 B params per visible (view, Gaussian) and writes 56 B/Gaussian. Pure streaming.
@@ -189,113 +189,145 @@ __device__ __forceinline__ void project_view(ViewProj& o, const GaussAct& g, con
 }
 
 // K1 ---------------------------------------------------------------------------------------------
-// One CTA handles 1024 consecutive Gaussians of one view in three phases:
+// One CTA owns 512 consecutive Gaussians for ALL views of the batch: the means are loaded once (two
+// Gaussians per thread) and the views are walked in chunks of K1_VCHUNK cameras staged in shared memory.
+// Per chunk:
 //   1. every (Gaussian, view) pair is tested against a CONSERVATIVE screen-space radius bound that
 //      needs only the mean (and, in ACTIVATED mode, the scales):
 //      a,c <= s_max^2 (f/t_z)^2 (1 + lim^2) + 0.3,  lambda_1 <= a + c + sqrt(0.1)  =>  R_b.
-//      A pair whose tile rect is empty even with R_b cannot be visible (C2: ~85 % of the pairs);
-//      the survivors are compacted into a shared-memory candidate list,
-//   2. the exact projection runs on the compacted candidates only, so the warps that execute the
-//      heavy path are dense even when the visible Gaussians are scattered over the index range,
-//   3. the visible pairs of the CTA are appended to the global compact list (one atomic per CTA)
-//      that drives the scatter and K6.
+//      A pair whose tile rect is empty even with R_b cannot be visible (C2: ~85 % of the pairs); the
+//      survivors are compacted into a shared-memory candidate list (one ballot + one shared atomic per
+//      warp and view),
+//   2. the exact projection (activations fused in RAW mode) runs on the compacted candidates only, so the
+//      warps that execute the heavy path are dense even when the visible Gaussians are scattered over the
+//      index range; per-tile counting with fire-and-forget REDs,
+//   3. the visible pairs of the chunk are appended to the global compact list (one atomic per CTA and
+//      chunk) that drives the scatter and K6.
 constexpr int K1_THREADS = 256;
-#ifndef AGS_K1_PER_THREAD
-#define AGS_K1_PER_THREAD 4
-#endif
-constexpr int K1_PER_THREAD = AGS_K1_PER_THREAD;
-constexpr int K1_PAIRS = K1_THREADS * K1_PER_THREAD;
+constexpr int K1_GPT = 2;                          // Gaussians per thread
+constexpr int K1_G = K1_THREADS * K1_GPT;          // Gaussians per CTA
+constexpr int K1_VCHUNK = 4;                       // views per pass
+constexpr int K1_LIST = K1_G * K1_VCHUNK;          // worst case: every pair of the pass is a candidate
 
 __global__ void __launch_bounds__(K1_THREADS)
 project_fwd_kernel(AgsRenderArgs a, AgsWorkspace w, int for_backward) {
-    __shared__ Cam s_cam;                 // the view is uniform per block (blockIdx.y)
-    __shared__ int s_cand[K1_PAIRS], s_vis[K1_PAIRS];
+    __shared__ Cam s_cam[K1_VCHUNK];
+    __shared__ int s_cand[K1_LIST], s_vis[K1_LIST];
     __shared__ int s_ncand, s_nvis, s_base;
-    const int v = blockIdx.y;
-    const int tid = threadIdx.x;
-    if (tid < 16) {
-        s_cam.V[tid] = __ldg(a.viewmatrix + v * 16 + tid);
-        s_cam.M[tid] = __ldg(a.projmatrix + v * 16 + tid);
-    }
-    if (tid == 32) { s_cam.tanx = __ldg(a.tanfov + v * 2); s_cam.tany = __ldg(a.tanfov + v * 2 + 1); }
-    if (tid == 64) { s_ncand = 0; s_nvis = 0; }
-    __syncthreads();
-    const Cam& cam = s_cam;
-    const float* V = cam.V;
-    const float* M = cam.M;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int tiles_x = (a.W + TILE - 1) / TILE, tiles_y = (a.H + TILE - 1) / TILE;
-    const size_t vN = (size_t)v * a.N;
-    const float fx = a.W / (2.f * cam.tanx), fy = a.H / (2.f * cam.tany);
-    const float kx = fx * fx * (1.f + 1.69f * cam.tanx * cam.tanx), ky = fy * fy * (1.f + 1.69f * cam.tany * cam.tany);
-    // ---- phase 1: conservative cull, compaction of the candidates
-    for (int r = 0; r < K1_PER_THREAD; ++r) {
-        const int i = blockIdx.x * K1_PAIRS + r * K1_THREADS + tid;
-        if (i >= a.N) break;
-        const float mx = __ldg(a.means3D + 3 * i), my = __ldg(a.means3D + 3 * i + 1), mz = __ldg(a.means3D + 3 * i + 2);
-        const float tz = mx * V[2] + my * V[6] + mz * V[10] + V[14];
-        bool maybe = tz > AGS_NEAR_CULL;
-        if (maybe) {
-            float smax;
+    const int g0 = blockIdx.x * K1_G;
+    // the CTA's means, once for all views
+    float mx[K1_GPT], my[K1_GPT], mz[K1_GPT], smax[K1_GPT];
+    bool have[K1_GPT];
+#pragma unroll
+    for (int r = 0; r < K1_GPT; ++r) {
+        const int i = g0 + r * K1_THREADS + tid;
+        have[r] = i < a.N;
+        mx[r] = my[r] = mz[r] = 0.f; smax[r] = 0.f;
+        if (have[r]) {
+            mx[r] = __ldg(a.means3D + 3 * i); my[r] = __ldg(a.means3D + 3 * i + 1); mz[r] = __ldg(a.means3D + 3 * i + 2);
             if (a.param_mode == AGS_PARAMS_RAW) {
-                smax = a.scale_max * a.scale_modifier;
+                smax[r] = a.scale_max * a.scale_modifier;
             } else {
-                smax = fmaxf(fmaxf(fabsf(__ldg(a.scales + 3 * i)), fabsf(__ldg(a.scales + 3 * i + 1))),
-                             fabsf(__ldg(a.scales + 3 * i + 2))) * a.scale_modifier;
-            }
-            const float homx = mx * M[0] + my * M[4] + mz * M[8] + M[12];
-            const float homy = mx * M[1] + my * M[5] + mz * M[9] + M[13];
-            const float homw = mx * M[3] + my * M[7] + mz * M[11] + M[15];
-            const float iw = 1.f / (homw + 1e-7f);
-            const float xg = ((homx * iw + 1.f) * a.W - 1.f) * 0.5f, yg = ((homy * iw + 1.f) * a.H - 1.f) * 0.5f;
-            const float sz = smax / tz;
-            const float Rb = ceilf(3.f * sqrtf(sz * sz * (kx + ky) + 2.f * AGS_LOWPASS + 0.3163f)) * 1.001f + 2.f;
-            if (xg == xg && yg == yg && fabsf(xg) < 1e9f && fabsf(yg) < 1e9f && Rb < 1e9f) {
-                const int minx = min(tiles_x, max(0, (int)((xg - Rb) / TILE)));
-                const int miny = min(tiles_y, max(0, (int)((yg - Rb) / TILE)));
-                const int maxx = min(tiles_x, max(0, (int)((xg + Rb + TILE - 1) / TILE)));
-                const int maxy = min(tiles_y, max(0, (int)((yg + Rb + TILE - 1) / TILE)));
-                maybe = (maxx - minx) * (maxy - miny) > 0;
+                smax[r] = fmaxf(fmaxf(fabsf(__ldg(a.scales + 3 * i)), fabsf(__ldg(a.scales + 3 * i + 1))),
+                                fabsf(__ldg(a.scales + 3 * i + 2))) * a.scale_modifier;
             }
         }
-        if (maybe) s_cand[atomicAdd(&s_ncand, 1)] = i;
-        else a.radii[vN + i] = 0;
     }
-    __syncthreads();
-    // ---- phase 2: exact projection of the candidates
-    const int ncand = s_ncand;
-    for (int c = tid; c < ncand; c += K1_THREADS) {
-        const int i = s_cand[c];
-        const size_t idx = vN + i;
-        GaussAct g;
-        activate(g, a, i);
-        ViewProj p;
-        project_view(p, g, cam, a.H, a.W, a.front_only != 0);
-        a.radii[idx] = p.valid ? p.radius : 0;
-        if (!p.valid) continue;
-        const float conf = a.confidences ? __ldg(a.confidences + i) : 0.f;
-        w.geom0[idx] = make_float4(p.xg, p.yg, p.ca, p.cb);
-        w.geom1[idx] = make_float4(p.cc, g.o, p.sx, p.sy);
-        w.feat0[idx] = make_float4(__ldg(a.colors + 3 * i), __ldg(a.colors + 3 * i + 1),
-                                   __ldg(a.colors + 3 * i + 2), p.t[2]);
-        w.feat1[idx] = make_float4(p.nv[0], p.nv[1], p.nv[2], conf);
-        w.rect[idx] = make_uint2((unsigned)p.minx | ((unsigned)p.maxx << 16),
-                                 (unsigned)p.miny | ((unsigned)p.maxy << 16));
-        if (for_backward) {
-            float4* d = reinterpret_cast<float4*>(w.dsplat + idx * 16);
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            d[0] = z; d[1] = z; d[2] = z; d[3] = z;
+    for (int v0 = 0; v0 < a.B; v0 += K1_VCHUNK) {
+        const int nv = min(K1_VCHUNK, a.B - v0);
+        __syncthreads();                                   // previous pass done with s_cam / lists
+        if (tid < nv * 34) {
+            const int vl = tid / 34, k = tid - vl * 34, v = v0 + vl;
+            if (k < 16) s_cam[vl].V[k] = __ldg(a.viewmatrix + v * 16 + k);
+            else if (k < 32) s_cam[vl].M[k - 16] = __ldg(a.projmatrix + v * 16 + k - 16);
+            else if (k == 32) s_cam[vl].tanx = __ldg(a.tanfov + v * 2);
+            else s_cam[vl].tany = __ldg(a.tanfov + v * 2 + 1);
         }
-        int32_t* tc = w.tile_count + (size_t)v * tiles_x * tiles_y;
-        for (int ty = p.miny; ty < p.maxy; ++ty)
-            for (int tx = p.minx; tx < p.maxx; ++tx) atomicAdd(tc + ty * tiles_x + tx, 1);
-        s_vis[atomicAdd(&s_nvis, 1)] = (int)idx;
+        if (tid == K1_THREADS - 1) { s_ncand = 0; s_nvis = 0; }
+        __syncthreads();
+        // ---- phase 1: conservative cull, compaction of the candidates
+        for (int vl = 0; vl < nv; ++vl) {
+            const Cam& cam = s_cam[vl];
+            const float* V = cam.V;
+            const float* M = cam.M;
+            const float fx = a.W / (2.f * cam.tanx), fy = a.H / (2.f * cam.tany);
+            const float kx = fx * fx * (1.f + 1.69f * cam.tanx * cam.tanx), ky = fy * fy * (1.f + 1.69f * cam.tany * cam.tany);
+            const size_t vN = (size_t)(v0 + vl) * a.N;
+#pragma unroll
+            for (int r = 0; r < K1_GPT; ++r) {
+                bool maybe = false;
+                if (have[r]) {
+                    const float tz = mx[r] * V[2] + my[r] * V[6] + mz[r] * V[10] + V[14];
+                    maybe = tz > AGS_NEAR_CULL;
+                    if (maybe) {
+                        const float homx = mx[r] * M[0] + my[r] * M[4] + mz[r] * M[8] + M[12];
+                        const float homy = mx[r] * M[1] + my[r] * M[5] + mz[r] * M[9] + M[13];
+                        const float homw = mx[r] * M[3] + my[r] * M[7] + mz[r] * M[11] + M[15];
+                        const float iw = 1.f / (homw + 1e-7f);
+                        const float xg = ((homx * iw + 1.f) * a.W - 1.f) * 0.5f, yg = ((homy * iw + 1.f) * a.H - 1.f) * 0.5f;
+                        const float sz = smax[r] / tz;
+                        const float Rb = ceilf(3.f * sqrtf(sz * sz * (kx + ky) + 2.f * AGS_LOWPASS + 0.3163f)) * 1.001f + 2.f;
+                        if (xg == xg && yg == yg && fabsf(xg) < 1e9f && fabsf(yg) < 1e9f && Rb < 1e9f) {
+                            const int minx = min(tiles_x, max(0, (int)((xg - Rb) / TILE)));
+                            const int miny = min(tiles_y, max(0, (int)((yg - Rb) / TILE)));
+                            const int maxx = min(tiles_x, max(0, (int)((xg + Rb + TILE - 1) / TILE)));
+                            const int maxy = min(tiles_y, max(0, (int)((yg + Rb + TILE - 1) / TILE)));
+                            maybe = (maxx - minx) * (maxy - miny) > 0;
+                        }
+                    }
+                    if (!maybe) a.radii[vN + g0 + r * K1_THREADS + tid] = 0;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, maybe);
+                if (m) {
+                    int base = 0;
+                    const int leader = __ffs(m) - 1;
+                    if (lane == leader) base = atomicAdd(&s_ncand, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (maybe) s_cand[base + __popc(m & ((1u << lane) - 1u))] = ((r * K1_THREADS + tid) << 4) | vl;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: exact projection of the candidates
+        const int ncand = s_ncand;
+        for (int c = tid; c < ncand; c += K1_THREADS) {
+            const int code = s_cand[c];
+            const int vl = code & 15, v = v0 + vl;
+            const int i = g0 + (code >> 4);
+            const size_t idx = (size_t)v * a.N + i;
+            GaussAct g;
+            activate(g, a, i);
+            ViewProj p;
+            project_view(p, g, s_cam[vl], a.H, a.W, a.front_only != 0);
+            a.radii[idx] = p.valid ? p.radius : 0;
+            if (!p.valid) continue;
+            const float conf = a.confidences ? __ldg(a.confidences + i) : 0.f;
+            w.geom0[idx] = make_float4(p.xg, p.yg, p.ca, p.cb);
+            w.geom1[idx] = make_float4(p.cc, g.o, p.sx, p.sy);
+            w.feat0[idx] = make_float4(__ldg(a.colors + 3 * i), __ldg(a.colors + 3 * i + 1),
+                                       __ldg(a.colors + 3 * i + 2), p.t[2]);
+            w.feat1[idx] = make_float4(p.nv[0], p.nv[1], p.nv[2], conf);
+            w.rect[idx] = make_uint2((unsigned)p.minx | ((unsigned)p.maxx << 16),
+                                     (unsigned)p.miny | ((unsigned)p.maxy << 16));
+            if (for_backward) {
+                float4* d = reinterpret_cast<float4*>(w.dsplat + idx * 16);
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                d[0] = z; d[1] = z; d[2] = z; d[3] = z;
+            }
+            int32_t* tc = w.tile_count + (size_t)v * tiles_x * tiles_y;
+            for (int ty = p.miny; ty < p.maxy; ++ty)
+                for (int tx = p.minx; tx < p.maxx; ++tx) atomicAdd(tc + ty * tiles_x + tx, 1);
+            s_vis[atomicAdd(&s_nvis, 1)] = (int)idx;
+        }
+        __syncthreads();
+        // ---- phase 3: append to the global visible list
+        const int nvis = s_nvis;
+        if (tid == 0) s_base = nvis ? atomicAdd(w.counters + 1, nvis) : 0;
+        __syncthreads();
+        for (int c = tid; c < nvis; c += K1_THREADS) w.vis_list[s_base + c] = s_vis[c];
     }
-    __syncthreads();
-    // ---- phase 3: append to the global visible list
-    const int nvis = s_nvis;
-    if (tid == 0) s_base = nvis ? atomicAdd(w.counters + 1, nvis) : 0;
-    __syncthreads();
-    for (int c = tid; c < nvis; c += K1_THREADS) w.vis_list[s_base + c] = s_vis[c];
 }
 
 // K6 ---------------------------------------------------------------------------------------------
@@ -488,7 +520,7 @@ project_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
 
 int ags_launch_project_fwd(const AgsRenderArgs& a, const AgsWorkspace& w, bool for_backward) {
     if (a.N == 0) return 0;
-    dim3 grid((a.N + K1_PAIRS - 1) / K1_PAIRS, a.B);
+    dim3 grid((a.N + K1_G - 1) / K1_G);
     ags_note_launch(); project_fwd_kernel<<<grid, K1_THREADS, 0, (cudaStream_t)a.stream>>>(a, w, for_backward ? 1 : 0);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;

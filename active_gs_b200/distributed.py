@@ -101,12 +101,19 @@ class FrameShard:
         return t
 
     def local_batch(self, B_global):
-        if B_global % self.world != 0:
-            raise ValueError(f"global keyframe batch {B_global} must divide by world size {self.world}")
-        return B_global // self.world
+        """frames per rank: the sampled batch is padded to a multiple of the world size (the reference
+        sampler yields T < 8 frames for the first keyframes, mapping/utils.py:196-204); padded slots are
+        rendered from a repeated keyframe with loss weight 0, so every rank enters every exchange"""
+        return max(1, -(-int(B_global) // self.world))
+
+    def pad(self, ids):
+        """ids -> array of local_batch(len(ids)) * world entries, -1 = padding"""
+        ids = [int(i) for i in ids]
+        total = self.local_batch(len(ids)) * self.world
+        return np.asarray(ids + [-1] * (total - len(ids)))
 
     def my_frames(self, ids):
-        """contiguous slice of the (balanced) sampled ids owned by this rank"""
+        """contiguous slice of the (padded, balanced) sampled ids owned by this rank"""
         ids = np.asarray(ids)
         b = len(ids) // self.world
         return ids[self.rank * b:(self.rank + 1) * b]
@@ -121,10 +128,11 @@ class FrameShard:
         partition) so that the slowest rank is as fast as possible: the first `n_active` ids stay at
         their pinned slots, the others are placed longest-first on the least loaded rank with a free
         slot (LPT with a cardinality constraint).  `cost`: id -> instances of its last render (missing
-        ids count as the mean).  Returns the ids reordered so that rank r owns [r*b, (r+1)*b).
+        ids count as the mean).  Returns the ids reordered so that rank r owns [r*b, (r+1)*b), b =
+        local_batch(len(ids)); slots left over when len(ids) is not a multiple of the world size hold -1.
         Deterministic: every rank computes the same answer from the same gathered costs."""
         ids = [int(i) for i in ids]
-        W, b = self.world, len(ids) // self.world
+        W, b = self.world, self.local_batch(len(ids))
         known = [cost[i] for i in ids if i in cost]
         mean = float(np.mean(known)) if known else 0.0
         c = [float(cost.get(i, mean)) for i in ids]
@@ -142,7 +150,7 @@ class FrameShard:
             slots[r][slots[r].index(None)] = ids[j]
             load[r] += c[j]
             free[r] -= 1
-        return np.asarray([i for r in range(W) for i in slots[r]])
+        return np.asarray([(-1 if i is None else i) for r in range(W) for i in slots[r]])      # None = padding
 
     def all_reduce_sum_(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)

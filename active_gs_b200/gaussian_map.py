@@ -119,117 +119,139 @@ class _MapStore:
 
 
 class _TrainEngine:
-    """Preallocated buffers + the fused iteration for one train() call (fixed N, B, H, W)."""
+    """Preallocated buffers + the fused iteration.  Everything that depends only on (B, H, W), the
+    process group and where the keyframes live survives across train() calls (GaussianMap._engine: the
+    reference calls train() once per keyframe with 10 iterations, so per-call set-up is a fixed cost of
+    every update); bind() attaches the current map, whose N changes at every keyframe."""
 
-    def __init__(self, gm, B, H, W, dist_ctx=None, cam_table=None):
+    def __init__(self, gm, B, H, W, dist_ctx=None, on_host=False):
         dev = gm.device
+        self.key = (B, H, W, id(dist_ctx), bool(on_host))
         self.gm, self.B, self.H, self.W, self.dev = gm, B, H, W, dev
         self.dist = dist_ctx
-        self.B_total = B * (dist_ctx.world if dist_ctx else 1)
+        self.world = dist_ctx.world if dist_ctx else 1
+        self.fused = dist_ctx is not None and dist_ctx.fused
+        self.on_host = bool(on_host)
+        o = dict(device=dev, dtype=torch.float32)
+        self.images = (torch.empty(B, 3, H, W, **o), torch.empty(B, 3, H, W, **o), torch.empty(B, 1, H, W, **o),
+                       torch.empty(B, 1, H, W, **o), torch.empty(B, 1, H, W, **o))
+        # host-resident keyframes (bench end-to-end mode): ground-truth staging is double buffered, the
+        # H2D of step i+1 runs on a copy stream while backward/Adam of step i and the forward of step
+        # i+1 execute (only the loss kernel reads the ground truth).  Device-resident keyframes are read
+        # in place through per-frame pointers (no stacked copy).
+        self.gt = None
+        self.gt_k = 0
+        if self.on_host:
+            self.gt = [(torch.empty(B, 3, H, W, **o), torch.empty(B, 1, H, W, **o)) for _ in range(2)]
+            self.copy_stream = torch.cuda.Stream(device=dev)
+            for a, b in self.gt:                       # written on the copy stream, freed on the compute stream
+                a.record_stream(self.copy_stream); b.record_stream(self.copy_stream)
+            self.copy_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.copy_pending = False
+        self.prefetched = [{}, {}]          # per ground-truth buffer: local slot -> keyframe id already staged
+        self.gt_lists = None                # device mode: ([rgb tensors], [depth tensors]) of the staged batch
+        # camera blocks of the batch: one flat device buffer [B*16 view | B*16 proj | B*2 tanfov], gathered
+        # by a kernel from the device table of all keyframes (ids travel as kernel arguments)
+        self.cam_flat = torch.empty(B * 34, **o)
+        self.view = self.cam_flat[:B * 16].view(B, 16)
+        self.proj = self.cam_flat[B * 16:B * 32].view(B, 16)
+        self.tanfov = self.cam_flat[B * 32:].view(B, 2)
+        self.cam_ids = (C.c_int32 * B)()
+        self.frame_w = torch.ones(B, **o)                # 0 marks a padded slot of a sharded batch
+        self.frame_w_host = [1.0] * B
+        self.vis_count = torch.empty(H, W, device=dev, dtype=torch.int32) if dist_ctx else None
+        self.nterm = 2 * B + 4 + B + 2                # loss terms, per-frame perf | per-view instances | (instances, overflow)
+        self.host = torch.empty(self.world * self.nterm, dtype=torch.float32).pin_memory()
+        self.terms_all = torch.empty(self.world * self.nterm, **o) if dist_ctx else None
+        self.terms_loc = torch.empty(self.nterm, **o) if dist_ctx else None
+        self.host_stats = torch.empty(L.AGS_NUM_STATS, dtype=torch.int32).pin_memory()
+        self.event = torch.cuda.Event()
+        self.aux = dist_ctx.aux_buffers(H * W, self.nterm, dev) if self.fused else None
+        self.marks = [] if os.environ.get("AGS_DIST_PROFILE") else None     # (name, event) per segment boundary
+        self.loss_outs = [None, None]       # one per ground-truth buffer (each has its own argument struct)
+        self.loss_out = None
+        self.vis_args = self.terms_args = None
+        self.N = -1
+
+    def bind(self, cam_table, B_total):
+        """attach the map as it is now: parameter / gradient / Adam-state views, fresh Adam state
+        (mapping/gaussian_map.py:259-292: a new optimiser per train() call), the rasterizer workspace"""
+        gm, dev, B, H, W = self.gm, self.dev, self.B, self.H, self.W
         N = gm._means.shape[0]
-        self.N = N
+        self.N, self.B_total = N, int(B_total)
+        self.cam_table = cam_table                       # (T, 34) device: view | proj | tanfov per keyframe
         o = dict(device=dev, dtype=torch.float32)
         self.params = [gm._means, gm._scales, gm._rotations, gm._opacities, gm._harmonics]
         for p in self.params:
             assert p.is_contiguous() and p.dtype == torch.float32
         total = sum(p.numel() for p in self.params)
-        self.fused = dist_ctx is not None and dist_ctx.fused
         self.flat = None
+        self.m = self.v = None
         if self.fused:
             # parameters and gradients live in symmetric (peer-mapped) flat buffers; the GaussianMap
             # tensors become views of the parameter buffer for the duration of train()
-            self.flat = dist_ctx.flat_buffers(total, dev)
+            self.flat = self.dist.flat_buffers(total, dev)
             off, views = 0, []
             for p in self.params:
                 dst = self.flat.param[off:off + p.numel()].view(p.shape)
-                dst.copy_(p)
+                if dst.data_ptr() != p.data_ptr():
+                    dst.copy_(p)
                 views.append(dst)
                 off += p.numel()
             gm._means, gm._scales, gm._rotations, gm._opacities, gm._harmonics = views
             self.params = views
             self.grad_flat = self.flat.grad
-            self.m_flat = torch.zeros(self.flat.numel_padded, **o)
-            self.v_flat = torch.zeros(self.flat.numel_padded, **o)
+            self.m_flat = gm._pool.floats("adam_m", self.flat.numel_padded, zero=True)
+            self.v_flat = gm._pool.floats("adam_v", self.flat.numel_padded, zero=True)
         else:
-            # gradients are views of ONE flat buffer (14 floats per Gaussian): a single all-reduce
-            # in the frame-sharded multi-GPU path
-            self.grad_flat = gm._pool.floats("grad", total)
-        self.grads, off = [], 0
-        for p in self.params:
-            self.grads.append(self.grad_flat[off:off + p.numel()].view(p.shape))
-            off += p.numel()
-        self.m = self.v = None
-        if not self.fused:                       # fresh Adam state every train() call (gaussian_map.py:259-292)
+            # gradients are views of ONE flat buffer (14 floats per Gaussian): a single all-reduce in the
+            # NCCL-baseline sharded path.  Zeroed once here: the Adam kernel re-zeroes what it consumed.
+            self.grad_flat = gm._pool.floats("grad", total, zero=True)
             mf, vf = gm._pool.floats("adam_m", total, zero=True), gm._pool.floats("adam_v", total, zero=True)
             self.m, self.v, off = [], [], 0
             for p in self.params:
                 self.m.append(mf[off:off + p.numel()].view(p.shape))
                 self.v.append(vf[off:off + p.numel()].view(p.shape))
                 off += p.numel()
+        self.grads, off = [], 0
+        for p in self.params:
+            self.grads.append(self.grad_flat[off:off + p.numel()].view(p.shape))
+            off += p.numel()
         self.lrs = [gm.cfg.optimizer.mean_lr, gm.cfg.optimizer.scale_lr, gm.cfg.optimizer.rotation_lr,
                     gm.cfg.optimizer.opacity_lr, gm.cfg.optimizer.harmonic_lr]
         self.step = 0
         self.conf = gm.get_confidences.contiguous()
-        # ground-truth staging is double buffered: with host-resident keyframes the H2D of step i+1
-        # runs on a copy stream while backward/Adam of step i and the forward of step i+1 execute
-        # (only the loss kernel reads the ground truth)
-        self.gt = [(torch.empty(B, 3, H, W, **o), torch.empty(B, 1, H, W, **o)) for _ in range(2)]
-        self.gt_k = 0
-        self.rgb_gt, self.depth_gt = self.gt[0]
-        self.copy_stream = torch.cuda.Stream(device=dev)
-        self.copy_done = [torch.cuda.Event(), torch.cuda.Event()]
-        self.copy_pending = False
-        self.prefetched = [{}, {}]          # per ground-truth buffer: local slot -> keyframe id already staged
-        # camera blocks of the batch: one flat device buffer [B*16 view | B*16 proj | B*2 tanfov]
-        # refreshed by ONE small H2D copy per iteration from a pinned staging buffer
-        self.cam_flat = torch.empty(B * 34, **o)
-        self.view = self.cam_flat[:B * 16].view(B, 16)
-        self.proj = self.cam_flat[B * 16:B * 32].view(B, 16)
-        self.tanfov = self.cam_flat[B * 32:].view(B, 2)
-        self.cam_table = cam_table                       # (T, 34) device: view | proj | tanfov per keyframe
-        self.cam_ids = (C.c_int32 * B)()
         self.bg = gm.background_color.to(dev).float().contiguous()
         cap = gm._inst_cap_hint(N, B)
         self.rb = RenderBatch(gm._means, gm._scales, gm._rotations, gm._opacities,
                               gm._harmonics.reshape(N, 3), self.conf, self.view, self.proj, self.tanfov,
                               self.bg, H, W, param_mode=L.PARAMS_RAW, scale_factor=gm.scale_factor,
                               scale_max=0.05, inst_cap=cap, with_importance=False,
-                              pool=lambda nbytes: gm._pool.get("workspace", nbytes))
+                              pool=lambda nbytes: gm._pool.get("workspace", nbytes), images=self.images)
         # RenderBatch copies nothing for contiguous fp32 inputs, but make the aliasing explicit
         self.rb.inputs = [gm._means, gm._scales, gm._rotations, gm._opacities,
                           gm._harmonics.reshape(N, 3), self.conf]
         self.rb.view = [self.view, self.proj, self.tanfov, self.bg]
         if self.fused:
             self.rb.stats = self.flat.stats          # peers read the overflow flag through NVLink
-        self.loss = None
-        self.loss_out = None
-        self.vis_count = torch.empty(H, W, device=dev, dtype=torch.int32) if dist_ctx else None
-        W_ = dist_ctx.world if dist_ctx else 1
-        self.nterm = 2 * B + 4 + B + 2                # loss terms, per-frame perf | per-view instances | (instances, overflow)
-        self.host = torch.empty(W_ * self.nterm, dtype=torch.float32).pin_memory()
-        self.terms_all = torch.empty(W_ * self.nterm, **o) if dist_ctx else None
-        self.terms_loc = torch.empty(self.nterm, **o) if dist_ctx else None
-        self.host_stats = torch.empty(L.AGS_NUM_STATS, dtype=torch.int32).pin_memory()
-        self.event = torch.cuda.Event()
-        self.aux = self.vis_args = self.terms_args = None
-        self.marks = [] if os.environ.get("AGS_DIST_PROFILE") else None     # (name, event) per segment boundary
-        if self.fused:
-            self.aux = dist_ctx.aux_buffers(H * W, self.nterm, dev)
-        self.fwd_args = self.rb._args()      # argument structs are built once: pointers never change
-        self.grad_args = [None, None]        # one per ground-truth buffer (each has its own loss outputs)
-        self.loss_outs = [None, None]
+        self.fwd_args = self.rb._args()      # argument structs are built once per bind: pointers never change
+        self.grad_args = [None, None]
         self.adam_cache = {}
         self.dist_args = None
+        for lo in self.loss_outs:
+            if lo is not None:
+                lo.args.B_total = self.B_total
+        self.copy_pending = False
+        self.prefetched = [{}, {}]
 
-    def set_batch(self, rgbs, depths, idx, ids=None):
-        """Stage this iteration's keyframes (lists of (3,H,W)/(1,H,W) tensors) and camera blocks
-        (rows `idx` of the device camera table) in the fixed device buffers.  Pinned host frames make
-        this the per-step H2D of the end-to-end path; device frames are gathered with one stack
-        kernel per tensor.  `ids` (keyframe ids of the batch) lets the copy skip frames that
+    def set_batch(self, frames, idx, weights=None, ids=None):
+        """Stage this iteration's keyframes (`frames`: list of B (rgb (3,H,W), depth (1,H,W)) pairs) and
+        camera blocks (rows `idx` of the device camera table).  Device-resident keyframes are only
+        referenced (the loss kernel reads them in place); pinned host frames are uploaded into the
+        double-buffered staging tensors -- the per-step H2D of the host-resident mode.  `weights` (B):
+        0 for padded slots.  `ids` (keyframe ids of the batch) lets the copy skip frames that
         prefetch_next() already staged in this buffer."""
         B = self.B
-        self.gt_k ^= 1
-        self.rgb_gt, self.depth_gt = self.gt[self.gt_k]
         # camera blocks: gathered on the device from the table of all keyframes; the ids travel as
         # kernel arguments (an H2D copy here would queue on the copy engine behind the keyframe
         # uploads and stall the forward)
@@ -238,32 +260,36 @@ class _TrainEngine:
         L.check(L.load().ags_stage_cameras(self.cam_table.data_ptr(), self.cam_table.shape[0], self.cam_ids, B,
                                            self.view.data_ptr(), self.proj.data_ptr(), self.tanfov.data_ptr(),
                                            L.current_stream(self.dev)), "ags_stage_cameras")
-        if rgbs[0].is_cuda:
-            torch.stack(rgbs, out=self.rgb_gt)
-            torch.stack(depths, out=self.depth_gt)
-            self.copy_pending = False
-        else:
-            # buffer gt_k was last read by the loss of step i-2, which finished before fetch(i-1)
-            staged = self.prefetched[self.gt_k]
-            with torch.cuda.stream(self.copy_stream):
-                for k in range(B):
-                    if ids is not None and staged.get(k) == int(ids[k]):
-                        continue
-                    self.rgb_gt[k].copy_(rgbs[k], non_blocking=True)
-                    self.depth_gt[k].copy_(depths[k], non_blocking=True)
-                self.copy_done[self.gt_k].record(self.copy_stream)
-            staged.clear()
-            self.copy_pending = True
+        wl = [1.0] * B if weights is None else [float(x) for x in weights]
+        if wl != self.frame_w_host:
+            self.frame_w.copy_(torch.tensor(wl, dtype=torch.float32), non_blocking=True)
+            self.frame_w_host = wl
+        if not self.on_host:
+            self.gt_lists = ([f[0] for f in frames], [f[1] for f in frames])
+            return
+        self.gt_k ^= 1
+        rgb_gt, depth_gt = self.gt[self.gt_k]
+        # buffer gt_k was last read by the loss of step i-2, which finished before fetch(i-1)
+        staged = self.prefetched[self.gt_k]
+        with torch.cuda.stream(self.copy_stream):
+            for k in range(B):
+                if ids is not None and staged.get(k) == int(ids[k]):
+                    continue
+                rgb_gt[k].copy_(frames[k][0], non_blocking=True)
+                depth_gt[k].copy_(frames[k][1], non_blocking=True)
+            self.copy_done[self.gt_k].record(self.copy_stream)
+        staged.clear()
+        self.copy_pending = True
 
-    def prefetch_next(self, fixed, training_data):
-        """Start the H2D of the NEXT step's keyframes whose ids do not depend on the sampler draw
-        (`fixed`: local batch slot -> keyframe id; the sampler's always-selected active frames,
-        mapping/utils.py:196-204) into the other ground-truth buffer.  Called right after a step is
-        enqueued and before the host waits for its loss terms, so this part of the per-step copy
-        overlaps the forward + loss of the current step; the drawn frames follow in set_batch().
-        The target buffer was last read by the loss of the previous step, which the host has
-        already waited for."""
-        if not fixed or training_data[next(iter(fixed.values()))]["rgb"].is_cuda:
+    def prefetch_next(self, fixed, frame_of):
+        """Host-resident mode: start the H2D of the NEXT step's keyframes whose ids do not depend on the
+        sampler draw (`fixed`: local batch slot -> keyframe id; the sampler's always-selected active
+        frames, mapping/utils.py:196-204) into the other ground-truth buffer.  Called right after a step
+        is enqueued and before the host waits for its loss terms, so this part of the per-step copy
+        overlaps the forward + loss of the current step; the drawn frames follow in set_batch().  The
+        target buffer was last read by the loss of the previous step, which the host has already waited
+        for."""
+        if not fixed or not self.on_host:
             return
         nk = self.gt_k ^ 1
         staged = self.prefetched[nk]
@@ -272,13 +298,20 @@ class _TrainEngine:
         rgb_gt, depth_gt = self.gt[nk]
         with torch.cuda.stream(self.copy_stream):
             for k, fid in fixed.items():
-                rgb_gt[k].copy_(training_data[fid]["rgb"], non_blocking=True)
-                depth_gt[k].copy_(training_data[fid]["depth"], non_blocking=True)
+                rgb, depth = frame_of(fid)
+                rgb_gt[k].copy_(rgb, non_blocking=True)
+                depth_gt[k].copy_(depth, non_blocking=True)
                 staged[k] = int(fid)
+
+    def drain(self):
+        """nothing of this engine may still be in flight on the copy stream when train() returns"""
+        if self.on_host:
+            self.copy_stream.synchronize()
+            self.prefetched = [{}, {}]
 
     def grow(self, need):
         """re-plan the instance capacity after an overflow (nothing was rendered or updated)"""
-        self.rb.inst_cap = int(need * 1.3) + 65536
+        self.rb.inst_cap = min(int(need * 1.3) + 65536, 2 ** 31 - 1)
         self.rb._alloc(L.load())
         self.fwd_args = self.rb._args()
 
@@ -302,15 +335,21 @@ class _TrainEngine:
             # every rank must take the same overflow decision: (instances, overflow) -> MAX.
             # (the fused path reads the peers' flags itself; the host gets them via the gather)
             self.dist.all_reduce_max_(rb.stats[:2])
-            torch.sum(rb.opacity[:, 0] > 1e-3, dim=0, dtype=torch.int32, out=self.vis_count)
+            seen = (rb.opacity[:, 0] > 1e-3) & (self.frame_w[:, None, None] > 0)
+            torch.sum(seen, dim=0, dtype=torch.int32, out=self.vis_count)
             self.dist.all_reduce_sum_(self.vis_count)
             vis = self.vis_count
-        if self.copy_pending:
-            torch.cuda.current_stream(self.dev).wait_event(self.copy_done[self.gt_k])
-        self.loss_outs[self.gt_k] = ops.loss_forward_backward(
-            rb.rgb, rb.normal, rb.depth, rb.opacity, self.rgb_gt, self.depth_gt, self.tanfov,
-            B_total=self.B_total, vis_count=vis, out=self.loss_outs[self.gt_k])
-        lo = self.loss_out = self.loss_outs[self.gt_k]
+        k = self.gt_k if self.on_host else 0
+        if self.on_host:
+            if self.copy_pending:
+                torch.cuda.current_stream(self.dev).wait_event(self.copy_done[k])
+            gts = self.gt[k]
+        else:
+            gts = self.gt_lists
+        self.loss_outs[k] = ops.loss_forward_backward(
+            rb.rgb, rb.normal, rb.depth, rb.opacity, gts[0], gts[1], self.tanfov,
+            B_total=self.B_total, vis_count=vis, out=self.loss_outs[k], frame_weight=self.frame_w, want_maps=False)
+        lo = self.loss_out = self.loss_outs[k]
         self._mark("loss")
         if self.fused:
             self._fused_terms_gather(lib, st, lo)
@@ -327,17 +366,20 @@ class _TrainEngine:
             self.host[:4 + 2 * self.B].copy_(lo.terms, non_blocking=True)
         self.host_stats.copy_(rb.stats, non_blocking=True)
         self.event.record(torch.cuda.current_stream(self.dev))
-        if self.grad_args[self.gt_k] is None:
+        single = self.dist is None
+        if self.grad_args[k] is None:
             g = L.RenderGradArgs()
             g.d_rgb, g.d_normal, g.d_depth = L.ptr(lo.d_rgb), L.ptr(lo.d_normal), L.ptr(lo.d_depth)
             g.d_opacity = g.d_confidence = None
             (g.d_means3D, g.d_scales, g.d_rotations, g.d_opacities, g.d_colors) = [
                 L.ptr(t) for t in self.grads]
             g.d_means2D = None
-            g.accumulate = 0
+            # single GPU: the gradients start at zero (bind) and the Adam kernel zeroes them again as it
+            # consumes them, so the backward accumulates and no separate zeroing pass runs
+            g.accumulate = 1 if single else 0
             g.clear_records = 0                 # exactly one backward per forward in this loop
-            self.grad_args[self.gt_k] = g
-        L.check(lib.ags_render_backward(C.byref(fa), C.byref(self.grad_args[self.gt_k])), "ags_render_backward")
+            self.grad_args[k] = g
+        L.check(lib.ags_render_backward(C.byref(fa), C.byref(self.grad_args[k])), "ags_render_backward")
         self._mark("backward")
         self.step += 1
         if self.fused:
@@ -346,7 +388,8 @@ class _TrainEngine:
         if self.dist is not None:
             self.dist.all_reduce_grads_(self.grads)
         ops.adam_step(self.params, self.grads, self.m, self.v, self.lrs, step=self.step,
-                      skip_flag_ptr=rb.stats.data_ptr() + 4 * L.STAT_OVERFLOW, cache=self.adam_cache)
+                      skip_flag_ptr=rb.stats.data_ptr() + 4 * L.STAT_OVERFLOW, cache=self.adam_cache,
+                      zero_grad=single)
 
     def _mark(self, name):
         if self.marks is not None:
@@ -369,7 +412,8 @@ class _TrainEngine:
         if a is None:
             a = L.DistVisArgs()
             a.world, a.rank, a.B, a.H, a.W = d.world, d.rank, self.B, self.H, self.W
-            a.opacity, a.vis_local, a.vis_count = L.ptr(self.rb.opacity), L.ptr(x.vis), L.ptr(self.vis_count)
+            a.opacity, a.vis_local, a.vis_count = L.ptr(self.images[3]), L.ptr(x.vis), L.ptr(self.vis_count)
+            a.frame_weight = L.ptr(self.frame_w)
             for p in range(d.world):
                 a.vis_peers[p] = x.vis_ptrs[p]
             a.vis_multicast = x.vis_mc if (d.use_multicast and x.vis_mc) else None
@@ -390,11 +434,11 @@ class _TrainEngine:
         if a is None:
             a = L.DistTermsArgs()
             a.world, a.rank, a.nterm, a.nview = d.world, d.rank, self.nterm, self.B
-            a.stats = L.ptr(self.rb.stats)
             for p in range(d.world):
                 a.gather_peers[p] = x.gather_ptrs[p]
             a.gather_multicast = x.gather_mc if (d.use_multicast and x.gather_mc) else None
             self.terms_args = a
+        a.stats = L.ptr(self.rb.stats)
         a.terms = L.ptr(lo.terms)
         a.stream = st
         L.check(lib.ags_dist_terms_put(C.byref(a)), "ags_dist_terms_put")
@@ -440,7 +484,7 @@ class _TrainEngine:
         h = self.host.clone().view(-1, self.nterm)          # one row per rank
         terms = h[:, :4].sum(0)                             # every rank's terms are already / B_total
         pf = h[:, 4:4 + 2 * B]
-        perf = (pf[:, 0::2] + pf[:, 1::2]).reshape(-1)      # ordered like the sampled ids
+        perf = (pf[:, 0::2] + pf[:, 1::2]).reshape(-1)      # ordered like the (padded) batch
         stats = self.host_stats.to(torch.int64)
         nt = 4 + 2 * B
         if self.dist is not None:                           # global view: max instances, any overflow
@@ -477,6 +521,8 @@ class GaussianMap:
         self._pool = _BufferPool(self.device)
         self._store = _MapStore(self.device)
         self._cams = []                      # per keyframe: host camera products, computed once
+        self._gt_cache = []                  # per keyframe: (source rgb, source depth, training rgb, training depth)
+        self._engine = None                  # _TrainEngine, kept across train() calls
         self._frame_cost = {}                # keyframe id -> instances of its last training render
         if cfg is not None:
             self.cfg = cfg
@@ -518,9 +564,31 @@ class GaussianMap:
         """(len(ids), 34) host tensor of camera rows"""
         return torch.stack([self._camera(i)["row"] for i in ids])
 
+    def _frame_gt(self, i):
+        """(rgb (3,H,W), depth (1,H,W)) of keyframe i as the training loop reads them: contiguous fp32, on
+        the device unless the map keeps its keyframes in pinned host memory (frames_on_host).  Converted
+        copies are cached per keyframe (the reference moves every dataframe to the device once,
+        mapping/mapper.py:95)."""
+        f = self.training_data[i]
+        while len(self._gt_cache) <= i:
+            self._gt_cache.append(None)
+        c = self._gt_cache[i]
+        if c is not None and c[0] is f["rgb"] and c[1] is f["depth"]:
+            return c[2], c[3]
+
+        def conv(t):
+            if self.frames_on_host:
+                t = t.detach().float().contiguous().cpu()
+                return t if t.is_pinned() else t.pin_memory()
+            return t.detach().to(self.device, torch.float32).contiguous()
+
+        rgb, depth = conv(f["rgb"]), conv(f["depth"])
+        self._gt_cache[i] = (f["rgb"], f["depth"], rgb, depth)
+        return rgb, depth
+
     def begin_training(self):
         """Everything train() sets up once per call (mapping/gaussian_map.py:71-74): fresh Adam
-        state, the sampler, the camera table of all keyframes, and the preallocated engine."""
+        state, the sampler, the camera table of all keyframes, and the (persistent) engine."""
         from types import SimpleNamespace
         T = len(self.training_data)
         self._make_contiguous()
@@ -538,11 +606,14 @@ class GaussianMap:
                 r, k = self.dist.pinned_slot(j)
                 if r == self.dist.rank:
                     fixed[k] = int(fid)
-        return SimpleNamespace(fixed=fixed,
-            sampler=sampler, B=B, H=H, W=W,
-            eng=_TrainEngine(self, B, H, W, self.dist,
-                             cam_table=cam_rows.to(self.device)),
-            perf_host=self.training_performance.detach().float().cpu().clone(), log=[])
+        on_host = bool(self.frames_on_host)
+        key = (B, H, W, id(self.dist), on_host)
+        eng = self._engine
+        if eng is None or eng.key != key:
+            eng = self._engine = _TrainEngine(self, B, H, W, self.dist, on_host=on_host)
+        eng.bind(cam_rows.to(self.device), sampler.v)
+        return SimpleNamespace(fixed=fixed, sampler=sampler, B=B, H=H, W=W, eng=eng,
+                               perf_host=self.training_performance.detach().float().cpu().clone(), log=[])
 
     def train_step(self, ctx, ids=None):
         """One iteration of mapping/gaussian_map.py:76-127: sample keyframes, stage them, enqueue
@@ -550,18 +621,26 @@ class GaussianMap:
         eng = ctx.eng
         sampled = ids is None
         ids = np.asarray(ids) if ids is not None else ctx.sampler.next_ids(ctx.perf_host)
-        if self.dist is not None and sampled:
-            # same keyframes, load-balanced partition over the ranks (cost = instances of the last render)
-            ids = self.dist.balance(ids, len(ctx.sampler.active_ids), self._frame_cost)
-        my = ids if self.dist is None else self.dist.my_frames(ids)
-        idx = torch.as_tensor(my, dtype=torch.long)
-        eng.set_batch([self.training_data[i]["rgb"] for i in my],
-                      [self.training_data[i]["depth"] for i in my],
-                      idx, ids=my)
+        weights = None
+        if self.dist is not None:
+            # same keyframes on every rank; the batch is padded to a multiple of the world size (-1 =
+            # padding: rendered from a repeated keyframe with loss weight 0) and, when the sampler drew
+            # it, partitioned over the ranks by cost (instances of the last render)
+            if sampled:
+                ids = self.dist.balance(ids, len(ctx.sampler.active_ids), self._frame_cost)
+            else:
+                ids = self.dist.pad(ids)
+            my = self.dist.my_frames(ids)
+            weights = [1.0 if i >= 0 else 0.0 for i in my]
+            filler = int(ids[ids >= 0][0])
+            my = np.asarray([i if i >= 0 else filler for i in my])
+        else:
+            my = ids
+        eng.set_batch([self._frame_gt(int(i)) for i in my], my, weights=weights, ids=my)
         while True:
             eng.iterate()
             if sampled:
-                eng.prefetch_next(ctx.fixed, self.training_data)
+                eng.prefetch_next(ctx.fixed, self._frame_gt)
             terms, perf, stats, view_cost = eng.fetch()
             if stats[L.STAT_OVERFLOW] == 0:
                 break
@@ -571,14 +650,18 @@ class GaussianMap:
             eng.grow(int(stats[L.STAT_INSTANCES]))
         need = float(stats[L.STAT_INSTANCES]) / max(1, eng.N * ctx.B)
         self._cap_per_gaussian = max(self._cap_per_gaussian, 1.5 * need)
-        ctx.perf_host[torch.as_tensor(ids, dtype=torch.long)] = perf
-        for i, c in zip(ids.tolist(), view_cost.tolist()):
+        real = ids >= 0
+        rid = torch.as_tensor(ids[real], dtype=torch.long)
+        perf = perf[torch.as_tensor(real)]
+        ctx.perf_host[rid] = perf
+        for i, c in zip(ids[real].tolist(), view_cost[torch.as_tensor(real)].tolist()):
             self._frame_cost[int(i)] = c
         loss = float(terms[0] + 0.8 * terms[1] + 0.1 * terms[2] + 0.1 * terms[3])
         ctx.log.append((loss, perf.clone(), int(stats[L.STAT_INSTANCES]), int(stats[L.STAT_VISIBLE])))
         return loss
 
     def end_training(self, ctx):
+        ctx.eng.drain()
         self.training_performance = ctx.perf_host.to(self.device)
         self.last_train_log = ctx.log
 
@@ -673,6 +756,10 @@ class GaussianMap:
         rgb = dataframe["rgb"].to(dev).float().contiguous()
         depth = dataframe["depth"].to(dev).float().contiguous()
         _, H, W = rgb.shape
+        if not self.frames_on_host and not (dataframe["rgb"].is_cuda and dataframe["depth"].is_cuda):
+            # keyframes stay resident in HBM: the H2D of a keyframe happens once, here
+            # (the reference: mapping/mapper.py:95)
+            dataframe = {**dataframe, "rgb": rgb, "depth": depth}
         self.training_data.append(dataframe)
         self.training_performance = torch.cat(
             (self.training_performance, torch.tensor([10.0], device=dev)), 0)
@@ -684,6 +771,7 @@ class GaussianMap:
             self._make_contiguous()
             rb = self._render_raw([k], H, W)
             pred = (rb.rgb, rb.depth, rb.opacity)
+            self._frame_cost[k] = float(rb.last_instances)      # seeds the cost-balanced frame partition
         n_old = self._means.shape[0]
         st = self._store
         seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())

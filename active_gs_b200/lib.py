@@ -53,6 +53,8 @@ class LossArgs(C.Structure):
         ("loss_terms", _f),
         ("w_depth", C.c_float), ("w_cons", C.c_float), ("w_tv", C.c_float),
         ("workspace", _f), ("workspace_bytes", C.c_size_t), ("stream", _f),
+        ("frame_weight", _f), ("rgb_gt_frames_host", C.POINTER(C.c_void_p)),
+        ("depth_gt_frames_host", C.POINTER(C.c_void_p)),
     ]
 
 
@@ -64,6 +66,7 @@ class AdamArgs(C.Structure):
         ("lr", C.c_float * ADAM_GROUPS),
         ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
         ("step", C.c_int32), ("step_dev", _f), ("skip_flag", _f), ("stream", _f),
+        ("zero_grad", C.c_int32),
     ]
 
 
@@ -84,7 +87,7 @@ class DistVisArgs(C.Structure):
     _fields_ = [
         ("world", C.c_int32), ("rank", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("opacity", _f), ("vis_local", _f), ("vis_peers", _f * MAX_PEERS), ("vis_multicast", _f),
-        ("vis_count", _f), ("stream", _f),
+        ("vis_count", _f), ("stream", _f), ("frame_weight", _f),
     ]
 
 

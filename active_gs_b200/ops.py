@@ -7,7 +7,7 @@ from . import lib as L
 
 
 class LossResult:
-    __slots__ = ("normal_unit", "d2n", "d_rgb", "d_normal", "d_depth", "terms", "workspace", "args", "keep")
+    __slots__ = ("normal_unit", "d2n", "d_rgb", "d_normal", "d_depth", "terms", "workspace", "args", "keep", "gt_ptrs")
 
     def total(self, w_depth=0.8, w_cons=0.1, w_tv=0.1):
         t = self.terms
@@ -19,22 +19,33 @@ class LossResult:
 
 
 def loss_forward_backward(rgb, normal, depth, opacity, rgb_gt, depth_gt, tanfov, *, B_total=None,
-                          vis_count=None, w_depth=0.8, w_cons=0.1, w_tv=0.1, out=None):
+                          vis_count=None, w_depth=0.8, w_cons=0.1, w_tv=0.1, out=None, frame_weight=None,
+                          want_maps=True):
     """Post-processing + loss + gradients for a batch of rendered frames (all (B,C,H,W) CUDA fp32).
-    `tanfov` is (B,2) tan(fov/2).  Returns a LossResult; `terms` = [L_rgb, L_depth, L_cons, L_tv,
+    `tanfov` is (B,2) tan(fov/2).  `rgb_gt` / `depth_gt`: stacked (B,3,H,W) / (B,1,H,W) tensors, or LISTS
+    of B per-frame tensors (3,H,W) / (1,H,W), read in place (no stacked copy).  `frame_weight` (B) float:
+    0 marks a padded frame that contributes nothing.  `want_maps=False` skips the normal_unit / d2n outputs
+    (the training loop never reads them).  Returns a LossResult; `terms` = [L_rgb, L_depth, L_cons, L_tv,
     (rgb_f, depth_f) per frame].  Passing `out` (a previous result) reuses all buffers and the cached
-    argument struct (the training loop calls this with fixed pointers every iteration)."""
+    argument struct (the training loop calls this with fixed pointers every iteration); with ground-truth
+    lists the per-frame pointers are refreshed from the lists given."""
     lib = L.load()
+    as_list = isinstance(rgb_gt, (list, tuple))
     if out is not None and getattr(out, "args", None) is not None:
-        out.args.stream = L.current_stream(rgb.device)
-        L.check(lib.ags_loss_forward_backward(C.byref(out.args)), "ags_loss_forward_backward")
+        a = out.args
+        if as_list:
+            for k in range(a.B):
+                out.gt_ptrs[0][k], out.gt_ptrs[1][k] = L.ptr(rgb_gt[k]), L.ptr(depth_gt[k])
+            out.keep = out.keep[:7] + (list(rgb_gt), list(depth_gt))
+        a.stream = L.current_stream(rgb.device)
+        L.check(lib.ags_loss_forward_backward(C.byref(a)), "ags_loss_forward_backward")
         return out
     B, _, H, W = rgb.shape
     dev = rgb.device
     r = LossResult()
     o = dict(device=dev, dtype=torch.float32)
-    r.normal_unit = torch.empty(B, 3, H, W, **o)
-    r.d2n = torch.empty(B, 3, H, W, **o)
+    r.normal_unit = torch.empty(B, 3, H, W, **o) if want_maps else None
+    r.d2n = torch.empty(B, 3, H, W, **o) if want_maps else None
     r.d_rgb = torch.empty(B, 3, H, W, **o)
     r.d_normal = torch.empty(B, 3, H, W, **o)
     r.d_depth = torch.empty(B, 1, H, W, **o)
@@ -44,8 +55,18 @@ def loss_forward_backward(rgb, normal, depth, opacity, rgb_gt, depth_gt, tanfov,
     a.B, a.H, a.W = B, H, W
     a.B_total = int(B_total or B)
     a.rgb, a.normal, a.depth, a.opacity = L.ptr(rgb), L.ptr(normal), L.ptr(depth), L.ptr(opacity)
-    a.rgb_gt, a.depth_gt, a.tanfov = L.ptr(rgb_gt), L.ptr(depth_gt), L.ptr(tanfov)
+    a.tanfov = L.ptr(tanfov)
+    r.gt_ptrs = None
+    if as_list:
+        r.gt_ptrs = ((C.c_void_p * B)(), (C.c_void_p * B)())
+        for k in range(B):
+            r.gt_ptrs[0][k], r.gt_ptrs[1][k] = L.ptr(rgb_gt[k]), L.ptr(depth_gt[k])
+        a.rgb_gt_frames_host = C.cast(r.gt_ptrs[0], C.POINTER(C.c_void_p))
+        a.depth_gt_frames_host = C.cast(r.gt_ptrs[1], C.POINTER(C.c_void_p))
+    else:
+        a.rgb_gt, a.depth_gt = L.ptr(rgb_gt), L.ptr(depth_gt)
     a.vis_count = L.ptr(vis_count)
+    a.frame_weight = L.ptr(frame_weight)
     a.normal_unit, a.d2n = L.ptr(r.normal_unit), L.ptr(r.d2n)
     a.d_rgb, a.d_normal, a.d_depth = L.ptr(r.d_rgb), L.ptr(r.d_normal), L.ptr(r.d_depth)
     a.loss_terms = L.ptr(r.terms)
@@ -53,13 +74,14 @@ def loss_forward_backward(rgb, normal, depth, opacity, rgb_gt, depth_gt, tanfov,
     a.workspace, a.workspace_bytes = L.ptr(r.workspace), r.workspace.numel()
     a.stream = L.current_stream(dev)
     r.args = a
-    r.keep = (rgb, normal, depth, opacity, rgb_gt, depth_gt, tanfov, vis_count)   # pointers stay valid
+    r.keep = (rgb, normal, depth, opacity, tanfov, vis_count, frame_weight,
+              list(rgb_gt) if as_list else rgb_gt, list(depth_gt) if as_list else depth_gt)   # pointers stay valid
     L.check(lib.ags_loss_forward_backward(C.byref(a)), "ags_loss_forward_backward")
     return r
 
 
 def adam_step(params, grads, exp_avgs, exp_avg_sqs, lrs, step=None, step_dev=None,
-              betas=(0.9, 0.999), eps=1e-15, skip_flag_ptr=None, cache=None):
+              betas=(0.9, 0.999), eps=1e-15, skip_flag_ptr=None, cache=None, zero_grad=False):
     """One fused Adam step over up to 5 groups (in place on params / exp_avg / exp_avg_sq).
     `cache` (a dict) keeps the argument struct between calls with identical tensors."""
     lib = L.load()
@@ -81,6 +103,7 @@ def adam_step(params, grads, exp_avgs, exp_avg_sqs, lrs, step=None, step_dev=Non
     a.step = int(step or 0)
     a.step_dev = L.ptr(step_dev)
     a.skip_flag = skip_flag_ptr
+    a.zero_grad = int(bool(zero_grad))
     a.stream = L.current_stream(params[0].device)
     if cache is not None:
         cache["a"] = a

@@ -55,7 +55,7 @@ class RenderBatch:
                  projmatrix, tanfov, bg, H, W, *, render_mask=None, scale_modifier=1.0,
                  weight_thres=0.03, require_importance=False, front_only=False,
                  param_mode=L.PARAMS_ACTIVATED, scale_factor=0.01, scale_max=0.05, inst_cap=None,
-                 with_importance=True, pool=None):
+                 with_importance=True, pool=None, images=None):
         lib = L.load()
         dev = means3D.device
         if dev.type != "cuda":
@@ -75,11 +75,14 @@ class RenderBatch:
         if render_mask is not None and render_mask.numel() > 0:
             self.mask = _f32c(render_mask).reshape(B, self.H, self.W)
         o = dict(device=dev, dtype=torch.float32)
-        self.rgb = torch.empty(B, 3, H, W, **o)
-        self.normal = torch.empty(B, 3, H, W, **o)
-        self.depth = torch.empty(B, 1, H, W, **o)
-        self.opacity = torch.empty(B, 1, H, W, **o)
-        self.confidence = torch.empty(B, 1, H, W, **o)
+        if images is not None:           # preallocated (B,C,H,W) outputs of a persistent training engine
+            self.rgb, self.normal, self.depth, self.opacity, self.confidence = images
+        else:
+            self.rgb = torch.empty(B, 3, H, W, **o)
+            self.normal = torch.empty(B, 3, H, W, **o)
+            self.depth = torch.empty(B, 1, H, W, **o)
+            self.opacity = torch.empty(B, 1, H, W, **o)
+            self.confidence = torch.empty(B, 1, H, W, **o)
         # optional outputs (all-zero unless require_importance): the training engine skips them
         with_importance = with_importance or require_importance
         self.importance = torch.empty(B, N, **o) if with_importance else None
@@ -136,9 +139,11 @@ class RenderBatch:
         larger workspace if the batch needed more instances than `inst_cap`."""
         lib = L.load()
         L.check(lib.ags_render_forward(C.byref(self._args())), "ags_render_forward")
+        self.last_instances = 0
         if check_overflow:
             st = self.stats.tolist()
             need = st[L.STAT_INSTANCES]
+            self.last_instances = need
             if st[L.STAT_OVERFLOW]:
                 self.inst_cap = min(int(need * 1.25) + 4096, INT32_MAX)
                 self._alloc(lib)

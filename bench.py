@@ -31,6 +31,7 @@ from active_gs_b200.config import default_gaussian_map_config  # noqa: E402
 CONFIG_IDX = 2          # BASELINE.json config[1] (the headline workload); --config 3 / 5 select the
 B_PER_GPU = 8           # larger parity configurations (not the headline line)
 METRIC, UNIT = "train_mpix_per_s", "Mpix/s"
+AGS_STATS_BYTES = 72 * 4
 WORKLOAD_C2 = ("BASELINE config[1]: office0-shaped room, 200k Gaussian surfels, 640x480, "
                "train-loop iteration (render 8 keyframes fwd+bwd, 4-term loss, Adam)")
 
@@ -108,29 +109,30 @@ def bind_to_gpu_numa_node(local_rank):
         return f"NUMA binding skipped: {e}"
 
 
-def build_workload(dev, rank, world, seed_base=1000 + CONFIG_IDX):
+def build_workload(dev, rank, world, seed_base=1000 + CONFIG_IDX, extra=0):
     """Scene + 8*world keyframes (rendered from the generating scene with our own renderer, then
-    depth noise) + the perturbed start state.  Deterministic; identical on every rank."""
+    depth noise) + `extra` further keyframes (the new keyframes of the end-to-end update loop) + the
+    perturbed start state.  Deterministic; identical on every rank."""
     from active_gs_b200 import operations as O
     from active_gs_b200.gaussian_map import GaussianMap
     box, H, W, N = syn.ROOMS[CONFIG_IDX]
     T = B_PER_GPU * world
     state = syn.make_room_scene(N, box=box, seed=seed_base)
-    ext, K = syn.make_cameras(T, box=box, H=H, W=W, seed=seed_base + 1000)
+    ext, K = syn.make_cameras(T + extra, box=box, H=H, W=W, seed=seed_base + 1000)
     cfg = default_gaussian_map_config()
     cfg.sampler.batch_size = T
     gm = GaussianMap(cfg, dev)
     load_state(gm, state, dev)
     frames = []
     with torch.no_grad():
-        for i in range(T):
+        for i in range(T + extra):
             out = O.GaussianRenderer(ext[i:i + 1].to(dev), K[i:i + 1].to(dev), gm.get_attr(), gm.background_color,
                                      (gm.scene_near, gm.scene_far), (H, W), dev).render_view_all()
             depth = syn.noisy_depth(out[1][0].cpu(), seed=4000 + i)
             frames.append(dict(rgb=out[0][0].clamp(0, 1).cpu(), depth=depth, extrinsic=ext[i], intrinsic=K[i],
                                depth_range=torch.tensor([0.0, 5.0])))
     start = syn.perturb_state(state, seed=seed_base + 2000)
-    return state, start, frames, cfg, (H, W, N, T)
+    return state, start, frames[:T], frames[T:], cfg, (H, W, N, T)
 
 
 def load_state(gm, state, dev):
@@ -153,37 +155,42 @@ def fresh_map(cfg, start, frames, dev, on_host, shard):
     return gm
 
 
-def stage_profile(eng, reps=5):
+def stage_profile(eng, reps=5, with_adam=True):
     """Average device time of every kernel of one step, CUDA events on the launching stream."""
     import ctypes as C
     from active_gs_b200 import lib as L, ops
     lib = L.load()
     rb = eng.rb
-    names = ["clear", "project_fwd", "binning", "composite_fwd", "loss", "composite_bwd", "project_bwd", "adam"]
+    names = ["clear", "project_fwd", "binning", "composite_fwd", "loss", "composite_bwd", "project_bwd"] + (
+        ["adam"] if with_adam else [])
     acc = {n: 0.0 for n in names}
     st = torch.cuda.current_stream()
+    k = eng.gt_k if eng.on_host else 0
+    gts = eng.gt[k] if eng.on_host else eng.gt_lists
     for _ in range(reps):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
         a = rb._args()
         ev[0].record(st)
-        for k, stage in enumerate([0, 1, 2, 3]):
+        for j, stage in enumerate([0, 1, 2, 3]):
             L.check(lib.ags_render_stage(C.byref(a), None, stage), "stage")
-            ev[k + 1].record(st)
-        eng.loss_out = eng.loss_outs[eng.gt_k] = ops.loss_forward_backward(
-            rb.rgb, rb.normal, rb.depth, rb.opacity, eng.rgb_gt, eng.depth_gt, eng.tanfov, B_total=eng.B_total,
-            out=eng.loss_outs[eng.gt_k])
+            ev[j + 1].record(st)
+        eng.loss_out = eng.loss_outs[k] = ops.loss_forward_backward(
+            rb.rgb, rb.normal, rb.depth, rb.opacity, gts[0], gts[1], eng.tanfov, B_total=eng.B_total,
+            out=eng.loss_outs[k], frame_weight=eng.frame_w, want_maps=False)
         ev[5].record(st)
         lo = eng.loss_out
         g = L.RenderGradArgs()
         g.d_rgb, g.d_normal, g.d_depth = L.ptr(lo.d_rgb), L.ptr(lo.d_normal), L.ptr(lo.d_depth)
         (g.d_means3D, g.d_scales, g.d_rotations, g.d_opacities, g.d_colors) = [L.ptr(t) for t in eng.grads]
+        g.accumulate = 1 if with_adam else 0
         L.check(lib.ags_render_stage(C.byref(a), C.byref(g), 4), "stage"); ev[6].record(st)
         L.check(lib.ags_render_stage(C.byref(a), C.byref(g), 5), "stage"); ev[7].record(st)
-        eng.step += 1
-        ops.adam_step(eng.params, eng.grads, eng.m, eng.v, eng.lrs, step=eng.step); ev[8].record(st)
+        if with_adam:
+            eng.step += 1
+            ops.adam_step(eng.params, eng.grads, eng.m, eng.v, eng.lrs, step=eng.step, zero_grad=True); ev[8].record(st)
         torch.cuda.synchronize()
-        for k, n in enumerate(names):
-            acc[n] += ev[k].elapsed_time(ev[k + 1])
+        for j, n in enumerate(names):
+            acc[n] += ev[j].elapsed_time(ev[j + 1])
     return {n: v / reps for n, v in acc.items()}
 
 
@@ -260,7 +267,10 @@ def run_ours(args, rank, world, local_rank):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()                      # nvidia-smi takes a moment to start: launch it early
-    state, start, frames, cfg, (H, W, N, T) = build_workload(dev, rank, world)
+    ITERS = 10                               # optimisation iterations per update (incremental.yaml:18)
+    n_upd = max(1, args.steps // ITERS)      # timed updates of the end-to-end arm
+    WARM_UPD = 2
+    state, start, frames, new_frames, cfg, (H, W, N, T) = build_workload(dev, rank, world, extra=n_upd + WARM_UPD)
     B = B_PER_GPU
     P = H * W
 
@@ -274,7 +284,9 @@ def run_ours(args, rank, world, local_rank):
     np.random.seed(1234)
     gm = fresh_map(cfg, start, frames, dev, on_host=False, shard=shard)
     ctx = gm.begin_training()
-    for _ in range(args.warmup):
+    # W untimed warm-up steps as asked, and never fewer than 10: the first iterations still learn the
+    # instance capacity and (multi-GPU) the per-keyframe costs the partition is balanced with
+    for _ in range(max(args.warmup, 10)):
         gm.train_step(ctx)
     barrier()
     clocks.mark_begin()
@@ -294,22 +306,36 @@ def run_ours(args, rank, world, local_rank):
     inst = int(np.mean([l[2] for l in ctx.log[-args.steps:]]))
     vis = int(np.mean([l[3] for l in ctx.log[-args.steps:]]))
     loss_first, loss_last = ctx.log[0][0], ctx.log[-1][0]
-    stages = stage_profile(ctx.eng) if world == 1 else None
+    stages = stage_profile(ctx.eng, with_adam=(world == 1))      # no collective inside: every rank runs it
     clk = clocks.stop() if rank == 0 else None
+    gm.end_training(ctx)
 
-    # ---------------- end-to-end arm: the public call GaussianMap.train(steps=K) with the
-    # keyframes in pinned HOST memory (per step: H2D of the 8 sampled frames, D2H of the loss terms)
-    np.random.seed(1234)
-    gm2 = fresh_map(cfg, start, frames, dev, on_host=True, shard=shard)
-    gm2.train(steps=max(1, args.warmup))
-    barrier()
-    gm2 = fresh_map(cfg, start, frames, dev, on_host=True, shard=shard)
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    gm2.train(steps=args.steps)
-    f1.record()
-    barrier()
+    # ---------------- end-to-end arm: the public call GaussianMap.update(dataframe) -- what
+    # mapping/mapper.py:95-101 does per keyframe -- on NEW keyframes that arrive in pinned HOST memory:
+    # H2D of the keyframe (it then stays resident in HBM, as in the reference), spawn, ITERS
+    # optimisation iterations over the sampled batch (D2H of the loss terms every iteration, the
+    # sampler needs them), confidence bookkeeping / prune.  Engine and buffers persist across updates;
+    # WARM_UPD untimed updates first.
+    np.random.seed(1234); torch.manual_seed(1234)
+    gm2 = fresh_map(cfg, start, frames, dev, on_host=False, shard=shard)
+    gm2.is_init = True
+    iters = ITERS if args.steps >= ITERS else args.steps
+    gm2.optimization_steps = iters
+    host_new = [{k: (v.pin_memory() if k in ("rgb", "depth") else v) for k, v in f.items()} for f in new_frames]
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):               # prune() prints like the reference
+        for f in host_new[:WARM_UPD]:
+            gm2.update(f)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for f in host_new[WARM_UPD:WARM_UPD + n_upd]:
+            gm2.update(f)
+        f1.record()
+        barrier()
     ms_e2e = f0.elapsed_time(f1)
+    steps_e2e = iters * n_upd
+    n_end = int(gm2._means.shape[0])
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -319,7 +345,7 @@ def run_ours(args, rank, world, local_rank):
         return None
     Bg = B * world
     value = Bg * P * args.steps / (ms / 1e3) / 1e6
-    e2e = Bg * P * args.steps / (ms_e2e / 1e3) / 1e6
+    e2e = Bg * P * steps_e2e / (ms_e2e / 1e3) / 1e6
     peaks, which = measured_peaks()
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     line = {
@@ -335,16 +361,20 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "inputs+outputs per step (~%.0f MB) exceed the 126 MB L2; no explicit flush"
                          % ((88 * B * P + 136 * inst + 500 * N) / 1e6),
                    "loss_first": loss_first, "loss_last": loss_last},
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * P * 16 + B * 36 * 4,
-                "d2h_bytes_per_step": (4 + 2 * B) * 4 + 32, "ms_per_step": ms_e2e / args.steps,
-                "what": "GaussianMap.train(steps=K) incl. engine set-up and post_processing, keyframes in pinned host memory"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": (P * 16 + 34 * 4 * (T + n_upd)) // iters,
+                "d2h_bytes_per_step": (4 + 2 * B) * 4 + AGS_STATS_BYTES + 16 // iters, "ms_per_step": ms_e2e / steps_e2e,
+                "steps": steps_e2e, "updates": n_upd, "gaussians_end": n_end,
+                "what": "GaussianMap.update(dataframe) per NEW keyframe from pinned host memory (mapper.py:95-101): H2D of the "
+                        "keyframe (resident in HBM afterwards), spawn, %d iterations over %d keyframes per GPU with D2H of the "
+                        "loss terms each, confidence bookkeeping / prune; Mpix/s counts the training renders only" % (iters, B)},
         # kernels of libags_b200.so launched inside the timed region, counted by the library itself
         # (ags_launch_count); torch's own stack/memset/barrier launches are not included
         "gpu_launches": int(launches),
         "clocks": clk,
     }
     if stages is not None:
-        alg = algorithmic_bytes(N, B, P, inst, vis, tiles)
+        inst_r, vis_r = (inst, vis) if world == 1 else (inst, vis)      # rank 0's own batch (dist: max instances)
+        alg = algorithmic_bytes(N, B, P, inst_r, vis_r, tiles)
         kern = {k: {"ms": stages[k], "alg_bytes": alg.get(k), "gbs": (alg[k] / (stages[k] * 1e-3) / 1e9) if k in alg and stages[k] > 0 else None}
                 for k in stages}
         dom = max((k for k in stages if k in alg), key=lambda k: stages[k])

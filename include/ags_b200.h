@@ -140,14 +140,20 @@ typedef struct AgsLossArgs {
     const int32_t* vis_count;      /* (H,W) sum over ALL frames of (opacity>1e-3) (quirk Q1), or NULL:
                                       computed from this call's B frames */
     /* outputs */
-    float* normal_unit;            /* (B,3,H,W) normalize(normal)*mask   (operations.py:714-715) */
-    float* d2n;                    /* (B,3,H,W) depth2normal             (operations.py:718)     */
+    float* normal_unit;            /* (B,3,H,W) normalize(normal)*mask   (operations.py:714-715); NULL = not wanted */
+    float* d2n;                    /* (B,3,H,W) depth2normal             (operations.py:718);     NULL = not wanted */
     float* d_rgb; float* d_normal; float* d_depth;   /* dL/d(rasterizer outputs) */
     float* loss_terms;             /* (4 + 2*B): rgb, depth, cons, tv sums (already normalised),
                                       then per frame rgb-L1 mean, depth-L1 mean (track_performance) */
     float w_depth, w_cons, w_tv;   /* 0.8, 0.1, 0.1 (gaussian_map.py:119-124) */
     void* workspace; size_t workspace_bytes;   /* >= ags_loss_scratch_bytes */
     void* stream;
+    /* optional (NULL = absent) */
+    const float* frame_weight;     /* (B) 1 = real frame, 0 = padding: a padded frame contributes nothing to the
+                                      loss, to the visibility sum of quirk Q1 or to any gradient (frame sharding
+                                      pads the keyframe batch to a multiple of the world size) */
+    const float* const* rgb_gt_frames_host;    /* HOST array of B device pointers, each (3,H,W): ground truth read in */
+    const float* const* depth_gt_frames_host;  /* place from the keyframe store instead of a stacked (B,..) copy    */
 } AgsLossArgs;
 
 size_t ags_loss_scratch_bytes(int32_t B, int32_t H, int32_t W);
@@ -183,6 +189,9 @@ typedef struct AgsAdamArgs {
                                               stats + AGS_STAT_OVERFLOW so an overflowed forward never
                                               reaches the parameters) */
     void* stream;
+    int32_t zero_grad;                     /* 1: the gradients are set to zero after they are consumed
+                                              (optimizer.zero_grad(), gaussian_map.py:127, in the same pass; grad[]
+                                              is then written).  Pair with AgsRenderGradArgs.accumulate = 1 */
 } AgsAdamArgs;
 
 int ags_adam_step(const AgsAdamArgs* args);
@@ -228,6 +237,7 @@ typedef struct AgsDistVisArgs {
     const int32_t* vis_multicast;               /* NVLS multicast address of it, or NULL */
     int32_t* vis_count;                         /* local (H,W) output of ags_dist_vis_sum */
     void* stream;
+    const float* frame_weight;                  /* optional (B): frames with weight 0 (padding) are not counted */
 } AgsDistVisArgs;
 int ags_dist_vis_local(const AgsDistVisArgs* args);
 int ags_dist_vis_sum(const AgsDistVisArgs* args);

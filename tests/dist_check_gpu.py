@@ -8,7 +8,9 @@ Trains the same small map for a few iterations with
   (b) frame sharding + NCCL all-reduce + replicated Adam,
   (c) frame sharding + the fused NVLink kernel, peer-pointer path,
   (d) frame sharding + the fused NVLink kernel, NVLS multimem path (if the fabric supports it),
-and checks that all ranks hold identical parameters and that (b), (c), (d) agree with (a).
+and checks that all ranks hold identical parameters and that (b), (c), (d) agree with (a) -- once with a
+keyframe batch that divides by the world size and once with one that does not (padded slots with loss
+weight 0, the normal case for the first keyframes of a mission).
 """
 import os
 import sys
@@ -51,7 +53,8 @@ def main():
                            depth_range=torch.tensor([0.0, 5.0])))
     start = syn.perturb_state(gen, seed=13)
 
-    def run(shard, steps=4):
+    def run(shard, steps=4, batch=None):
+        cfg.sampler.batch_size = T if batch is None else batch
         gm = GaussianMap(cfg, dev)
         for k, v in start.items():
             setattr(gm, k if k.startswith("view_") else "_" + k, v.clone().to(dev))
@@ -66,33 +69,36 @@ def main():
         return [getattr(gm, n).detach().clone() for n in NAMES], losses, gm.training_performance.clone()
 
     ok = True
-    ref, ref_losses, ref_perf = run(None)              # every rank: the whole batch on its own GPU
-    results = {"nccl": run(FrameShard(fused=False))}
-    sh = FrameShard(fused=True); sh.use_multicast = False
-    results["fused-peer"] = run(sh)
-    sh2 = FrameShard(fused=True); sh2.use_multicast = True
-    results["fused-multimem"] = run(sh2)
-    mc = sh2._flat is not None and sh2._flat.grad_mc != 0
-    for name, (params, losses, perf) in results.items():
-        # (1) replicas identical across ranks
-        for p in params:
-            lo, hi = p.clone(), p.clone()
-            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-            same = bool(torch.equal(torch.nan_to_num(lo), torch.nan_to_num(hi)))
-            ok &= same
-            if not same and rank == 0:
-                print(f"[{name}] replicas differ: max {(hi - lo).abs().max().item():.3e}")
-        # (2) agrees with the unsharded run
-        errs = [((a - b).norm() / b.norm().clamp_min(1e-30)).item() for a, b in zip(params, ref) if True]
-        errs[1] = ((params[1][:, :2] - ref[1][:, :2]).norm() / ref[1][:, :2].norm()).item()   # skip the -1e10 lane
-        lerr = max(abs(a - b) / abs(b) for a, b in zip(losses, ref_losses))
-        perr = (perf - ref_perf).abs().max().item()
-        good = max(errs) < 2e-4 and lerr < 1e-4 and perr < 1e-5
-        ok &= good
-        if rank == 0:
-            print(f"[{name}{' (NVLS multimem active)' if name == 'fused-multimem' and mc else ''}] "
-                  f"param l2 err vs unsharded {['%.1e' % e for e in errs]} loss err {lerr:.1e} perf err {perr:.1e} "
-                  f"{'ok' if good else 'FAIL'}")
+    mc = False
+    for batch in (T, T - 1):
+        ref, ref_losses, ref_perf = run(None, batch=batch)              # every rank: the whole batch on its own GPU
+        results = {"nccl": run(FrameShard(fused=False), batch=batch)}
+        sh = FrameShard(fused=True); sh.use_multicast = False
+        results["fused-peer"] = run(sh, batch=batch)
+        sh2 = FrameShard(fused=True); sh2.use_multicast = True
+        results["fused-multimem"] = run(sh2, batch=batch)
+        mc = sh2._flat is not None and sh2._flat.grad_mc != 0
+        for name, (params, losses, perf) in results.items():
+            # (1) replicas identical across ranks
+            for p in params:
+                lo, hi = p.clone(), p.clone()
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+                same = bool(torch.equal(torch.nan_to_num(lo), torch.nan_to_num(hi)))
+                ok &= same
+                if not same and rank == 0:
+                    print(f"[{name}] replicas differ: max {(hi - lo).abs().max().item():.3e}")
+            # (2) agrees with the unsharded run
+            errs = [((a - b).norm() / b.norm().clamp_min(1e-30)).item() for a, b in zip(params, ref) if True]
+            errs[1] = ((params[1][:, :2] - ref[1][:, :2]).norm() / ref[1][:, :2].norm()).item()   # skip the -1e10 lane
+            lerr = max(abs(a - b) / abs(b) for a, b in zip(losses, ref_losses))
+            perr = (perf - ref_perf).abs().max().item()
+            good = max(errs) < 2e-4 and lerr < 1e-4 and perr < 1e-5
+            ok &= good
+            if rank == 0:
+                print(f"[batch {batch}{' (padded)' if batch % world else ''}] "
+                      f"[{name}{' (NVLS multimem active)' if name == 'fused-multimem' and mc else ''}] "
+                      f"param l2 err vs unsharded {['%.1e' % e for e in errs]} loss err {lerr:.1e} perf err {perr:.1e} "
+                      f"{'ok' if good else 'FAIL'}")
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -42,8 +42,10 @@ def _worker(rank, world, port, ret):
     assert int(sh.all_reduce_sum_(vis)[0, 0]) == 3
     pf = sh.gather_perf(torch.tensor([rank + 0.25, rank + 0.5]), None)
     assert torch.allclose(pf, torch.tensor([0.25, 0.5, 1.25, 1.5]))
-    with pytest.raises(ValueError):
-        sh.local_batch(7)
+    # a batch that does not divide by the world size is padded, not refused (the reference sampler
+    # yields T < 8 frames for the first keyframes)
+    assert sh.local_batch(7) == 4 and sh.pad(list(range(7))).tolist() == [0, 1, 2, 3, 4, 5, 6, -1]
+    assert sh.my_frames(sh.pad([5, 6, 7])).tolist() == ([5, 6] if rank == 0 else [7, -1])
     # load-balanced partition: same answer on every rank, a permutation of the sampled ids, the active
     # keyframes at their pinned slots, and a smaller maximum load than the contiguous split
     cost = {int(i): float(1000 + 900 * (int(i) % 5)) for i in range(16) if i != 3}     # id 3 unknown -> mean
@@ -108,3 +110,38 @@ def test_balance_partition_properties_all_world_sizes():
             better += load(bal) < load(ids) - 1e-6
             worse += load(bal) > load(ids) + 1e-6
     assert better > 100 and worse < 10
+
+
+def test_padded_batches_for_the_first_keyframes_all_world_sizes():
+    """with the reference sampler (batch_size 8, active_size 3) the sampled batch has
+    v = T frames for the first 7 keyframes, so v % world != 0 is the normal case.  For T = 1..9 and world
+    2/4/8: every rank gets the same number of slots, every real keyframe lands in exactly one slot, the
+    active keyframes sit at their pinned slots, padding is -1."""
+    from active_gs_b200.distributed import FrameShard
+    from active_gs_b200.gaussian_map import WeightedSampler
+    from active_gs_b200.config import default_gaussian_map_config
+    cfg = default_gaussian_map_config().sampler
+    rng = np.random.default_rng(1)
+    for world in (2, 4, 8):
+        for T in range(1, 10):
+            np.random.seed(T)
+            sampler = WeightedSampler(cfg, T)
+            ids = sampler.next_ids(torch.linspace(0.5, 1.5, T))
+            assert len(ids) == sampler.v == min(T, 8)
+            cost = {int(i): float(rng.uniform(1e4, 9e4)) for i in ids}
+            outs = []
+            for rank in range(world):
+                sh = FrameShard.__new__(FrameShard)
+                sh.world, sh.rank = world, rank
+                b = sh.local_batch(sampler.v)
+                assert b == -(-sampler.v // world)
+                bal = sh.balance(ids, len(sampler.active_ids), cost)
+                assert len(bal) == b * world and len(sh.my_frames(bal)) == b
+                outs.append(bal)
+            assert all(np.array_equal(outs[0], o) for o in outs)
+            real = outs[0][outs[0] >= 0]
+            assert sorted(real.tolist()) == sorted(int(i) for i in ids)
+            assert int((outs[0] < 0).sum()) == b * world - sampler.v
+            for j, fid in enumerate(sampler.active_ids):
+                r, k = sh.pinned_slot(j)
+                assert outs[0][r * b + k] == fid

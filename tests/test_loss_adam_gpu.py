@@ -157,3 +157,58 @@ def test_device_bilateral_matches_cv2():
         assert err < 2e-5
     flat = torch.full((1, 20, 30), 1.5, device=dev)
     assert torch.equal(O.get_smooth_depth_device(flat), flat)   # max == min: copied unchanged
+
+
+def test_fused_loss_frame_lists_padding_weights_and_no_maps():
+    """(i) ground truth through per-frame pointers == stacked tensors (bitwise); (ii) a padded frame
+    (weight 0) contributes nothing: the 3 real frames + 1 padded frame reproduce the 3-frame call and the
+    padded frame's gradients are zero; (iii) want_maps=False gives the same gradients."""
+    dev = _dev()
+    from active_gs_b200 import ops
+    B, H, W = 4, 37, 53
+    ins = [t.to(dev).contiguous() for t in make_inputs(B, H, W, seed=11)]
+    fovs = (0.5 * torch.tensor([[1.0, 0.8]])).tan().repeat(B, 1).to(dev)
+    full = ops.loss_forward_backward(*ins, fovs)
+    rgb_list = [ins[4][k].clone() for k in range(B)]
+    d_list = [ins[5][k].clone() for k in range(B)]
+    lst = ops.loss_forward_backward(*ins[:4], rgb_list, d_list, fovs, want_maps=False)
+    assert lst.normal_unit is None and lst.d2n is None
+    for name in ["d_rgb", "d_normal", "d_depth", "terms"]:
+        assert torch.equal(getattr(lst, name), getattr(full, name)), name
+    # second call through the cached argument struct with DIFFERENT frame tensors (pointers refreshed)
+    perm = [2, 0, 3, 1]
+    ins_p = [t[perm].contiguous() for t in ins]
+    ref_p = ops.loss_forward_backward(*ins_p, fovs[perm].contiguous())
+    lst = ops.loss_forward_backward(ins_p[0], ins_p[1], ins_p[2], ins_p[3], [rgb_list[k] for k in perm],
+                                    [d_list[k] for k in perm], fovs, out=None, want_maps=False)
+    torch.testing.assert_close(lst.d_depth, ref_p.d_depth, rtol=1e-6, atol=1e-10)
+    # padding: frames 0..2 real, frame 3 padded
+    three = ops.loss_forward_backward(*[t[:3].contiguous() for t in ins], fovs[:3].contiguous())
+    w = torch.tensor([1.0, 1.0, 1.0, 0.0], device=dev)
+    pad = ops.loss_forward_backward(*ins, fovs, B_total=3, frame_weight=w)
+    for name in ["d_rgb", "d_normal", "d_depth"]:
+        got = getattr(pad, name)
+        torch.testing.assert_close(got[:3], getattr(three, name), rtol=1e-5, atol=1e-10)
+        assert float(got[3].abs().max()) == 0.0
+    torch.testing.assert_close(pad.terms[:4], three.terms[:4], rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(pad.terms[4:10], three.terms[4:10], rtol=1e-5, atol=1e-9)
+
+
+def test_adam_zero_grad_consumes_the_gradients():
+    dev = _dev()
+    from active_gs_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    shapes = [(1001, 3), (1001, 3), (1001, 4), (1001,), (1001, 1, 3)]
+    p = [torch.randn(*s, generator=g).to(dev) for s in shapes]
+    q = [t.clone() for t in p]
+    gr = [torch.randn(*s, generator=g).to(dev) for s in shapes]
+    gq = [t.clone() for t in gr]
+    m, v = [torch.zeros_like(t) for t in p], [torch.zeros_like(t) for t in p]
+    m2, v2 = [torch.zeros_like(t) for t in p], [torch.zeros_like(t) for t in p]
+    lrs = [1e-3] * 5
+    ops.adam_step(p, gr, m, v, lrs, step=1, zero_grad=True)
+    ops.adam_step(q, gq, m2, v2, lrs, step=1)
+    for a, b, c in zip(p, q, gr):
+        assert torch.equal(a, b) and float(c.abs().max()) == 0.0
+    for c in gq:
+        assert float(c.abs().max()) > 0.0
