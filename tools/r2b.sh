@@ -1,0 +1,25 @@
+# round 2, call B: new K1 / scatter / fused loss / clear kernel / persistent engine; backward reduction variants
+tag=r2b
+python -m pytest tests -m gpu -q --tb=short -x > gpurun_out/${tag}_pytest_gpu_full.log 2>&1
+tail -15 gpurun_out/${tag}_pytest_gpu_full.log
+run() {  # name, env...
+  name=$1; shift
+  env "$@" python bench.py --steps 200 --warmup 5 --no-cpu-baseline > gpurun_out/${tag}_bench_$name.json 2> gpurun_out/${tag}_bench_$name.err
+  python - <<PY
+import json
+try:
+    d=json.loads([l for l in open('gpurun_out/${tag}_bench_$name.json') if l.startswith('{')][-1])
+    k=d['kernels']
+    print('$name step %.1f us e2e %.1f us/step' % (d['ms_per_step']*1e3, d['e2e']['ms_per_step']*1e3), ' '.join('%s=%.0f' % (n[:11], k[n]['ms']*1e3) for n in k), 'launches', d['gpu_launches'], 'update', {a: round(b,2) for a,b in d.get('update',{}).items() if a.endswith('_ms') or a=='ms_per_keyframe'})
+except Exception as e:
+    print('$name FAILED', e); print(open('gpurun_out/${tag}_bench_$name.err').read()[-1500:])
+PY
+}
+run red0 AGS_BWD_RED=0
+run red1 AGS_BWD_RED=1
+run red2 AGS_BWD_RED=2
+run px2red1 AGS_BWD_PX=2 AGS_BWD_RED=1
+run px2red2 AGS_BWD_PX=2 AGS_BWD_RED=2
+ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 150 -c 60 --csv --log-file gpurun_out/${tag}_launches.csv \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > /dev/null 2> gpurun_out/${tag}_ncu.err
+ls -la gpurun_out | tail -8
