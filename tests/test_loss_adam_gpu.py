@@ -173,8 +173,9 @@ def test_fused_loss_frame_lists_padding_weights_and_no_maps():
     d_list = [ins[5][k].clone() for k in range(B)]
     lst = ops.loss_forward_backward(*ins[:4], rgb_list, d_list, fovs, want_maps=False)
     assert lst.normal_unit is None and lst.d2n is None
-    for name in ["d_rgb", "d_normal", "d_depth", "terms"]:
+    for name in ["d_rgb", "d_normal", "d_depth"]:
         assert torch.equal(getattr(lst, name), getattr(full, name)), name
+    torch.testing.assert_close(lst.terms, full.terms, rtol=1e-5, atol=1e-9)       # block sums land in atomic order
     # second call through the cached argument struct with DIFFERENT frame tensors (pointers refreshed)
     perm = [2, 0, 3, 1]
     ins_p = [t[perm].contiguous() for t in ins]
