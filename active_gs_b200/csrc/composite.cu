@@ -159,6 +159,9 @@ __device__ void sort_oversize_tile(const AgsWorkspace& w, int n, int off, uint64
 #ifndef AGS_BWD_PX_DEFAULT
 #define AGS_BWD_PX_DEFAULT 1  // pixels per lane of the backward (composite_bwd_kernel<PX>)
 #endif
+#ifndef AGS_BWD_PX2_MINB
+#define AGS_BWD_PX2_MINB 6
+#endif
 #ifndef AGS_BWD_RED_DEFAULT
 #define AGS_BWD_RED_DEFAULT 2 // cross-lane reduction variant of the backward (see bwd_red()): measured 318 / 313 / 301 us for 0 / 1 / 2
 #endif
@@ -507,7 +510,7 @@ __device__ __forceinline__ void bwd_accumulate(float (&val)[15], BwdPix& s, cons
 // loads and the bounding-box test are shared by the PX pixels.  Sub-blocks of 8x4 pixels the splat's
 // cutoff box does not reach are skipped warp-uniformly.
 template <int PX, bool HAS_CONF, int RED>
-__global__ void __launch_bounds__(256 / PX, PX == 1 ? AGS_BWD_MINB : (PX == 2 ? 6 : 8))
+__global__ void __launch_bounds__(256 / PX, PX == 1 ? AGS_BWD_MINB : (PX == 2 ? AGS_BWD_PX2_MINB : 8))
 composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
     constexpr int THREADS = 256 / PX, WARPS = 8 / PX;
     constexpr int RED_FLOATS = RED == 0 ? 15 * RED_STRIDE : (RED == 1 ? RED1_FLOATS : 4);

@@ -8,7 +8,7 @@
 //   /root/reference/mapping/gaussian_map.py:132-139  track_performance per-frame means
 // and the autograd backward of all of it down to d rgb / d depth / d normal(raw).
 //
-// ONE tiled kernel (loss_fused_kernel): a CTA owns a 32x8 pixel tile of one frame and stages, in shared
+// ONE tiled kernel (loss_fused_kernel): a CTA owns a 32x16 pixel tile of one frame and stages, in shared
 // memory, depth / opacity mask of the tile + a halo of 2 and the unit normals / visibility sum / depth
 // mask of the tile + a halo of 1.  Phase 1 evaluates depth2normal and its adjoint (the pixel's own depth
 // gradient and what it pushes to its four neighbours) for the tile + halo 1; phase 2 gathers the
@@ -17,7 +17,7 @@
 // atomics on images, deterministic.
 // HBM roofline: reads 12 planes (8 predicted + 4 ground truth) + the (H,W) visibility sum, writes 7 planes
 // of B*H*W floats (+6 when the caller wants normal_unit / d2n): 76 B per pixel and frame.  The halo
-// (1.33x / 1.69x of the tile) is served by L2.
+// (1.20x / 1.41x of the tile) is served by L2.
 #include <string.h>
 #include "ags_common.cuh"
 
@@ -137,7 +137,7 @@ loss_vis_count(AgsLossArgs a, float* __restrict__ msum_plane) {
 #define AGS_LOSS_MINB 4
 #endif
 
-constexpr int LT_W = 32, LT_H = 8;                 // output tile
+constexpr int LT_W = 32, LT_H = 16;                // output tile: 256 threads, two rows (y, y + 8) per thread
 constexpr int LE_W = LT_W + 2, LE_H = LT_H + 2;    // tile + halo 1 (d2n adjoint, unit normals)
 constexpr int LR_W = LT_W + 4, LR_H = LT_H + 4;    // tile + halo 2 (depth, opacity mask)
 constexpr int LE_N = LE_W * LE_H, LR_N = LR_W * LR_H;
@@ -164,13 +164,13 @@ template <bool USE_LIST>
 __global__ void __launch_bounds__(256, AGS_LOSS_MINB)
 loss_fused_kernel(AgsLossArgs a, LossFrames fr, const float* __restrict__ msum_plane) {
     __shared__ float sD[LR_N], sM[LR_N];                         // depth, d2n mask (opacity > 1e-2); 0 outside
-    __shared__ float sNU[3][LE_N], sMS[LE_N], sMD[LE_N];         // unit normal, visibility sum, depth_gt > 0
+    __shared__ float sNU[3][LE_N], sMS[LE_N], sMD[LE_N], sIN[LE_N];   // unit normal, visibility sum, depth_gt > 0, inside the image
     __shared__ float sDN[3][LE_N];                               // d2n (= u * m2)
     __shared__ float sAdj[5][LE_N];                              // own, up, left, bottom, right depth adjoints
     const int H = a.H, W = a.W;
     const unsigned P = (unsigned)H * (unsigned)W;
     const unsigned f = blockIdx.z;
-    const int tid = threadIdx.y * LT_W + threadIdx.x;
+    const int tid = threadIdx.y * LT_W + threadIdx.x;          // block = (32, 8)
     const int x0 = blockIdx.x * LT_W, y0 = blockIdx.y * LT_H;
     const float wf = a.frame_weight ? __ldg(a.frame_weight + f) : 1.f;
     const float Bt = (float)a.B_total;
@@ -201,8 +201,9 @@ loss_fused_kernel(AgsLossArgs a, LossFrames fr, const float* __restrict__ msum_p
         const int ey = i / LE_W, ex = i - ey * LE_W;
         const int y = y0 - 1 + ey, x = x0 - 1 + ex;
         F3 nu = f3(0.f, 0.f, 0.f);
-        float ms = 0.f, md = 0.f;
+        float ms = 0.f, md = 0.f, inside = 0.f;
         if (x >= 0 && x < W && y >= 0 && y < H) {
+            inside = 1.f;
             const unsigned p = (unsigned)y * W + x;
             const F3 n = f3(__ldg(normal + p), __ldg(normal + P + p), __ldg(normal + 2u * P + p));
             const float m2 = (__ldg(opac + p) > 1e-2f) ? 1.f : 0.f;
@@ -210,7 +211,7 @@ loss_fused_kernel(AgsLossArgs a, LossFrames fr, const float* __restrict__ msum_p
             ms = __ldg(msum_plane + p);
             md = (__ldg(depth_gt + p) > 0.f) ? 1.f : 0.f;
         }
-        sNU[0][i] = nu.x; sNU[1][i] = nu.y; sNU[2][i] = nu.z; sMS[i] = ms; sMD[i] = md;
+        sNU[0][i] = nu.x; sNU[1][i] = nu.y; sNU[2][i] = nu.z; sMS[i] = ms; sMD[i] = md; sIN[i] = inside;
     }
     __syncthreads();
     // ---- phase 1: depth2normal + adjoint for the tile + halo 1
@@ -260,15 +261,18 @@ loss_fused_kernel(AgsLossArgs a, LossFrames fr, const float* __restrict__ msum_p
         sAdj[0][i] = a_own; sAdj[1][i] = a_up; sAdj[2][i] = a_left; sAdj[3][i] = a_bottom; sAdj[4][i] = a_right;
     }
     __syncthreads();
-    // ---- phase 2: one thread per pixel of the tile
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    const bool in = (x < W) && (y < H);
+    // ---- phase 2: every thread finishes two pixels of the tile (rows ty and ty + 8)
     float fr_rgb = 0.f, fr_d = 0.f, acc_cons = 0.f, acc_tv = 0.f;
-    if (in) {
+    const float ctv2 = 2.f * a.w_tv * inv_tv;
+#pragma unroll
+    for (int half = 0; half < LT_H / 8; ++half) {
+        const int ty = threadIdx.y + 8 * half;
+        const int x = x0 + threadIdx.x, y = y0 + ty;
+        if (x >= W || y >= H) continue;
         const unsigned p = (unsigned)y * (unsigned)W + (unsigned)x;
         const unsigned o1 = f * P + p, o3 = f * 3u * P + p;
-        const int e = (threadIdx.y + 1) * LE_W + (threadIdx.x + 1);
-        const int r = (threadIdx.y + 2) * LR_W + (threadIdx.x + 2);
+        const int e = (ty + 1) * LE_W + (threadIdx.x + 1);
+        const int r = (ty + 2) * LR_W + (threadIdx.x + 2);
         const float msum = sMS[e];
         const float A = __ldg(opac + p);
         const float mvis = (A > 1e-3f) ? 1.f : 0.f;
@@ -278,14 +282,14 @@ loss_fused_kernel(AgsLossArgs a, LossFrames fr, const float* __restrict__ msum_p
         for (unsigned c = 0; c < 3; ++c) {
             const float er = (__ldg(a.rgb + o3 + c * P) - __ldg(rgb_gt + p + c * P)) * mvis;
             fr_rgb += fabsf(er);
-            a.d_rgb[o3 + c * P] = (er > 0.f ? 1.f : (er < 0.f ? -1.f : 0.f)) * mvis * inv_rgb;
+            a.d_rgb[o3 + c * P] = (er > 0.f ? inv_rgb : (er < 0.f ? -inv_rgb : 0.f));
         }
         // ---- L1 depth + gradient, plus the depth2normal adjoint gathered from the neighbours
         const float dp = sD[r];
         const float md_p = sMD[e];
         const float ed = (dp - __ldg(depth_gt + p)) * md_p;
-        fr_d = fabsf(ed);
-        float dd = a.w_depth * (ed > 0.f ? 1.f : (ed < 0.f ? -1.f : 0.f)) * md_p * inv_d;
+        fr_d += fabsf(ed);
+        float dd = a.w_depth * (ed > 0.f ? inv_d : (ed < 0.f ? -inv_d : 0.f));
         dd += sAdj[0][e];
         dd += sAdj[1][e + LE_W];        // "up" share of the pixel below
         dd += sAdj[2][e + 1];           // "left" share of the pixel to the right
@@ -295,28 +299,29 @@ loss_fused_kernel(AgsLossArgs a, LossFrames fr, const float* __restrict__ msum_p
         // ---- consistency loss + normal gradient (consistency + TV, through normalize*mask)
         const F3 nu = f3(sNU[0][e], sNU[1][e], sNU[2][e]);
         const F3 d2n = f3(sDN[0][e], sDN[1][e], sDN[2][e]);
-        acc_cons = (1.f - dot(nu, d2n)) * msum;
+        acc_cons += (1.f - dot(nu, d2n)) * msum;
         F3 gnu = d2n * (-a.w_cons * msum * inv_cons);
-        const float ctv = a.w_tv * inv_tv;
-        // each neighbour q contributes the own one-sided difference (mask of p) and the mirrored
-        // difference of q that references p (mask of q)
-#define AGS_TV_NEIGHBOUR(EO, RO, OK)                                                        \
+        // TV: the one-sided difference towards neighbour q enters twice -- as p's own term (mask of p) and
+        // as q's mirrored term that references p (mask of q); both share the difference vector, its
+        // squared norm, the depth gate and the exponential, so they are evaluated once.
+        // (the staged depth mask is 0 outside the image, so no border test is needed)
+#define AGS_TV_NEIGHBOUR(EO, RO)                                                            \
         {                                                                                   \
-            const float okf = (OK) ? 1.f : 0.f;                                             \
-            const F3 nq = f3(sNU[0][e + (EO)], sNU[1][e + (EO)], sNU[2][e + (EO)]);         \
-            const float dq = sD[r + (RO)];                                                  \
-            const float mdq = sMD[e + (EO)] * okf;                                          \
-            float val, coef;                                                                \
-            tv_term(nu, nq, dp, dq, md_p * okf, inv2s2, val, coef);                         \
-            acc_tv += val;                                                                  \
-            gnu = gnu + (nu - nq) * (2.f * coef * ctv);                                     \
-            tv_term(nq, nu, dq, dp, mdq, inv2s2, val, coef);                                \
-            gnu = gnu - (nq - nu) * (2.f * coef * ctv);                                     \
+            const F3 dl = nu - f3(sNU[0][e + (EO)], sNU[1][e + (EO)], sNU[2][e + (EO)]);    \
+            const float nd = dot(dl, dl);                                                   \
+            const float ddq = dp - sD[r + (RO)];                                            \
+            const float mq = sMD[e + (EO)];                                                 \
+            const float in_q = sIN[e + (EO)];                                               \
+            const float gate = (ddq * ddq <= 1e-4f) ? 1.f : 0.f;                            \
+            const float ex = __expf(-nd * inv2s2) * gate;                                   \
+            acc_tv += md_p * in_q * ex * nd;                                                \
+            const float coef = ex * (1.f - nd * inv2s2) * (md_p * in_q + mq);               \
+            gnu = gnu + dl * (coef * ctv2);                                                 \
         }
-        AGS_TV_NEIGHBOUR(1, 1, x < W - 1)
-        AGS_TV_NEIGHBOUR(-1, -1, x > 0)
-        AGS_TV_NEIGHBOUR(LE_W, LR_W, y < H - 1)
-        AGS_TV_NEIGHBOUR(-LE_W, -LR_W, y > 0)
+        AGS_TV_NEIGHBOUR(1, 1)
+        AGS_TV_NEIGHBOUR(-1, -1)
+        AGS_TV_NEIGHBOUR(LE_W, LR_W)
+        AGS_TV_NEIGHBOUR(-LE_W, -LR_W)
 #undef AGS_TV_NEIGHBOUR
         const F3 n = f3(__ldg(normal + p), __ldg(normal + P + p), __ldg(normal + 2u * P + p));
         const float inn = rsqrtf(fmaxf(dot(n, n), 1e-24f));
@@ -406,7 +411,7 @@ extern "C" int ags_loss_forward_backward(const AgsLossArgs* a) {
             fr.rgb[f] = a->rgb_gt_frames_host[f];
             fr.depth[f] = a->depth_gt_frames_host[f];
         }
-    dim3 grid((a->W + LT_W - 1) / LT_W, (a->H + LT_H - 1) / LT_H, a->B), block(LT_W, LT_H);
+    dim3 grid((a->W + LT_W - 1) / LT_W, (a->H + LT_H - 1) / LT_H, a->B), block(LT_W, 8);
     ags_note_launch(); loss_vis_count<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(*a, msum_plane);
     AGS_CHECK_CUDA(cudaGetLastError());
     ags_note_launch();

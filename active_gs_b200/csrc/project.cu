@@ -189,7 +189,7 @@ __device__ __forceinline__ void project_view(ViewProj& o, const GaussAct& g, con
 }
 
 // K1 ---------------------------------------------------------------------------------------------
-// One CTA owns 512 consecutive Gaussians for ALL views of the batch: the means are loaded once (two
+// One CTA owns K1_G (256) consecutive Gaussians for ALL views of the batch: the means are loaded once (two
 // Gaussians per thread) and the views are walked in chunks of K1_VCHUNK cameras staged in shared memory.
 // Per chunk:
 //   1. every (Gaussian, view) pair is tested against a CONSERVATIVE screen-space radius bound that
@@ -203,13 +203,19 @@ __device__ __forceinline__ void project_view(ViewProj& o, const GaussAct& g, con
 //      index range; per-tile counting with fire-and-forget REDs,
 //   3. the visible pairs of the chunk are appended to the global compact list (one atomic per CTA and
 //      chunk) that drives the scatter and K6.
-constexpr int K1_THREADS = 256;
-constexpr int K1_GPT = 2;                          // Gaussians per thread
-constexpr int K1_G = K1_THREADS * K1_GPT;          // Gaussians per CTA
-constexpr int K1_VCHUNK = 4;                       // views per pass
+#ifndef AGS_K1_THREADS
+#define AGS_K1_THREADS 128
+#endif
+#ifndef AGS_K1_MINB
+#define AGS_K1_MINB 8
+#endif
+constexpr int K1_THREADS = AGS_K1_THREADS;         // small CTAs: the kernel is a chain of dependent latencies
+constexpr int K1_GPT = 2;                          // Gaussians per thread           (load -> cull -> barrier -> load ->
+constexpr int K1_G = K1_THREADS * K1_GPT;          // Gaussians per CTA               project -> store), so many independent
+constexpr int K1_VCHUNK = 8;                       // views per pass                  CTAs per SM hide it
 constexpr int K1_LIST = K1_G * K1_VCHUNK;          // worst case: every pair of the pass is a candidate
 
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1_THREADS, AGS_K1_MINB)
 project_fwd_kernel(AgsRenderArgs a, AgsWorkspace w, int for_backward) {
     __shared__ Cam s_cam[K1_VCHUNK];
     __shared__ int s_cand[K1_LIST], s_vis[K1_LIST];
@@ -238,8 +244,8 @@ project_fwd_kernel(AgsRenderArgs a, AgsWorkspace w, int for_backward) {
     for (int v0 = 0; v0 < a.B; v0 += K1_VCHUNK) {
         const int nv = min(K1_VCHUNK, a.B - v0);
         __syncthreads();                                   // previous pass done with s_cam / lists
-        if (tid < nv * 34) {
-            const int vl = tid / 34, k = tid - vl * 34, v = v0 + vl;
+        for (int q = tid; q < nv * 34; q += K1_THREADS) {
+            const int vl = q / 34, k = q - vl * 34, v = v0 + vl;
             if (k < 16) s_cam[vl].V[k] = __ldg(a.viewmatrix + v * 16 + k);
             else if (k < 32) s_cam[vl].M[k - 16] = __ldg(a.projmatrix + v * 16 + k - 16);
             else if (k == 32) s_cam[vl].tanx = __ldg(a.tanfov + v * 2);

@@ -306,6 +306,9 @@ def run_ours(args, rank, world, local_rank):
     inst = int(np.mean([l[2] for l in ctx.log[-args.steps:]]))
     vis = int(np.mean([l[3] for l in ctx.log[-args.steps:]]))
     loss_first, loss_last = ctx.log[0][0], ctx.log[-1][0]
+    if args.device_arm_only:
+        clocks.stop() if rank == 0 else None
+        return None
     stages = stage_profile(ctx.eng, with_adam=(world == 1))      # no collective inside: every rank runs it
     clk = clocks.stop() if rank == 0 else None
     gm.end_training(ctx)
@@ -478,6 +481,8 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5],
                     help="SURVEY 8d config index: 2 = 200k/640x480 (headline), 3 = 500k/1280x720, 5 = 1M/1920x1080")
     ap.add_argument("--frames-per-gpu", type=int, default=8)
+    ap.add_argument("--device-arm-only", action="store_true",
+                    help="profiling runs (ncu): stop after the device-resident arm, print nothing")
     args = ap.parse_args()
     global CONFIG_IDX, B_PER_GPU
     CONFIG_IDX, B_PER_GPU = args.config, args.frames_per_gpu
