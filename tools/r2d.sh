@@ -22,7 +22,7 @@ python -c "
 import json
 d=json.loads([l for l in open('gpurun_out/${tag}_bench_steps20.json') if l.startswith('{')][-1])
 print('steps20: step %.1f us, e2e %.1f us/step (%d updates, N end %d)' % (d['ms_per_step']*1e3, d['e2e']['ms_per_step']*1e3, d['e2e']['updates'], d['e2e']['gaussians_end']))"
-ncu --set full --clock-control none --import-source on -k regex:"composite|project|scatter|loss|alloc|adam|clear" -s 110 -c 11 -o gpurun_out/${tag}_ncu_step \
+ncu --set full --clock-control none --import-source on -k regex:"composite|project|scatter|loss|alloc|adam|clear" -s 155 -c 10 -o gpurun_out/${tag}_ncu_step \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --device-arm-only > /dev/null 2> gpurun_out/${tag}_ncu.err
 ncu -i gpurun_out/${tag}_ncu_step.ncu-rep --page raw --csv > gpurun_out/${tag}_ncu_step_raw.csv 2>&1
 ls -la gpurun_out | tail -6
