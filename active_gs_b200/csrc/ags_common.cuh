@@ -19,6 +19,21 @@
 // the 20 KB staging buffer); larger tiles are chunk-sorted and merged by the same CTA (sort_oversize_tile)
 #define AGS_FUSED_SORT_MAX 2048
 
+// slots of the 16-float per-(view, Gaussian) gradient record `dsplat` (raw moments written by composite_bwd,
+// chain rule applied by project_bwd; the order is what the folded butterfly of composite_bwd ends with)
+#define AGS_REC_C0 0      // [0..2] sum w*gC
+#define AGS_REC_N0 3      // [3..5] sum w*gN
+#define AGS_REC_WD 6      // sum w*gD
+#define AGS_REC_PAD 7
+#define AGS_REC_PDX 8     // sum dpower*dx
+#define AGS_REC_PXX 9     // sum dpower*dx^2
+#define AGS_REC_WDX 10    // sum w*gD*dx
+#define AGS_REC_PXY 11    // sum dpower*dx*dy
+#define AGS_REC_PDY 12    // sum dpower*dy
+#define AGS_REC_PYY 13    // sum dpower*dy^2
+#define AGS_REC_WDY 14    // sum w*gD*dy
+#define AGS_REC_P1 15     // sum dpower          (d opacity = sum / opacity)
+
 // ------------------------------------------------------------------------------------------------
 // Workspace layout (all offsets 256-byte aligned). One workspace serves one batch of B views and
 // carries everything the backward needs.
@@ -119,4 +134,61 @@ __device__ __forceinline__ void load_cam(Cam& c, const float* vm, const float* p
     }
     c.tanx = __ldg(tf + v * 2);
     c.tany = __ldg(tf + v * 2 + 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// cross-GPU signal / wait folded into the exchange kernels (AgsDistSync, include/ags_b200.h)
+struct SyncP {
+    int32_t* peers[AGS_MAX_PEERS];
+    int epoch, world, rank;
+    bool on;
+};
+
+inline SyncP make_sync(const AgsDistSync& s, int world, int rank) {
+    SyncP p;
+    for (int r = 0; r < AGS_MAX_PEERS; ++r) p.peers[r] = r < world ? s.peers[r] : nullptr;
+    p.epoch = s.epoch; p.world = world; p.rank = rank;
+    p.on = s.peers[0] != nullptr;
+    return p;
+}
+
+// consumer side: every block, before it touches the peers' data
+__device__ __forceinline__ void sync_wait(const SyncP& s, int phase) {
+    if (!s.on) return;
+    if (threadIdx.x < s.world && threadIdx.y == 0) {
+        const int32_t* f = s.peers[s.rank] + phase * AGS_MAX_PEERS + threadIdx.x;
+        int v;
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        } while (v < s.epoch);
+    }
+    __syncthreads();
+}
+
+// producer side, called by ALL threads of ONE block after the data the phase publishes is written
+__device__ __forceinline__ void sync_signal(const SyncP& s, int phase) {
+    if (!s.on) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < s.world && threadIdx.y == 0) {
+        int32_t* f = s.peers[threadIdx.x] + phase * AGS_MAX_PEERS + s.rank;
+        asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(f), "r"(s.epoch) : "memory");
+    }
+}
+
+// "all blocks of this grid are done": true in exactly one block (the last to arrive); the counter lives in
+// the rank's own flags array (word AGS_SYNC_WORDS/2 + phase) and is reset for the next launch
+__device__ __forceinline__ bool sync_last_block(const SyncP& s, int phase) {
+    __shared__ int s_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        int32_t* c = s.peers[s.rank] + AGS_SYNC_WORDS / 2 + phase;
+        const int nblk = gridDim.x * gridDim.y * gridDim.z;
+        const int t = atomicAdd(c, 1);
+        s_last = (t == nblk - 1);
+        if (s_last) *c = 0;
+    }
+    __syncthreads();
+    return s_last != 0;
 }

@@ -163,7 +163,7 @@ __device__ void sort_oversize_tile(const AgsWorkspace& w, int n, int off, uint64
 #define AGS_BWD_PX2_MINB 6
 #endif
 #ifndef AGS_BWD_RED_DEFAULT
-#define AGS_BWD_RED_DEFAULT 2 // cross-lane reduction variant of the backward (see bwd_red()): measured 318 / 313 / 301 us for 0 / 1 / 2
+#define AGS_BWD_RED_DEFAULT 3 // cross-lane reduction variant of the backward (see bwd_red()): measured 318 / 313 / 301 us for 0 / 1 / 2
 #endif
 #ifndef AGS_FWD_MINB
 #define AGS_FWD_MINB 6
@@ -468,8 +468,9 @@ __device__ __forceinline__ void bwd_load_pixel(BwdPix& s, const AgsRenderArgs& a
 // The partials are the RAW MOMENTS of the pixel gradients (the chain rule through the conic, the centre
 // and the plane slopes is linear in them and is applied once per splat in project_bwd):
 //   [0] sum dpower*dx   [1] sum dpower*dy   [2] sum dpower*dx^2   [3] sum dpower*dx*dy   [4] sum dpower*dy^2
-//   [5] sum G*dalpha (d opacity)   [6..8] sum w*gC   [9..11] sum w*gN   [12] sum w*gD   [13] sum w*gD*dx
-//   [14] sum w*gD*dy        (dpower = dL/d(natural exponent), w = alpha*T, dx = x_splat - x_pixel)
+//   [5] sum dpower (d opacity = sum / o: alpha = o*G)   [6..8] sum w*gC   [9..11] sum w*gN   [12] sum w*gD
+//   [13] sum w*gD*dx   [14] sum w*gD*dy        (dpower = dL/d(natural exponent), w = alpha*T, dx = x_splat - x_pixel)
+// They land in the 16-float gradient record at the slots of AGS_REC_* (ags_common.cuh), shared with project_bwd.
 template <bool FIRST, bool HAS_CONF>
 __device__ __forceinline__ void bwd_accumulate(float (&val)[15], BwdPix& s, const float4 g1, const float4 f0,
                                                const float4 f1, float dx, float dy, float e_alpha, float e_G,
@@ -487,7 +488,7 @@ __device__ __forceinline__ void bwd_accumulate(float (&val)[15], BwdPix& s, cons
     // alpha = min(0.99, o*G): clamped -> no gradient
     const bool unclamped = (g1.y * G <= AGS_ALPHA_MAX);
     const float dpower = unclamped ? alpha * dalpha : 0.f;
-    const float dop = unclamped ? G * dalpha : 0.f;
+    const float dop = dpower;
     const float wgD = wgt * s.gD;
     const float pdx = dpower * dx, pdy = dpower * dy;
     if (FIRST) {
@@ -503,6 +504,90 @@ __device__ __forceinline__ void bwd_accumulate(float (&val)[15], BwdPix& s, cons
     }
 }
 
+// Variant 3 (default): the register butterfly with the lane-dependent selects folded away.
+// A butterfly level pairs slot i with slot i+w and every lane keeps one of the two depending on one bit of
+// its lane id -- two selects per pair, 30 per reduction.  Seven of the fifteen partials are w * (a per-pixel
+// constant): if lane l holds the constants PERMUTED by its role bits, Kp[t] = K[t ^ m(l)], every lane can
+// keep slot t and send slot t+w at every level and the right values still meet (partner m differs in exactly
+// the bit that swaps the halves): no selects for that group of eight through three levels.  The other
+// eight partials (the dpower / depth-slope moments) use the d1/d2 trick at the first level (dx and dy
+// swapped per lane once) and plain selects below.  12 selects instead of 30.
+//   roles: r1 = lane bit 4 (xor 16), r2 = bit 3 (xor 8), r3 = bit 2 (xor 4), r4 = bit 1 (xor 2); bit 0 is summed.
+//   the lane ends with record slot q = r4*8 + r1*4 + r2*2 + r3 (AGS_REC_* in ags_common.cuh).
+struct FoldLane {
+    float Kp[8];       // permuted per-pixel constants: K = (gC0, gC1, gC2, gN0, gN1, gN2, gD, 0)
+    bool r1, r2, r3, r4;
+};
+
+__device__ __forceinline__ void fold_setup(FoldLane& f, const BwdPix& s, int lane) {
+    f.r1 = (lane & 16) != 0; f.r2 = (lane & 8) != 0; f.r3 = (lane & 4) != 0; f.r4 = (lane & 2) != 0;
+    float K[8] = {s.gC0, s.gC1, s.gC2, s.gN0, s.gN1, s.gN2, s.gD, 0.f};
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const float a0 = f.r1 ? K[t ^ 4] : K[t];
+        f.Kp[t] = a0;
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) K[t] = f.Kp[t];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) f.Kp[t] = f.r2 ? K[t ^ 2] : K[t];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) K[t] = f.Kp[t];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) f.Kp[t] = f.r3 ? K[t ^ 1] : K[t];
+}
+
+template <bool HAS_CONF>
+__device__ __forceinline__ float bwd_pair_fold(BwdPix& s, const FoldLane& f, const float4 g1, const float4 f0,
+                                               const float4 f1, float dx, float dy, float e_alpha, float e_G,
+                                               bool active) {
+    const unsigned FULL = 0xffffffffu;
+    const float alpha = active ? e_alpha : 0.f;
+    const float G = active ? e_G : 0.f;
+    const float wgt = alpha * s.T;
+    const float one_m = 1.f - alpha;
+    const float dpix = f0.w - g1.z * dx - g1.w * dy;
+    float sdot = s.gC0 * f0.x + s.gC1 * f0.y + s.gC2 * f0.z + s.gN0 * f1.x + s.gN1 * f1.y + s.gN2 * f1.z + s.gD * dpix;
+    if (HAS_CONF) sdot += s.gCf * f1.w;
+    s.rem -= wgt * sdot;
+    const float dalpha = s.T * sdot - s.rem * rcp_approx(one_m);         // one_m >= 0.01
+    s.T *= one_m;
+    const bool unclamped = (g1.y * G <= AGS_ALPHA_MAX);                   // alpha = min(0.99, o*G): clamped -> no gradient
+    const float dpower = unclamped ? alpha * dalpha : 0.f;
+    const float wgD = wgt * s.gD;
+    // ---- level 1 (xor 16)
+    float W[4], P[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) W[t] = wgt * f.Kp[t] + __shfl_xor_sync(FULL, wgt * f.Kp[t + 4], 16);
+    {
+        const float d1 = f.r1 ? dy : dx, d2 = f.r1 ? dx : dy;
+        const float k0 = dpower * d1, s0 = dpower * d2;          // sum dpower*dx | dpower*dy
+        const float pxy = k0 * d2;                                // dpower*dx*dy
+        P[0] = k0 + __shfl_xor_sync(FULL, s0, 16);
+        P[1] = k0 * d1 + __shfl_xor_sync(FULL, s0 * d2, 16);      // dpower*dx^2 | dpower*dy^2
+        P[2] = wgD * d1 + __shfl_xor_sync(FULL, wgD * d2, 16);    // wgD*dx | wgD*dy
+        const float k3 = f.r1 ? dpower : pxy, s3 = f.r1 ? pxy : dpower;
+        P[3] = k3 + __shfl_xor_sync(FULL, s3, 16);                // dpower*dx*dy | dpower
+    }
+    // ---- level 2 (xor 8)
+    float W2[2], P2[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        W2[t] = W[t] + __shfl_xor_sync(FULL, W[t + 2], 8);
+        const float send = f.r2 ? P[t] : P[t + 2], keep = f.r2 ? P[t + 2] : P[t];
+        P2[t] = keep + __shfl_xor_sync(FULL, send, 8);
+    }
+    // ---- level 3 (xor 4)
+    const float W1 = W2[0] + __shfl_xor_sync(FULL, W2[1], 4);
+    const float send3 = f.r3 ? P2[0] : P2[1], keep3 = f.r3 ? P2[1] : P2[0];
+    const float P1 = keep3 + __shfl_xor_sync(FULL, send3, 4);
+    // ---- level 4 (xor 2): the lane keeps the W-group value (r4 = 0) or the P-group value (r4 = 1)
+    const float send4 = f.r4 ? W1 : P1, keep4 = f.r4 ? P1 : W1;
+    float r = keep4 + __shfl_xor_sync(FULL, send4, 2);
+    r += __shfl_xor_sync(FULL, r, 1);
+    return r;
+}
+
 // K5.  CTA = one 16x16 tile of one view, 256 / PX threads: every warp owns a block of 8 x (4*PX) pixels,
 // every lane PX pixels of one column (rows y, y+4, ...).  The partials of a lane's pixels are summed in
 // registers BEFORE the cross-lane reduction, so a splat costs one reduction + one 15-lane RED per
@@ -514,6 +599,7 @@ __global__ void __launch_bounds__(256 / PX, PX == 1 ? AGS_BWD_MINB : (PX == 2 ? 
 composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
     constexpr int THREADS = 256 / PX, WARPS = 8 / PX;
     constexpr int RED_FLOATS = RED == 0 ? 15 * RED_STRIDE : (RED == 1 ? RED1_FLOATS : 4);
+    static_assert(RED != 3 || PX == 1, "the folded butterfly is written for one pixel per lane");
     __shared__ SplatRec s_rec[BATCH];
     __shared__ int s_id[BATCH];
     __shared__ int s_max_last;
@@ -557,7 +643,24 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
         red_st = (unsigned)__cvta_generic_to_shared(&s_red[wid][RED == 0 ? lane : 0]);
         red_ld = (unsigned)__cvta_generic_to_shared(&s_red[wid][RED == 0 ? (lane >> 1) * RED_STRIDE + (lane & 1) * 16 : 0]);
     }
-    float* const dsplat_lane = w.dsplat + vN * 16 + (lane >> 1);
+    // record slot this lane's reduced value goes to (AGS_REC_*): the folded butterfly ends with slot
+    // r4*8 + r1*4 + r2*2 + r3; the others with partial (lane >> 1) in the order of bwd_accumulate
+    int rec_slot;
+    bool rec_lane;
+    FoldLane fold;
+    if (RED == 3) {
+        fold_setup(fold, s[0], lane);
+        rec_slot = ((lane >> 1) & 1) * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        rec_lane = (lane & 1) == 0 && rec_slot != AGS_REC_PAD;
+    } else {
+        const int q = lane >> 1;
+        rec_slot = q == 0 ? AGS_REC_PDX : q == 1 ? AGS_REC_PDY : q == 2 ? AGS_REC_PXX : q == 3 ? AGS_REC_PXY
+                 : q == 4 ? AGS_REC_PYY : q == 5 ? AGS_REC_P1 : q == 6 ? AGS_REC_C0 : q == 7 ? AGS_REC_C0 + 1
+                 : q == 8 ? AGS_REC_C0 + 2 : q == 9 ? AGS_REC_N0 : q == 10 ? AGS_REC_N0 + 1 : q == 11 ? AGS_REC_N0 + 2
+                 : q == 12 ? AGS_REC_WD : q == 13 ? AGS_REC_WDX : AGS_REC_WDY;
+        rec_lane = (lane & 1) == 0 && lane < 30;
+    }
+    float* const dsplat_lane = w.dsplat + vN * 16 + rec_slot;
     for (int base = 0; base < n_eff; base += BATCH) {
         __syncthreads();
 #pragma unroll
@@ -609,6 +712,11 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
                 }
                 if (any == 0u) continue;
                 const float4 f0 = rec.f0, f1 = rec.f1;
+                if (RED == 3) {                              // PX == 1 only (launcher)
+                    const float r = bwd_pair_fold<HAS_CONF>(s[0], fold, g1, f0, f1, dx, eDy[0], eA[0], eG[0], act[0]);
+                    if (rec_lane) atomicAdd(dsplat_lane + (size_t)s_id[k] * 16, r);
+                    continue;
+                }
                 float val[15];
                 if (PX == 1) {
                     bwd_accumulate<true, HAS_CONF>(val, s[0], g1, f0, f1, dx, eDy[0], eA[0], eG[0], act[0]);
@@ -651,13 +759,14 @@ static int bwd_px() {
 }
 
 // Cross-lane reduction of the 15 partials: 0 = shared-memory transposition, 1 = one shuffle step + half
-// transposition, 2 = register butterfly.  AGS_BWD_RED overrides the default for tuning runs.
+// transposition, 2 = register butterfly, 3 = register butterfly with folded selects (one pixel per lane).
+// AGS_BWD_RED overrides the default for tuning runs.
 static int bwd_red() {
     static int red = -1;
     if (red < 0) {
         const char* e = getenv("AGS_BWD_RED");
         red = e ? atoi(e) : AGS_BWD_RED_DEFAULT;
-        if (red < 0 || red > 2) red = AGS_BWD_RED_DEFAULT;
+        if (red < 0 || red > 3) red = AGS_BWD_RED_DEFAULT;
     }
     return red;
 }
@@ -674,6 +783,7 @@ static void launch_bwd(const AgsRenderArgs& a, const AgsRenderGradArgs& g, const
     switch (bwd_red()) {
         case 0: launch_bwd2<PX, 0>(a, g, w, grid); break;
         case 1: launch_bwd2<PX, 1>(a, g, w, grid); break;
+        case 3: if (PX == 1) { launch_bwd2<1, 3>(a, g, w, grid); break; }   // else: fall through
         default: launch_bwd2<PX, 2>(a, g, w, grid); break;
     }
 }

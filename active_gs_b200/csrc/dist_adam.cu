@@ -35,6 +35,7 @@ struct DistAdamParams {
     int groups;
     float b1, b2, eps;
     int step;
+    SyncP sync;
 };
 
 __device__ __forceinline__ float4 ld_peer4(const float* p) {          // bypass L1: written by another GPU
@@ -76,11 +77,20 @@ __device__ __forceinline__ float lr_of(const DistAdamParams& P, long long e) {
 // peers costs occupancy (162 registers: 135 us).
 __global__ void __launch_bounds__(256)
 dist_adam_kernel(DistAdamParams P) {
+    // folded barrier: this kernel runs after the rank's own backward (stream order), so block 0 can tell
+    // every rank "my gradients are complete" right away; then every block waits for all ranks
+    if (P.sync.on) {
+        if (blockIdx.x == 0) sync_signal(P.sync, AGS_SYNC_GRADS);
+        sync_wait(P.sync, AGS_SYNC_GRADS);
+    }
     // any rank's overflow flag skips the step everywhere; the peer loads are issued together
     int skip = 0;
     for (int p = 0; p < P.world; ++p)
         if (P.skip[p]) skip |= *reinterpret_cast<const volatile int*>(P.skip[p]);
-    if (skip) return;
+    if (skip) {
+        if (P.sync.on && sync_last_block(P.sync, AGS_SYNC_PARAMS)) sync_signal(P.sync, AGS_SYNC_PARAMS);
+        return;
+    }
     __shared__ float s_c[2];
     if (threadIdx.x == 0) {                     // bias corrections once per block (double pow)
         const double bc1 = 1.0 - pow((double)P.b1, (double)P.step);
@@ -141,6 +151,8 @@ dist_adam_kernel(DistAdamParams P) {
         }
     }
     __threadfence_system();
+    // every rank's parameter buffer holds this rank's updated shard once the last block is done
+    if (P.sync.on && sync_last_block(P.sync, AGS_SYNC_PARAMS)) sync_signal(P.sync, AGS_SYNC_PARAMS);
 }
 
 }  // namespace
@@ -177,6 +189,7 @@ extern "C" int ags_dist_adam_step(const AgsDistAdamArgs* a) {
     P.shard_begin = C * a->rank; P.shard_end = C * (a->rank + 1);
     P.groups = a->num_groups;
     P.b1 = a->beta1; P.b2 = a->beta2; P.eps = a->eps; P.step = a->step;
+    P.sync = make_sync(a->sync, a->world, a->rank);
     const long long n4 = C / 4;
     long long blocks = (n4 + 255) / 256;
     if (blocks > 148 * 2) blocks = 148 * 2;          // one wave (see the kernel's note)

@@ -24,22 +24,27 @@ struct VisParams {
     const int32_t* peers[AGS_MAX_PEERS];
     const int32_t* mc;
     int32_t* out;
+    SyncP sync;
 };
 
 __global__ void __launch_bounds__(256)
 dist_vis_local_kernel(VisParams a) {
     const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.P) return;
-    int c = 0;
-    for (int f = 0; f < a.B; ++f) {
-        const bool real = !a.frame_weight || __ldg(a.frame_weight + f) != 0.f;      // padded frames do not count
-        c += (real && __ldg(a.opacity + (size_t)f * a.P + p) > 1e-3f) ? 1 : 0;
+    if (p < a.P) {
+        int c = 0;
+        for (int f = 0; f < a.B; ++f) {
+            const bool real = !a.frame_weight || __ldg(a.frame_weight + f) != 0.f;      // padded frames do not count
+            c += (real && __ldg(a.opacity + (size_t)f * a.P + p) > 1e-3f) ? 1 : 0;
+        }
+        a.vis_local[p] = c;
     }
-    a.vis_local[p] = c;
+    // the plane is complete when the last block is: tell every rank (folded barrier, AGS_SYNC_VIS)
+    if (a.sync.on && sync_last_block(a.sync, AGS_SYNC_VIS)) sync_signal(a.sync, AGS_SYNC_VIS);
 }
 
 __global__ void __launch_bounds__(256)
 dist_vis_sum_kernel(VisParams a) {
+    sync_wait(a.sync, AGS_SYNC_VIS);                 // every rank's plane is complete
     const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.P) return;
     int s;
@@ -62,24 +67,29 @@ struct TermsParams {
     const int32_t* stats;
     float* peers[AGS_MAX_PEERS];
     float* mc;
+    SyncP sync;
 };
 
 __global__ void dist_terms_put_kernel(TermsParams a) {
     const int k = threadIdx.x;
-    if (k >= a.nterm) return;
-    const int nt = a.nterm - a.nview - 2;            // layout: terms | per-view instances | instances, overflow
-    const float v = (k < nt) ? a.terms[k]
-                  : (k < nt + a.nview) ? (float)a.stats[AGS_STAT_VIEW0 + (k - nt)]
-                  : (float)a.stats[k - (nt + a.nview)];
-    const size_t slot = (size_t)a.rank * a.nterm + k;
-    if (a.mc) {
-        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" :: "l"(a.mc + slot), "f"(v) : "memory");
-    } else {
-        for (int r = 0; r < a.world; ++r)
-            asm volatile("st.global.relaxed.sys.f32 [%0], %1;" :: "l"(a.peers[r] + slot), "f"(v) : "memory");
+    if (k < a.nterm) {
+        const int nt = a.nterm - a.nview - 2;            // layout: terms | per-view instances | instances, overflow
+        const float v = (k < nt) ? a.terms[k]
+                      : (k < nt + a.nview) ? (float)a.stats[AGS_STAT_VIEW0 + (k - nt)]
+                      : (float)a.stats[k - (nt + a.nview)];
+        const size_t slot = (size_t)a.rank * a.nterm + k;
+        if (a.mc) {
+            asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" :: "l"(a.mc + slot), "f"(v) : "memory");
+        } else {
+            for (int r = 0; r < a.world; ++r)
+                asm volatile("st.global.relaxed.sys.f32 [%0], %1;" :: "l"(a.peers[r] + slot), "f"(v) : "memory");
+        }
     }
     __threadfence_system();
+    sync_signal(a.sync, AGS_SYNC_TERMS);             // single block: its stores are out
 }
+
+__global__ void dist_wait_kernel(SyncP s, int phase) { sync_wait(s, phase); }
 
 int fill_vis(const AgsDistVisArgs* a, VisParams& P, bool need_peers) {
     AGS_CHECK_ARG(a != nullptr, "args is NULL");
@@ -87,6 +97,7 @@ int fill_vis(const AgsDistVisArgs* a, VisParams& P, bool need_peers) {
     AGS_CHECK_ARG(a->B > 0 && a->H > 0 && a->W > 0 && (long long)a->H * a->W < (1ll << 31), "bad sizes");
     AGS_CHECK_ARG(a->vis_local != nullptr, "NULL vis_local");
     P.world = a->world; P.B = a->B; P.P = (unsigned)a->H * (unsigned)a->W;
+    P.sync = make_sync(a->sync, a->world, a->rank);
     P.opacity = a->opacity; P.frame_weight = a->frame_weight; P.vis_local = a->vis_local; P.mc = a->vis_multicast; P.out = a->vis_count;
     for (int r = 0; r < AGS_MAX_PEERS; ++r) {
         P.peers[r] = r < a->world ? a->vis_peers[r] : nullptr;
@@ -127,11 +138,22 @@ extern "C" int ags_dist_terms_put(const AgsDistTermsArgs* a) {
     TermsParams P;
     P.world = a->world; P.rank = a->rank; P.nterm = a->nterm; P.nview = a->nview; P.terms = a->terms; P.stats = a->stats;
     P.mc = a->gather_multicast;
+    P.sync = make_sync(a->sync, a->world, a->rank);
     for (int r = 0; r < AGS_MAX_PEERS; ++r) {
         P.peers[r] = r < a->world ? a->gather_peers[r] : nullptr;
         if (!a->gather_multicast && r < a->world) AGS_CHECK_ARG(a->gather_peers[r] != nullptr, "NULL peer pointer %d", r);
     }
     ags_note_launch(); dist_terms_put_kernel<<<1, ((a->nterm + 31) / 32) * 32, 0, (cudaStream_t)a->stream>>>(P);
+    AGS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ags_dist_wait(const AgsDistSync* sync, int32_t phase, int32_t world, int32_t rank, void* stream) {
+    AGS_CHECK_ARG(sync != nullptr && sync->peers[0] != nullptr, "NULL sync");
+    AGS_CHECK_ARG(world >= 1 && world <= AGS_MAX_PEERS && rank >= 0 && rank < world, "bad world/rank %d/%d", world, rank);
+    AGS_CHECK_ARG(phase >= 0 && phase < 4, "bad phase %d", phase);
+    for (int r = 0; r < world; ++r) AGS_CHECK_ARG(sync->peers[r] != nullptr, "NULL sync pointer %d", r);
+    ags_note_launch(); dist_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(make_sync(*sync, world, rank), phase);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

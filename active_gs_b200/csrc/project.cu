@@ -369,19 +369,26 @@ project_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
         ViewProj p;
         project_view(p, g, cam, a.H, a.W, false);
         float4* dr = reinterpret_cast<float4*>(w.dsplat + idx * 16);
-        const float4 d0 = dr[0], d1 = dr[1], d2 = dr[2], d3 = dr[3];
+        float rec[16];
+        {
+            const float4 d0 = dr[0], d1 = dr[1], d2 = dr[2], d3 = dr[3];
+            rec[0] = d0.x; rec[1] = d0.y; rec[2] = d0.z; rec[3] = d0.w; rec[4] = d1.x; rec[5] = d1.y; rec[6] = d1.z; rec[7] = d1.w;
+            rec[8] = d2.x; rec[9] = d2.y; rec[10] = d2.z; rec[11] = d2.w; rec[12] = d3.x; rec[13] = d3.y; rec[14] = d3.z; rec[15] = d3.w;
+        }
         if (gr.clear_records) {   // consume-and-clear: a second backward on the same forward starts from zero again
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             dr[0] = z; dr[1] = z; dr[2] = z; dr[3] = z;
         }
-        // the record holds the raw moments accumulated by composite_bwd (composite.cu, bwd_accumulate);
+        // the record holds the raw moments accumulated by composite_bwd (slots AGS_REC_*, ags_common.cuh);
         // the chain rule through the conic, the centre and the plane slopes is applied here, once per splat:
-        //   power = -0.5 (a dx^2 + c dy^2) - b dx dy,  dx = x_splat - x_pixel,  depth(pix) = z - sx dx - sy dy
-        const float M0 = d0.x, M1 = d0.y, M20 = d0.z, M11 = d0.w, M02 = d1.x;
-        const float d_o = d1.y;
-        const float dcol[3] = {d1.z, d1.w, d2.x};
-        float dnv[3] = {d2.y, d2.z, d2.w};
-        const float dz = d3.x, dsx = -d3.y, dsy = -d3.z;
+        //   power = -0.5 (a dx^2 + c dy^2) - b dx dy,  dx = x_splat - x_pixel,  depth(pix) = z - sx dx - sy dy,
+        //   alpha = o * G  =>  dL/do = (sum dpower) / o
+        const float M0 = rec[AGS_REC_PDX], M1 = rec[AGS_REC_PDY], M20 = rec[AGS_REC_PXX], M11 = rec[AGS_REC_PXY],
+                    M02 = rec[AGS_REC_PYY];
+        const float d_o = g.o > 0.f ? rec[AGS_REC_P1] / g.o : 0.f;
+        const float dcol[3] = {rec[AGS_REC_C0], rec[AGS_REC_C0 + 1], rec[AGS_REC_C0 + 2]};
+        float dnv[3] = {rec[AGS_REC_N0], rec[AGS_REC_N0 + 1], rec[AGS_REC_N0 + 2]};
+        const float dz = rec[AGS_REC_WD], dsx = -rec[AGS_REC_WDX], dsy = -rec[AGS_REC_WDY];
         const float dxg = -(p.ca * M0 + p.cb * M1) - p.sx * dz;
         const float dyg = -(p.cc * M1 + p.cb * M0) - p.sy * dz;
         const float dca = -0.5f * M20, dcb = -M11, dcc = -0.5f * M02;

@@ -70,6 +70,22 @@ class SymmetricAux:
         self.h_vis.barrier()
 
 
+class SymmetricSync:
+    """The flags array of the folded cross-GPU ordering (AgsDistSync, include/ags_b200.h): AGS_SYNC_WORDS int32 per
+    rank, peer-mapped; producers store the iteration's epoch into every peer's array, consumers spin on their own."""
+
+    def __init__(self, group, device, words=64):
+        import torch.distributed._symmetric_memory as symm
+        self.flags = symm.empty(words, dtype=torch.int32, device=device)
+        self.flags.zero_()
+        g = group if group is not None else dist.group.WORLD
+        self.h = symm.rendezvous(self.flags, g)
+        self.ptrs = [int(p) for p in self.h.buffer_ptrs]
+        self.epoch = 0
+        torch.cuda.synchronize(device)
+        self.h.barrier()                       # everybody's flags are zero before anybody signals
+
+
 class FrameShard:
     def __init__(self, group=None, fused=False):
         self.group = group
@@ -83,12 +99,22 @@ class FrameShard:
         self.use_multicast = self.world >= 4
         self._flat = None
         self._aux = None
+        self._sync = None
+        # fold the four per-iteration barriers into the exchange kernels (signal / wait on symmetric flags)
+        # instead of separate barrier launches; AGS_DIST_BARRIER=1 keeps the barrier launches (A/B runs)
+        import os
+        self.folded = os.environ.get("AGS_DIST_BARRIER", "0") != "1"
 
     def flat_buffers(self, numel, device):
         """symmetric buffers with head-room, re-allocated (collective!) only when the map outgrows them"""
         if self._flat is None or self._flat.numel_padded < numel:
             self._flat = SymmetricFlat(self.group, int(numel * 1.25) + 1024, device)
         return self._flat
+
+    def sync_buffers(self, device):
+        if self._sync is None:
+            self._sync = SymmetricSync(self.group, device)
+        return self._sync
 
     def aux_buffers(self, P, nterm, device):
         """symmetric buffers of the visibility / loss-term exchange (collective allocation)"""

@@ -167,6 +167,8 @@ class _TrainEngine:
         self.host_stats = torch.empty(L.AGS_NUM_STATS, dtype=torch.int32).pin_memory()
         self.event = torch.cuda.Event()
         self.aux = dist_ctx.aux_buffers(H * W, self.nterm, dev) if self.fused else None
+        self.sync = dist_ctx.sync_buffers(dev) if (self.fused and dist_ctx.folded) else None
+        self.sync_wait = None
         self.marks = [] if os.environ.get("AGS_DIST_PROFILE") else None     # (name, event) per segment boundary
         self.loss_outs = [None, None]       # one per ground-truth buffer (each has its own argument struct)
         self.loss_out = None
@@ -325,6 +327,8 @@ class _TrainEngine:
         st = L.current_stream(self.dev)
         fa = self.fwd_args
         fa.stream = st
+        if self.sync is not None:
+            self.sync.epoch += 1                      # one epoch per enqueued iteration (retries included)
         self._mark("start")
         L.check(lib.ags_render_forward(C.byref(fa)), "ags_render_forward")
         self._mark("forward")
@@ -417,12 +421,16 @@ class _TrainEngine:
             for p in range(d.world):
                 a.vis_peers[p] = x.vis_ptrs[p]
             a.vis_multicast = x.vis_mc if (d.use_multicast and x.vis_mc) else None
+            self._fill_sync(a.sync)
             self.vis_args = a
         a.stream = st
+        if self.sync is not None:
+            a.sync.epoch = self.sync.epoch
         L.check(lib.ags_dist_vis_local(C.byref(a)), "ags_dist_vis_local")
         self._mark("vis local")
-        x.barrier()
-        self._mark("barrier A")
+        if self.sync is None:
+            x.barrier()
+            self._mark("barrier A")
         L.check(lib.ags_dist_vis_sum(C.byref(a)), "ags_dist_vis_sum")
         self._mark("vis sum")
         return self.vis_count
@@ -437,12 +445,18 @@ class _TrainEngine:
             for p in range(d.world):
                 a.gather_peers[p] = x.gather_ptrs[p]
             a.gather_multicast = x.gather_mc if (d.use_multicast and x.gather_mc) else None
+            self._fill_sync(a.sync)
             self.terms_args = a
         a.stats = L.ptr(self.rb.stats)
         a.terms = L.ptr(lo.terms)
         a.stream = st
+        if self.sync is not None:
+            a.sync.epoch = self.sync.epoch
         L.check(lib.ags_dist_terms_put(C.byref(a)), "ags_dist_terms_put")
-        x.barrier()
+        if self.sync is None:
+            x.barrier()
+        else:
+            self._wait(lib, L.SYNC_TERMS, st)          # every rank's terms have landed in the local gather buffer
         self._mark("terms put + barrier T")
         self.host.copy_(x.gather, non_blocking=True)
 
@@ -466,15 +480,41 @@ class _TrainEngine:
                 a.lr[k] = self.lrs[k]
             a.numel_padded = f.numel_padded
             a.beta1, a.beta2, a.eps = 0.9, 0.999, 1e-15
+            self._fill_sync(a.sync)
             self.dist_args = a
         a.step = self.step
         a.stream = st
-        f.barrier()                                  # every rank's gradients are complete
-        self._mark("barrier G1")
+        if self.sync is None:
+            f.barrier()                                  # every rank's gradients are complete
+            self._mark("barrier G1")
+            L.check(lib.ags_dist_adam_step(C.byref(a)), "ags_dist_adam_step")
+            self._mark("dist adam")
+            f.barrier()                                  # every rank's parameters are updated
+            self._mark("barrier G2")
+            return
+        # folded: the kernel signals "my gradients are complete" on entry, waits for all ranks, and signals
+        # "my shard is in everybody's parameter buffer" from its last block; the next forward (or the end of
+        # training) waits for that signal of all ranks
+        a.sync.epoch = self.sync.epoch
         L.check(lib.ags_dist_adam_step(C.byref(a)), "ags_dist_adam_step")
         self._mark("dist adam")
-        f.barrier()                                  # every rank's parameters are updated
-        self._mark("barrier G2")
+        self._wait(lib, L.SYNC_PARAMS, st)
+        self._mark("wait params")
+
+    def _fill_sync(self, sy):
+        if self.sync is None:
+            return
+        for p in range(self.dist.world):
+            sy.peers[p] = self.sync.ptrs[p]
+        sy.epoch = self.sync.epoch
+
+    def _wait(self, lib, phase, st):
+        sy = self.sync_wait
+        if sy is None:
+            sy = self.sync_wait = L.DistSync()
+            self._fill_sync(sy)
+        sy.epoch = self.sync.epoch
+        L.check(lib.ags_dist_wait(C.byref(sy), phase, self.dist.world, self.dist.rank, st), "ags_dist_wait")
 
     def fetch(self):
         """Wait for the loss terms / per-frame performance / instance statistics of the step that

@@ -73,6 +73,13 @@ class AdamArgs(C.Structure):
 MAX_PEERS = 8
 
 
+class DistSync(C.Structure):
+    _fields_ = [("peers", _f * 8), ("epoch", C.c_int32)]
+
+
+SYNC_VIS, SYNC_TERMS, SYNC_GRADS, SYNC_PARAMS, SYNC_WORDS = 0, 1, 2, 3, 64
+
+
 class DistAdamArgs(C.Structure):
     _fields_ = [
         ("world", C.c_int32), ("rank", C.c_int32), ("num_groups", C.c_int32), ("step", C.c_int32),
@@ -80,6 +87,7 @@ class DistAdamArgs(C.Structure):
         ("grad_multicast", _f), ("param_multicast", _f), ("exp_avg", _f), ("exp_avg_sq", _f),
         ("numel", C.c_int64 * ADAM_GROUPS), ("numel_padded", C.c_int64), ("lr", C.c_float * ADAM_GROUPS),
         ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("stream", _f),
+        ("sync", DistSync),
     ]
 
 
@@ -87,7 +95,7 @@ class DistVisArgs(C.Structure):
     _fields_ = [
         ("world", C.c_int32), ("rank", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("opacity", _f), ("vis_local", _f), ("vis_peers", _f * MAX_PEERS), ("vis_multicast", _f),
-        ("vis_count", _f), ("stream", _f), ("frame_weight", _f),
+        ("vis_count", _f), ("stream", _f), ("frame_weight", _f), ("sync", DistSync),
     ]
 
 
@@ -95,7 +103,7 @@ class DistTermsArgs(C.Structure):
     _fields_ = [
         ("world", C.c_int32), ("rank", C.c_int32), ("nterm", C.c_int32), ("nview", C.c_int32), ("terms", _f),
         ("stats", _f),
-        ("gather_peers", _f * MAX_PEERS), ("gather_multicast", _f), ("stream", _f),
+        ("gather_peers", _f * MAX_PEERS), ("gather_multicast", _f), ("stream", _f), ("sync", DistSync),
     ]
 
 
@@ -147,7 +155,7 @@ EXPORTS = ["ags_scratch_bytes", "ags_render_forward", "ags_render_backward", "ag
            "ags_dist_adam_step", "ags_smooth_depth", "ags_stage_cameras",
            "ags_spawn_scratch_bytes", "ags_spawn", "ags_view_stats_update", "ags_prune_scratch_bytes",
            "ags_prune_compact", "ags_view_utility", "ags_dist_vis_local", "ags_dist_vis_sum", "ags_dist_terms_put",
-           "ags_voxel_roi",
+           "ags_voxel_roi", "ags_dist_wait",
            "ags_last_error", "ags_version", "ags_launch_count"]
 
 
@@ -197,6 +205,8 @@ def load():
         getattr(lib, name).restype = C.c_int
     lib.ags_voxel_roi.argtypes = [C.POINTER(VoxelRoiArgs)]
     lib.ags_voxel_roi.restype = C.c_int
+    lib.ags_dist_wait.argtypes = [C.POINTER(DistSync), C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.ags_dist_wait.restype = C.c_int
     lib.ags_dist_adam_step.argtypes = [C.POINTER(DistAdamArgs)]
     lib.ags_dist_adam_step.restype = C.c_int
     lib.ags_postprocess.argtypes = [C.c_int32] * 3 + [C.c_void_p] * 7

@@ -203,6 +203,25 @@ int ags_adam_step(const AgsAdamArgs* args);
  * The flat vector holds the AGS_ADAM_GROUPS parameter tensors back to back (numel[], lr[]), padded to
  * numel_padded (multiple of 4*world); rank r updates [r*C, (r+1)*C), C = numel_padded/world. */
 #define AGS_MAX_PEERS 8
+
+/* Cross-GPU ordering folded into the exchange kernels (instead of a separate barrier launch between them):
+ * every rank owns a symmetric int32 array `flags` of AGS_SYNC_WORDS words.  A producer kernel, once ALL its
+ * blocks are done, stores `epoch` into word [phase*AGS_MAX_PEERS + rank] of every peer's array (release,
+ * system scope); a consumer kernel spins (acquire) on its OWN array until all `world` words of the phase
+ * have reached `epoch`.  `epoch` must grow by one per iteration.  peers[0] == NULL disables the folding
+ * (the caller then brackets the kernels with its own barriers). */
+#define AGS_SYNC_WORDS 64
+#define AGS_SYNC_VIS 0      /* ags_dist_vis_local  -> ags_dist_vis_sum */
+#define AGS_SYNC_TERMS 1    /* ags_dist_terms_put  -> ags_dist_wait(AGS_SYNC_TERMS) before the D2H of the gather buffer */
+#define AGS_SYNC_GRADS 2    /* start of ags_dist_adam_step (this rank's gradients are complete) -> its reduce phase */
+#define AGS_SYNC_PARAMS 3   /* end of ags_dist_adam_step -> ags_dist_wait(AGS_SYNC_PARAMS) before the next forward */
+typedef struct AgsDistSync {
+    int32_t* peers[AGS_MAX_PEERS];  /* the flags array of every rank (index = rank) */
+    int32_t epoch;
+} AgsDistSync;
+/* one tiny kernel: wait until all ranks have signalled `phase` for sync->epoch */
+int ags_dist_wait(const AgsDistSync* sync, int32_t phase, int32_t world, int32_t rank, void* stream);
+
 typedef struct AgsDistAdamArgs {
     int32_t world, rank;
     int32_t num_groups;
@@ -219,6 +238,7 @@ typedef struct AgsDistAdamArgs {
     float lr[AGS_ADAM_GROUPS];
     float beta1, beta2, eps;
     void* stream;
+    AgsDistSync sync;                           /* folded ordering (AGS_SYNC_GRADS in, AGS_SYNC_PARAMS out) */
 } AgsDistAdamArgs;
 int ags_dist_adam_step(const AgsDistAdamArgs* args);
 
@@ -238,6 +258,7 @@ typedef struct AgsDistVisArgs {
     int32_t* vis_count;                         /* local (H,W) output of ags_dist_vis_sum */
     void* stream;
     const float* frame_weight;                  /* optional (B): frames with weight 0 (padding) are not counted */
+    AgsDistSync sync;                           /* folded ordering (AGS_SYNC_VIS) */
 } AgsDistVisArgs;
 int ags_dist_vis_local(const AgsDistVisArgs* args);
 int ags_dist_vis_sum(const AgsDistVisArgs* args);
@@ -254,6 +275,7 @@ typedef struct AgsDistTermsArgs {
     float* gather_peers[AGS_MAX_PEERS];         /* symmetric (world*nterm) float buffer on every rank */
     float* gather_multicast;                    /* its NVLS multicast address or NULL */
     void* stream;
+    AgsDistSync sync;                           /* folded ordering (AGS_SYNC_TERMS) */
 } AgsDistTermsArgs;
 int ags_dist_terms_put(const AgsDistTermsArgs* args);
 
