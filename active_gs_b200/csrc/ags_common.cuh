@@ -54,8 +54,14 @@ struct AgsWorkspace {
     int32_t* inst_sorted;  // (inst_cap) gaussian ids, front-to-back per tile
     float* final_T;        // (B*P)
     int32_t* n_contrib;    // (B*P) index+1 of the last instance that contributed
+    float4* inst_rec;      // (inst_cap * 5) depth-sorted 80-byte staging records per tile, or NULL: written by
+                           // composite_fwd, bulk-copied (TMA) by composite_bwd -- only with AGS_BWD_TMA=1
     size_t total;
 };
+
+// AGS_BWD_TMA=1 in the environment (read once): composite_fwd also writes the sorted staging records and
+// composite_bwd stages its batches with cp.async.bulk + mbarrier instead of gathering them
+bool ags_use_tma();
 
 __host__ __device__ inline size_t ags_align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -83,6 +89,7 @@ inline AgsWorkspace ags_carve(void* base, int N, int B, int H, int W, int inst_c
     w.inst_sorted = (int32_t*)take((size_t)inst_cap * 4);
     w.final_T = (float*)take(BP * 4);
     w.n_contrib = (int32_t*)take(BP * 4);
+    w.inst_rec = ags_use_tma() ? (float4*)take((size_t)inst_cap * 80) : nullptr;
     w.total = off;
     return w;
 }

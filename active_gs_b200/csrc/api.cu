@@ -2,6 +2,7 @@
 // carving, kernel sequencing).  No torch types, no allocation, no synchronisation.
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include "ags_common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -11,6 +12,15 @@ void ags_set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool ags_use_tma() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("AGS_BWD_TMA");
+        on = (e && atoi(e) != 0) ? 1 : 0;
+    }
+    return on == 1;
 }
 
 static unsigned long long g_launches = 0;   // host-side, one mapper thread per process (SURVEY 8b threading)

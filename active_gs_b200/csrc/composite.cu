@@ -29,6 +29,28 @@ struct __align__(16) SplatRec {
 
 #define AGS_LOG2E 1.4426950408889634f
 
+__device__ __forceinline__ void store_rec(float4* base, size_t i, const SplatRec& r) {
+    float4* p = base + i * 5;
+    p[0] = r.g0; p[1] = r.g1; p[2] = r.f0; p[3] = r.f1; p[4] = r.bb;
+}
+
+// TMA bulk copy (cp.async.bulk, 1-D) of contiguous staging records into shared memory, completion on an mbarrier
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+                 :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {      // MUFU.EX2, flush-to-zero, no range fix-up
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -219,13 +241,15 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
         __syncthreads();            // every key has been read: the records may overwrite them
         if (tid < n) {
             s_id[rank] = id;
-            SplatRec& r = s_rec[rank];
+            SplatRec r;
             r.g0 = make_float4(g0.x, g0.y, g0.z * AGS_LOG2E, g0.w * AGS_LOG2E);   // conic * log2(e)
             r.g1 = make_float4(g1.x * AGS_LOG2E, g1.y, g1.z, g1.w);
             r.f0 = ldg4(w.feat0 + vN + id);
             r.f1 = ldg4(w.feat1 + vN + id);
             r.bb = splat_bbox(g0, g1);
+            s_rec[rank] = r;
             w.inst_sorted[off + rank] = id;                                       // the backward walks the same order
+            if (w.inst_rec) store_rec(w.inst_rec, off + rank, r);                 // ... and can bulk-copy the records
         }
         prestaged = true;
     } else if (n > 0 && n <= FUSED_SORT_MAX) {
@@ -295,12 +319,14 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
             const size_t idx = vN + id;
             const float4 g0 = ldg4(w.geom0 + idx), g1 = ldg4(w.geom1 + idx);
             s_id[tid] = id;
-            SplatRec& r = s_rec[tid];
+            SplatRec r;
             r.g0 = make_float4(g0.x, g0.y, g0.z * AGS_LOG2E, g0.w * AGS_LOG2E);   // conic * log2(e)
             r.g1 = make_float4(g1.x * AGS_LOG2E, g1.y, g1.z, g1.w);
             r.f0 = ldg4(w.feat0 + idx);
             r.f1 = ldg4(w.feat1 + idx);
             r.bb = splat_bbox(g0, g1);
+            s_rec[tid] = r;
+            if (w.inst_rec) store_rec(w.inst_rec, off + j, r);
         }
         if (!(prestaged && base == 0)) __syncthreads();   // (the rank-sorted first batch was ordered by the barrier above)
         const int cnt = min(BATCH, n - base);
@@ -594,13 +620,19 @@ __device__ __forceinline__ float bwd_pair_fold(BwdPix& s, const FoldLane& f, con
 // (warp block, splat) -- with PX = 4 half as many as with 8x4 blocks -- and the loop control, the record
 // loads and the bounding-box test are shared by the PX pixels.  Sub-blocks of 8x4 pixels the splat's
 // cutoff box does not reach are skipped warp-uniformly.
-template <int PX, bool HAS_CONF, int RED>
+// TMA = true: the batches are NOT gathered by the threads; composite_fwd left the tile's depth-sorted staging
+// records contiguous in global memory (w.inst_rec) and one elected thread copies each batch of up to 256
+// records (20 KB) into shared memory with ONE cp.async.bulk (TMA, completion on an mbarrier), double
+// buffered: the copy of batch b+1 is in flight while the warps composite batch b.
+template <int PX, bool HAS_CONF, int RED, bool TMA>
 __global__ void __launch_bounds__(256 / PX, PX == 1 ? AGS_BWD_MINB : (PX == 2 ? AGS_BWD_PX2_MINB : 8))
 composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
     constexpr int THREADS = 256 / PX, WARPS = 8 / PX;
     constexpr int RED_FLOATS = RED == 0 ? 15 * RED_STRIDE : (RED == 1 ? RED1_FLOATS : 4);
     static_assert(RED != 3 || PX == 1, "the folded butterfly is written for one pixel per lane");
-    __shared__ SplatRec s_rec[BATCH];
+    __shared__ __align__(128) SplatRec s_rec_all[TMA ? 2 * BATCH : BATCH];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    SplatRec* s_rec = s_rec_all;
     __shared__ int s_id[BATCH];
     __shared__ int s_max_last;
     __shared__ __align__(16) float s_red[WARPS][RED_FLOATS];   // per-warp transposition buffer
@@ -661,23 +693,50 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
         rec_lane = (lane & 1) == 0 && lane < 30;
     }
     float* const dsplat_lane = w.dsplat + vN * 16 + rec_slot;
+    if (TMA) {
+        if (tid == 0) {
+            mbar_init(&s_bar[0], 1);
+            mbar_init(&s_bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned bytes = (unsigned)min(BATCH, n_eff) * (unsigned)sizeof(SplatRec);
+            mbar_expect_tx(&s_bar[0], bytes);
+            bulk_g2s(s_rec_all, w.inst_rec + (size_t)off * 5, bytes, &s_bar[0]);
+        }
+    }
     for (int base = 0; base < n_eff; base += BATCH) {
         __syncthreads();
+        if (TMA) {
+            const int b = base / BATCH, buf = b & 1;
+            // everybody is done with batch b-1: its buffer takes batch b+1 while batch b is composited
+            if (tid == 0 && base + BATCH < n_eff) {
+                const unsigned bytes = (unsigned)min(BATCH, n_eff - base - BATCH) * (unsigned)sizeof(SplatRec);
+                mbar_expect_tx(&s_bar[buf ^ 1], bytes);
+                bulk_g2s(s_rec_all + (buf ^ 1) * BATCH, w.inst_rec + (size_t)(off + base + BATCH) * 5, bytes, &s_bar[buf ^ 1]);
+            }
+            for (int t = tid; t < BATCH; t += THREADS)
+                if (base + t < n_eff) s_id[t] = w.inst_sorted[off + base + t];
+            mbar_wait(&s_bar[buf], (unsigned)((b >> 1) & 1));
+            s_rec = s_rec_all + buf * BATCH;
+        } else {
 #pragma unroll
-        for (int h = 0; h < PX; ++h) {                       // THREADS threads stage BATCH records
-            const int t = tid + h * THREADS;
-            const int j = base + t;
-            if (j < n_eff) {
-                const int id = w.inst_sorted[off + j];
-                const size_t idx = vN + id;
-                const float4 g0 = ldg4(w.geom0 + idx), g1 = ldg4(w.geom1 + idx);
-                s_id[t] = id;
-                SplatRec& r = s_rec[t];
-                r.g0 = make_float4(g0.x, g0.y, g0.z * AGS_LOG2E, g0.w * AGS_LOG2E);   // conic * log2(e)
-                r.g1 = make_float4(g1.x * AGS_LOG2E, g1.y, g1.z, g1.w);
-                r.f0 = ldg4(w.feat0 + idx);
-                r.f1 = ldg4(w.feat1 + idx);
-                r.bb = splat_bbox(g0, g1);
+            for (int h = 0; h < PX; ++h) {                       // THREADS threads stage BATCH records
+                const int t = tid + h * THREADS;
+                const int j = base + t;
+                if (j < n_eff) {
+                    const int id = w.inst_sorted[off + j];
+                    const size_t idx = vN + id;
+                    const float4 g0 = ldg4(w.geom0 + idx), g1 = ldg4(w.geom1 + idx);
+                    s_id[t] = id;
+                    SplatRec& r = s_rec[t];
+                    r.g0 = make_float4(g0.x, g0.y, g0.z * AGS_LOG2E, g0.w * AGS_LOG2E);   // conic * log2(e)
+                    r.g1 = make_float4(g1.x * AGS_LOG2E, g1.y, g1.z, g1.w);
+                    r.f0 = ldg4(w.feat0 + idx);
+                    r.f1 = ldg4(w.feat1 + idx);
+                    r.bb = splat_bbox(g0, g1);
+                }
             }
         }
         __syncthreads();
@@ -774,8 +833,13 @@ static int bwd_red() {
 template <int PX, int RED>
 static void launch_bwd2(const AgsRenderArgs& a, const AgsRenderGradArgs& g, const AgsWorkspace& w, dim3 grid) {
     ags_note_launch();
-    if (g.d_confidence) composite_bwd_kernel<PX, true, RED><<<grid, 256 / PX, 0, (cudaStream_t)a.stream>>>(a, g, w);
-    else composite_bwd_kernel<PX, false, RED><<<grid, 256 / PX, 0, (cudaStream_t)a.stream>>>(a, g, w);
+    if (PX == 1 && RED == 3 && w.inst_rec != nullptr) {      // TMA-staged batches (AGS_BWD_TMA=1)
+        if (g.d_confidence) composite_bwd_kernel<1, true, 3, true><<<grid, 256, 0, (cudaStream_t)a.stream>>>(a, g, w);
+        else composite_bwd_kernel<1, false, 3, true><<<grid, 256, 0, (cudaStream_t)a.stream>>>(a, g, w);
+        return;
+    }
+    if (g.d_confidence) composite_bwd_kernel<PX, true, RED, false><<<grid, 256 / PX, 0, (cudaStream_t)a.stream>>>(a, g, w);
+    else composite_bwd_kernel<PX, false, RED, false><<<grid, 256 / PX, 0, (cudaStream_t)a.stream>>>(a, g, w);
 }
 
 template <int PX>
