@@ -193,6 +193,7 @@ __device__ void sort_oversize_tile(const AgsWorkspace& w, int n, int off, uint64
 #ifndef AGS_BWD_MINB
 #define AGS_BWD_MINB 5
 #endif
+template <bool WANT_IMP>
 __global__ void __launch_bounds__(256, AGS_FWD_MINB)
 composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
     // shared memory: the staging records; the same bytes first serve the tile's depth sort
@@ -241,13 +242,12 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
         __syncthreads();            // every key has been read: the records may overwrite them
         if (tid < n) {
             s_id[rank] = id;
-            SplatRec r;
+            SplatRec& r = s_rec[rank];
             r.g0 = make_float4(g0.x, g0.y, g0.z * AGS_LOG2E, g0.w * AGS_LOG2E);   // conic * log2(e)
             r.g1 = make_float4(g1.x * AGS_LOG2E, g1.y, g1.z, g1.w);
             r.f0 = ldg4(w.feat0 + vN + id);
             r.f1 = ldg4(w.feat1 + vN + id);
             r.bb = splat_bbox(g0, g1);
-            s_rec[rank] = r;
             w.inst_sorted[off + rank] = id;                                       // the backward walks the same order
             if (w.inst_rec) store_rec(w.inst_rec, off + rank, r);                 // ... and can bulk-copy the records
         }
@@ -302,9 +302,8 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
     }
     const size_t P = (size_t)a.H * a.W;
     const size_t pix = (size_t)py * a.W + px;
-    const bool want_imp = a.require_importance != 0;
     bool imp_pix = false;
-    if (want_imp && inside) imp_pix = a.render_mask ? (a.render_mask[(size_t)v * P + pix] == 1.f) : true;
+    if (WANT_IMP && inside) imp_pix = a.render_mask ? (a.render_mask[(size_t)v * P + pix] == 1.f) : true;
 
     float T = 1.f;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f, D = 0.f, Cf = 0.f;
@@ -319,13 +318,12 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
             const size_t idx = vN + id;
             const float4 g0 = ldg4(w.geom0 + idx), g1 = ldg4(w.geom1 + idx);
             s_id[tid] = id;
-            SplatRec r;
+            SplatRec& r = s_rec[tid];
             r.g0 = make_float4(g0.x, g0.y, g0.z * AGS_LOG2E, g0.w * AGS_LOG2E);   // conic * log2(e)
             r.g1 = make_float4(g1.x * AGS_LOG2E, g1.y, g1.z, g1.w);
             r.f0 = ldg4(w.feat0 + idx);
             r.f1 = ldg4(w.feat1 + idx);
             r.bb = splat_bbox(g0, g1);
-            s_rec[tid] = r;
             if (w.inst_rec) store_rec(w.inst_rec, off + j, r);
         }
         if (!(prestaged && base == 0)) __syncthreads();   // (the rank-sorted first batch was ordered by the barrier above)
@@ -336,24 +334,30 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
             while (mask) {
                 const int k = c + __ffs(mask) - 1;
                 mask &= mask - 1;
-                if (done) continue;
                 const SplatRec& rec = s_rec[k];
                 const float4 g0 = rec.g0, g1 = rec.g1;
                 const SplatEval e = eval_alpha(g0, g1, pxf, pyf);
-                if (e.skip) continue;
+                // branch-free per lane: a lane that is done, skips the splat or stops here runs the same
+                // arithmetic with weight 0 (one warp-uniform early-out when nobody takes the splat)
+                const bool use = !done && !e.skip;
+                if (__ballot_sync(0xffffffffu, use) == 0u) continue;
                 const float test_T = T * (1.f - e.alpha);
-                if (test_T < AGS_T_EPS) { done = true; continue; }
-                const float wgt = e.alpha * T;
+                const bool stop = use && (test_T < AGS_T_EPS);      // stop BEFORE applying this splat
+                const bool take = use && !stop;
+                done = done || stop;
+                const float wgt = take ? e.alpha * T : 0.f;
                 const float4 f0 = rec.f0, f1 = rec.f1;
                 C0 += wgt * f0.x; C1 += wgt * f0.y; C2 += wgt * f0.z;
                 D += wgt * (f0.w - g1.z * e.dx - g1.w * e.dy);
                 N0 += wgt * f1.x; N1 += wgt * f1.y; N2 += wgt * f1.z;
                 Cf += wgt * f1.w;
-                T = test_T;
-                last = base + k + 1;
-                if (imp_pix && wgt > a.weight_thres) {
-                    atomicAdd(a.count + vN + s_id[k], 1);
-                    atomicAdd(a.importance + vN + s_id[k], wgt);
+                T = take ? test_T : T;
+                last = take ? base + k + 1 : last;
+                if (WANT_IMP) {
+                    if (imp_pix && wgt > a.weight_thres) {
+                        atomicAdd(a.count + vN + s_id[k], 1);
+                        atomicAdd(a.importance + vN + s_id[k], wgt);
+                    }
                 }
             }
             warp_done = __all_sync(0xffffffffu, done);
@@ -800,7 +804,9 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
 int ags_launch_composite_fwd(const AgsRenderArgs& a, const AgsWorkspace& w) {
     dim3 grid((a.W + TILE - 1) / TILE, (a.H + TILE - 1) / TILE, a.B);
     dim3 block(TILE * TILE);
-    ags_note_launch(); composite_fwd_kernel<<<grid, block, 0, (cudaStream_t)a.stream>>>(a, w);
+    ags_note_launch();
+    if (a.require_importance) composite_fwd_kernel<true><<<grid, block, 0, (cudaStream_t)a.stream>>>(a, w);
+    else composite_fwd_kernel<false><<<grid, block, 0, (cudaStream_t)a.stream>>>(a, w);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
