@@ -187,7 +187,9 @@ __device__ __forceinline__ void sync_signal(const SyncP& s, int phase) {
 // the rank's own flags array (word AGS_SYNC_WORDS/2 + phase) and is reset for the next launch
 __device__ __forceinline__ bool sync_last_block(const SyncP& s, int phase) {
     __shared__ int s_last;
-    __threadfence_system();
+    // gpu scope is enough here: the data lives in this GPU's memory and the one block that signals the
+    // peers issues the system-scope fence (sync_signal) after it has observed every other block's arrival
+    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) {
         int32_t* c = s.peers[s.rank] + AGS_SYNC_WORDS / 2 + phase;

@@ -29,8 +29,7 @@ struct VisParams {
 
 __global__ void __launch_bounds__(256)
 dist_vis_local_kernel(VisParams a) {
-    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < a.P) {
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < a.P; p += gridDim.x * blockDim.x) {
         int c = 0;
         for (int f = 0; f < a.B; ++f) {
             const bool real = !a.frame_weight || __ldg(a.frame_weight + f) != 0.f;      // padded frames do not count
@@ -45,20 +44,20 @@ dist_vis_local_kernel(VisParams a) {
 __global__ void __launch_bounds__(256)
 dist_vis_sum_kernel(VisParams a) {
     sync_wait(a.sync, AGS_SYNC_VIS);                 // every rank's plane is complete
-    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.P) return;
-    int s;
-    if (a.mc) {
-        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.s32 %0, [%1];" : "=r"(s) : "l"(a.mc + p) : "memory");
-    } else {
-        s = 0;
-        for (int r = 0; r < a.world; ++r) {
-            int v;
-            asm volatile("ld.global.relaxed.sys.s32 %0, [%1];" : "=r"(v) : "l"(a.peers[r] + p) : "memory");
-            s += v;
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < a.P; p += gridDim.x * blockDim.x) {
+        int s;
+        if (a.mc) {
+            asm volatile("multimem.ld_reduce.relaxed.sys.global.add.s32 %0, [%1];" : "=r"(s) : "l"(a.mc + p) : "memory");
+        } else {
+            s = 0;
+            for (int r = 0; r < a.world; ++r) {
+                int v;
+                asm volatile("ld.global.relaxed.sys.s32 %0, [%1];" : "=r"(v) : "l"(a.peers[r] + p) : "memory");
+                s += v;
+            }
         }
+        a.out[p] = s;
     }
-    a.out[p] = s;
 }
 
 struct TermsParams {
@@ -113,7 +112,9 @@ extern "C" int ags_dist_vis_local(const AgsDistVisArgs* a) {
     int rc = fill_vis(a, P, false);
     if (rc) return rc;
     AGS_CHECK_ARG(a->opacity != nullptr, "NULL opacity");
-    ags_note_launch(); dist_vis_local_kernel<<<(P.P + 255) / 256, 256, 0, (cudaStream_t)a->stream>>>(P);
+    unsigned blocks = (P.P + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;             // grid-stride: every block pays a fence + a counter atomic
+    ags_note_launch(); dist_vis_local_kernel<<<blocks, 256, 0, (cudaStream_t)a->stream>>>(P);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -123,7 +124,9 @@ extern "C" int ags_dist_vis_sum(const AgsDistVisArgs* a) {
     int rc = fill_vis(a, P, true);
     if (rc) return rc;
     AGS_CHECK_ARG(a->vis_count != nullptr, "NULL vis_count");
-    ags_note_launch(); dist_vis_sum_kernel<<<(P.P + 255) / 256, 256, 0, (cudaStream_t)a->stream>>>(P);
+    unsigned blocks = (P.P + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    ags_note_launch(); dist_vis_sum_kernel<<<blocks, 256, 0, (cudaStream_t)a->stream>>>(P);
     AGS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -702,6 +702,10 @@ class GaussianMap:
 
     def end_training(self, ctx):
         ctx.eng.drain()
+        if ctx.eng.fused:
+            # the parameters live in the symmetric flat buffer while training (sub-tensors start at arbitrary
+            # 4-byte offsets there): bring them home into the capacity buffers the per-keyframe kernels expect
+            self._store.adopt(self, 0)
         self.training_performance = ctx.perf_host.to(self.device)
         self.last_train_log = ctx.log
 
