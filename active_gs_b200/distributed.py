@@ -87,7 +87,10 @@ class SymmetricSync:
 
 
 class FrameShard:
+    FLAT_RESERVE = 14 * (1 << 20)            # floats of head-room in the symmetric parameter / gradient buffers
+
     def __init__(self, group=None, fused=False):
+        self.flat_allocations = 0
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -108,7 +111,11 @@ class FrameShard:
     def flat_buffers(self, numel, device):
         """symmetric buffers with head-room, re-allocated (collective!) only when the map outgrows them"""
         if self._flat is None or self._flat.numel_padded < numel:
-            self._flat = SymmetricFlat(self.group, int(numel * 1.25) + 1024, device)
+            # allocation + rendezvous of symmetric memory costs ~100 ms per buffer on an 8-GPU box (measured:
+            # one re-allocation inside a 2-update timed region = 20 ms/step), the bytes are cheap: 2x plus room
+            # for ~1M further Gaussians, so a mapping run re-allocates O(log) times
+            self._flat = SymmetricFlat(self.group, 2 * int(numel) + self.FLAT_RESERVE, device)
+            self.flat_allocations += 1
         return self._flat
 
     def sync_buffers(self, device):
@@ -158,25 +165,39 @@ class FrameShard:
         local_batch(len(ids)); slots left over when len(ids) is not a multiple of the world size hold -1.
         Deterministic: every rank computes the same answer from the same gathered costs."""
         ids = [int(i) for i in ids]
-        W, b = self.world, self.local_batch(len(ids))
-        known = [cost[i] for i in ids if i in cost]
-        mean = float(np.mean(known)) if known else 0.0
-        c = [float(cost.get(i, mean)) for i in ids]
-        slots = [[None] * b for _ in range(W)]
+        n = len(ids)
+        W, b = self.world, self.local_batch(n)
+        get = cost.get
+        c = [get(i) for i in ids]
+        if None in c:
+            known = [x for x in c if x is not None]
+            mean = (sum(known) / len(known)) if known else 0.0
+            c = [mean if x is None else float(x) for x in c]
+        slots = [[] for _ in range(W)]                 # pinned ids first (slot j // W of rank j % W), then LPT
         load = [0.0] * W
-        free = [b] * W
-        for j in range(min(n_active, len(ids))):
-            r, k = self.pinned_slot(j)
-            slots[r][k] = ids[j]
+        na = min(n_active, n)
+        for j in range(na):
+            r = j % W
+            slots[r].append(ids[j])
             load[r] += c[j]
-            free[r] -= 1
-        rest = sorted(range(min(n_active, len(ids)), len(ids)), key=lambda j: (-c[j], j))
-        for j in rest:
-            r = min((q for q in range(W) if free[q] > 0), key=lambda q: (load[q], q))
-            slots[r][slots[r].index(None)] = ids[j]
-            load[r] += c[j]
-            free[r] -= 1
-        return np.asarray([(-1 if i is None else i) for r in range(W) for i in slots[r]])      # None = padding
+        # longest first onto the least loaded rank that still has a free slot (ties: lower rank): a heap of
+        # (load, rank); a rank leaves the heap when it is full
+        import heapq
+        heap = [(load[r], r) for r in range(W) if len(slots[r]) < b]
+        heapq.heapify(heap)
+        for j in sorted(range(na, n), key=lambda j: (-c[j], j)):
+            l, r = heap[0]
+            sr = slots[r]
+            sr.append(ids[j])
+            if len(sr) < b:
+                heapq.heapreplace(heap, (l + c[j], r))
+            else:
+                heapq.heappop(heap)
+        out = np.full(W * b, -1, dtype=np.int64)       # -1 = padding
+        for r in range(W):
+            sr = slots[r]
+            out[r * b:r * b + len(sr)] = sr
+        return out
 
     def all_reduce_sum_(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)

@@ -36,12 +36,17 @@ class WeightedSampler:
         self.v = len(self.active_ids) + self.selected_num
 
     def next_ids(self, weight_host):
+        """`weight_host`: per-keyframe performance, numpy or torch (host).  When the batch takes EVERY
+        non-active keyframe the draw is the whole population whatever the weights are; the 150 us
+        np.random.choice over it is skipped then (the ids come back in index order, and numpy's global
+        stream is not advanced -- the only place where the stream differs from the reference's)."""
         sel = self.active_ids.copy()
         if self.selected_num > 0:
-            w = torch.as_tensor(weight_host)[self.random_ids_all]
-            w = w / torch.sum(w)
-            drawn = np.random.choice(self.random_ids_all, size=self.selected_num, p=w.numpy(),
-                                     replace=False)
+            if self.selected_num == len(self.random_ids_all):
+                return np.append(sel, self.random_ids_all)
+            w = np.asarray(weight_host, dtype=np.float32)[self.random_ids_all]
+            w = w / np.sum(w, dtype=np.float32)
+            drawn = np.random.choice(self.random_ids_all, size=self.selected_num, p=w, replace=False)
             sel = np.append(sel, self.random_ids_all[drawn])
         return sel
 
@@ -97,11 +102,25 @@ class _MapStore:
         N = gm._means.shape[0]
         if self.owns(gm) and N + extra <= self.cap:
             return
-        cap = max(int(1.5 * (N + extra)) + 1024, 65536)
-        new = self._alloc(cap)
+        if self.buf is not None and N + extra <= self.cap:
+            # tensors assigned from outside (the symmetric flat buffer of the fused multi-GPU engine after
+            # every train() call): copy home into the buffers we already have -- no allocation
+            dst = self.buf
+            if any(getattr(gm, _ATTR[n]).data_ptr() == dst[n].data_ptr() for n, _ in ops.MAP_FIELDS):
+                dst = self.other()                     # partly aliased: go through the ping-pong set
+        else:
+            # grow geometrically (2x + room for the keyframe about to be added): a re-allocation is a
+            # cudaMalloc per field, which with peer mappings enabled costs milliseconds per GPU of the box
+            self.cap = max(2 * (N + extra) + 1024, 262144)
+            dst, self.alt = self._alloc(self.cap), None
         for n, w in ops.MAP_FIELDS:
-            new[n][:N].copy_(getattr(gm, _ATTR[n]).detach().reshape((N, w) if w > 1 else (N,)))
-        self.buf, self.cap, self.alt = new, cap, None
+            src = getattr(gm, _ATTR[n]).detach().reshape((N, w) if w > 1 else (N,))
+            if src.data_ptr() != dst[n].data_ptr():
+                dst[n][:N].copy_(src)
+        if dst is self.alt:
+            self.swap()
+        else:
+            self.buf = dst
         self.expose(gm, N)
 
     def expose(self, gm, n):
@@ -165,6 +184,7 @@ class _TrainEngine:
         self.terms_all = torch.empty(self.world * self.nterm, **o) if dist_ctx else None
         self.terms_loc = torch.empty(self.nterm, **o) if dist_ctx else None
         self.host_stats = torch.empty(L.AGS_NUM_STATS, dtype=torch.int32).pin_memory()
+        self.host_np, self.host_stats_np = self.host.numpy(), self.host_stats.numpy()
         self.event = torch.cuda.Event()
         self.aux = dist_ctx.aux_buffers(H * W, self.nterm, dev) if self.fused else None
         self.sync = dist_ctx.sync_buffers(dev) if (self.fused and dist_ctx.folded) else None
@@ -203,8 +223,12 @@ class _TrainEngine:
             gm._means, gm._scales, gm._rotations, gm._opacities, gm._harmonics = views
             self.params = views
             self.grad_flat = self.flat.grad
-            self.m_flat = gm._pool.floats("adam_m", self.flat.numel_padded, zero=True)
-            self.v_flat = gm._pool.floats("adam_v", self.flat.numel_padded, zero=True)
+            # the exchange covers the live 14*N floats rounded up to 4*world (one 16-byte element per rank),
+            # not the capacity of the symmetric buffers
+            q = 4 * self.world
+            self.active_padded = (total + q - 1) // q * q
+            self.m_flat = gm._pool.floats("adam_m", self.active_padded, zero=True)
+            self.v_flat = gm._pool.floats("adam_v", self.active_padded, zero=True)
         else:
             # gradients are views of ONE flat buffer (14 floats per Gaussian): a single all-reduce in the
             # NCCL-baseline sharded path.  Zeroed once here: the Adam kernel re-zeroes what it consumed.
@@ -478,7 +502,7 @@ class _TrainEngine:
             for k, p in enumerate(self.params):
                 a.numel[k] = p.numel()
                 a.lr[k] = self.lrs[k]
-            a.numel_padded = f.numel_padded
+            a.numel_padded = self.active_padded
             a.beta1, a.beta2, a.eps = 0.9, 0.999, 1e-15
             self._fill_sync(a.sync)
             self.dist_args = a
@@ -518,22 +542,24 @@ class _TrainEngine:
 
     def fetch(self):
         """Wait for the loss terms / per-frame performance / instance statistics of the step that
-        was just enqueued (the sampler needs them, mapping/utils.py:206-218)."""
+        was just enqueued (the sampler needs them, mapping/utils.py:206-218).  Plain numpy on the pinned
+        result buffers: this sits on the host's critical path between two iterations."""
         B = self.B
         self.event.synchronize()
-        h = self.host.clone().view(-1, self.nterm)          # one row per rank
+        h = self.host_np.reshape(-1, self.nterm)            # one row per rank (views of the pinned buffer)
         terms = h[:, :4].sum(0)                             # every rank's terms are already / B_total
         pf = h[:, 4:4 + 2 * B]
-        perf = (pf[:, 0::2] + pf[:, 1::2]).reshape(-1)      # ordered like the (padded) batch
-        stats = self.host_stats.to(torch.int64)
+        perf = (pf[:, 0::2] + pf[:, 1::2]).reshape(-1)      # ordered like the (padded) batch; a fresh array
         nt = 4 + 2 * B
         if self.dist is not None:                           # global view: max instances, any overflow
-            stats[L.STAT_INSTANCES] = int(h[:, self.nterm - 2].max())
-            stats[L.STAT_OVERFLOW] = int(h[:, self.nterm - 1].max())
-            view_cost = h[:, nt:nt + B].reshape(-1)         # instances per frame, ordered like the batch
+            instances = int(h[:, self.nterm - 2].max())
+            overflow = int(h[:, self.nterm - 1].max())
+            view_cost = h[:, nt:nt + B].reshape(-1).copy()  # instances per frame, ordered like the batch
         else:
-            view_cost = stats[L.STAT_VIEW0:L.STAT_VIEW0 + B].float()
-        return terms, perf, stats, view_cost
+            st = self.host_stats_np
+            instances, overflow = int(st[L.STAT_INSTANCES]), int(st[L.STAT_OVERFLOW])
+            view_cost = st[L.STAT_VIEW0:L.STAT_VIEW0 + B].astype(np.float32)
+        return terms, perf, (instances, overflow, int(self.host_stats_np[L.STAT_VISIBLE])), view_cost
 
 
 class GaussianMap:
@@ -652,15 +678,16 @@ class GaussianMap:
         if eng is None or eng.key != key:
             eng = self._engine = _TrainEngine(self, B, H, W, self.dist, on_host=on_host)
         eng.bind(cam_rows.to(self.device), sampler.v)
+        perf_host = self.training_performance.detach().float().cpu().clone()
         return SimpleNamespace(fixed=fixed, sampler=sampler, B=B, H=H, W=W, eng=eng,
-                               perf_host=self.training_performance.detach().float().cpu().clone(), log=[])
+                               perf_host=perf_host, perf_np=perf_host.numpy(), log=[])
 
     def train_step(self, ctx, ids=None):
         """One iteration of mapping/gaussian_map.py:76-127: sample keyframes, stage them, enqueue
         forward/loss/backward/Adam, wait for the loss terms (sampler dependency)."""
         eng = ctx.eng
         sampled = ids is None
-        ids = np.asarray(ids) if ids is not None else ctx.sampler.next_ids(ctx.perf_host)
+        ids = np.asarray(ids) if ids is not None else ctx.sampler.next_ids(ctx.perf_np)
         weights = None
         if self.dist is not None:
             # same keyframes on every rank; the batch is padded to a multiple of the world size (-1 =
@@ -681,23 +708,24 @@ class GaussianMap:
             eng.iterate()
             if sampled:
                 eng.prefetch_next(ctx.fixed, self._frame_gt)
-            terms, perf, stats, view_cost = eng.fetch()
-            if stats[L.STAT_OVERFLOW] == 0:
+            terms, perf, (instances, overflow, visible), view_cost = eng.fetch()
+            if overflow == 0:
                 break
             # capacity exceeded: nothing was rendered and the device-side flag turned the Adam
             # step into a no-op, so grow the workspace and redo the same iteration
             eng.step -= 1
-            eng.grow(int(stats[L.STAT_INSTANCES]))
-        need = float(stats[L.STAT_INSTANCES]) / max(1, eng.N * ctx.B)
+            eng.grow(instances)
+        need = float(instances) / max(1, eng.N * ctx.B)
         self._cap_per_gaussian = max(self._cap_per_gaussian, 1.5 * need)
-        real = ids >= 0
-        rid = torch.as_tensor(ids[real], dtype=torch.long)
-        perf = perf[torch.as_tensor(real)]
-        ctx.perf_host[rid] = perf
-        for i, c in zip(ids[real].tolist(), view_cost[torch.as_tensor(real)].tolist()):
-            self._frame_cost[int(i)] = c
+        if self.dist is not None:
+            real = ids >= 0
+            rid, perf, view_cost = ids[real], perf[real], view_cost[real]
+        else:
+            rid = ids
+        ctx.perf_np[rid] = perf
+        self._frame_cost.update(zip(rid.tolist(), view_cost.tolist()))
         loss = float(terms[0] + 0.8 * terms[1] + 0.1 * terms[2] + 0.1 * terms[3])
-        ctx.log.append((loss, perf.clone(), int(stats[L.STAT_INSTANCES]), int(stats[L.STAT_VISIBLE])))
+        ctx.log.append((loss, perf, instances, visible))
         return loss
 
     def end_training(self, ctx):
