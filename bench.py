@@ -475,12 +475,60 @@ def run_reference(args, rank, world):
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
+def run_gpu_naive(args, rank, world):
+    """GPU-class baseline arm: the reference's call chain -- torch activations,
+    sequential single-view renders, unfused ATen loss, autograd, torch Adam -- on a 3DGS-lineage rasterizer
+    (global cub radix sort, per-pixel atomics; baseline/gpu_naive.cu), same workload, same metric, N=1."""
+    if rank != 0:
+        return None
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    from baseline import gpu_naive as gn
+    from active_gs_b200 import lib as _L
+    clocks = ClockSampler(0)
+    clocks.start()
+    state, start, frames, _, cfg, (H, W, N, T) = build_workload(dev, 0, 1)
+    tr = gn.NaiveTrainer(start, frames, cfg, dev)
+    ids = list(range(B_PER_GPU))                       # T = 8 keyframes: the sampler takes all of them
+    losses = []
+    for _ in range(max(args.warmup, 3)):
+        loss, perf = tr.step(ids)
+        perf.cpu()
+    torch.cuda.synchronize()
+    clocks.mark_begin()
+    l0 = _L.load().ags_launch_count() + gn.lib().naive_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss, perf = tr.step(ids)
+        perf.cpu()                                     # the sampler's D2H of the per-frame errors (mapping/utils.py:206-218)
+        losses.append(loss.detach())
+    e1.record()
+    torch.cuda.synchronize()
+    clocks.mark_end()
+    launches = _L.load().ags_launch_count() + gn.lib().naive_launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    P = H * W
+    value = B_PER_GPU * P * args.steps / (ms / 1e3) / 1e6
+    return {"impl": "gpu_naive", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "iters_per_s": args.steps / (ms / 1e3),
+            "config": {"workload": WORKLOAD_C2 if CONFIG_IDX == 2 else
+                                   f"SURVEY 8d config {CONFIG_IDX}: {N} surfels, {W}x{H}, {B_PER_GPU} keyframes per step",
+                       "gaussians": N, "H": H, "W": W, "keyframes_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU,
+                       "parallelism": "single GPU; 3DGS-lineage structure: per-view global cub radix sort, per-pixel "
+                                      "atomics in the backward, unfused ATen loss, autograd, torch.optim.Adam",
+                       "loss_first": float(losses[0]), "loss_last": float(losses[-1])},
+            "gpu_launches": int(launches), "note": "library kernels only (cub passes count as one); ATen kernels not counted",
+            "e2e": None, "clocks": clocks.stop()}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "gpu_naive"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5],
                     help="SURVEY 8d config index: 2 = 200k/640x480 (headline), 3 = 500k/1280x720, 5 = 1M/1920x1080")
@@ -496,6 +544,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         line = run_reference(args, rank, world)
+    elif args.impl == "gpu_naive":
+        line = run_gpu_naive(args, rank, world)
     else:
         line = run_ours(args, rank, world, local_rank)
     if line is not None:

@@ -86,10 +86,11 @@ def test_product_refuses_cpu_tensors(lib):
 
 
 def test_product_never_imports_the_oracle():
-    """oracle/ is test infrastructure: no module of the product packages may import it."""
+    """oracle/ is test infrastructure and baseline/ is bench-only: no module of the product packages may import them."""
     for pkg in ["active_gs_b200", "diff_gaussian_rasterization_2d"]:
         for dirpath, _, files in os.walk(os.path.join(ROOT, pkg)):
             for f in files:
                 if f.endswith(".py"):
                     src = open(os.path.join(dirpath, f)).read()
                     assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{pkg}/{f} imports oracle"
+                    assert not re.search(r"^\s*(from|import)\s+baseline\b", src, flags=re.M), f"{pkg}/{f} imports baseline"
