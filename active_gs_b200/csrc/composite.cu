@@ -193,6 +193,9 @@ __device__ void sort_oversize_tile(const AgsWorkspace& w, int n, int off, uint64
 #ifndef AGS_BWD_MINB
 #define AGS_BWD_MINB 5
 #endif
+#ifndef AGS_BWD_MMA_MINB
+#define AGS_BWD_MMA_MINB 4    // the MMA reduction keeps 16 constant words per thread: 64 registers, no spills
+#endif
 template <bool WANT_IMP>
 __global__ void __launch_bounds__(256, AGS_FWD_MINB)
 composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
@@ -618,6 +621,140 @@ __device__ __forceinline__ float bwd_pair_fold(BwdPix& s, const FoldLane& f, con
     return r;
 }
 
+// Variant 4: the cross-lane reduction as a TENSOR-CORE matrix product (mma.sync m16n8k8, TF32 split into
+// hi + lo words for fp32-level accuracy).  Every one of the 15 per-splat sums is linear in two per-lane scalars,
+//      sum_l wgt_l * (gC, gN, gD, gD*px)_l       and      sum_l dpower_l * (1, px, py, px^2, px*py, py^2)_l,
+// where the second factors do not depend on the splat once the pixel coordinates are taken relative to the
+// warp block's centre (px in +-3.5, py in +-1.5; the moments about the SPLAT centre follow from the binomial
+// expansion, applied once per (warp block, splat) after the product).  So a warp parks (wgt, dpower) of 8
+// splats in shared memory (2 STS per lane and splat) and then multiplies
+//      D (16 sums x 8 splats) = A (16 x 64: the per-lane constants) * B (64 x 8: the parked scalars)
+// with 20 MMAs: 2.5 per splat instead of 16 SHFL + 15 FADD + 12 FSEL + 16 FMUL.  Rows of D:
+//   0-2 sum w gC | 3-5 sum w gN | 6 sum w gD | 7 sum w gD px | 8 sum dp | 9 sum dp px | 10 sum dp py |
+//   11 sum dp px^2 | 12 sum dp px py | 13 sum dp py^2 | 14 sum w gD (py - 0.5)   (k-block j holds row j of the
+//   8x4 block, so py - 0.5 = j - 2 scales the TF32 words of row 6 exactly) | 15 unused.
+// The position-only constants (rows 8-13) are exact in TF32, so that group needs 2 passes instead of 3.
+constexpr int MMA_N = 8;            // splats per product
+constexpr int MMA_XS = 36;          // floats per staging row: lane stores conflict-free, fragment loads (4g + 8j + t) too
+
+struct __align__(16) MmaStage {
+    float x[2][MMA_N][MMA_XS];     // [wgt | dpower][splat][lane]
+    int pend[MMA_N];                // batch slot of every parked splat
+};
+
+__device__ __forceinline__ uint32_t tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+// same conversion, pinned where it is written: the constants' words are recomputed per product on purpose
+// (hoisting them out of the splat loop costs 24 registers and with them a resident CTA per SM)
+__device__ __forceinline__ uint32_t tf32_hi_pinned(float x) {
+    uint32_t r;
+    asm volatile("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+struct MmaConsts {
+    float w[4][2];                  // rows 0-7 (this thread's row g = lane>>2) for lanes 8j+t and 8j+t+4; split into TF32 words per product
+};
+
+// the per-lane constants of rows 0-7 travel through the (still unused) staging buffer once per tile
+__device__ __forceinline__ void mma_setup(MmaConsts& c, MmaStage& st, const BwdPix& s, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const float pxr = (float)(lane & 7) - 3.5f;
+    float* tmp = &st.x[0][0][0];
+    const float K[8] = {s.gC0, s.gC1, s.gC2, s.gN0, s.gN1, s.gN2, s.gD, s.gD * pxr};
+#pragma unroll
+    for (int r = 0; r < 8; ++r) tmp[r * MMA_XS + lane] = K[r];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) c.w[j][h] = tmp[g * MMA_XS + 8 * j + t + 4 * h];
+    __syncwarp();
+}
+
+// Multiply out the `count` parked splats and add the converted sums to their gradient records.
+__device__ __forceinline__ void mma_flush(const MmaConsts& c, MmaStage& st, int count, const SplatRec* s_rec,
+                                          const int* s_id, float* dsplat_view, float cx, float cy, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    // rows 8-13: a = u + v*py + w2*py^2 with exact small numbers (px = t - 3.5 | t + 0.5, py = j - 1.5)
+    const float x1 = (float)t - 3.5f, x3 = (float)t + 0.5f;
+    const float u1 = g == 0 ? 1.f : g == 1 ? x1 : g == 3 ? x1 * x1 : 0.f;
+    const float u3 = g == 0 ? 1.f : g == 1 ? x3 : g == 3 ? x3 * x3 : 0.f;
+    const float v1 = g == 2 ? 1.f : g == 4 ? x1 : 0.f;
+    const float v3 = g == 2 ? 1.f : g == 4 ? x3 : 0.f;
+    const float w2 = g == 5 ? 1.f : 0.f;
+    const float f14 = g == 6 ? 1.f : 0.f;                      // the threads that own row 6 also feed row 14
+    __syncwarp();
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        {   // wgt group: rows 0-7 (a0, a2) and row 14 (a1, a3 of the row-6 threads), 3 passes
+            const float x0 = st.x[0][g][8 * j + t], xb = st.x[0][g][8 * j + t + 4];
+            const uint32_t b0h = tf32_hi(x0), b1h = tf32_hi(xb);
+            const uint32_t b0l = __float_as_uint(x0 - __uint_as_float(b0h)), b1l = __float_as_uint(xb - __uint_as_float(b1h));
+            const float m = f14 * (float)(j - 2);
+            const uint32_t a0h = tf32_hi_pinned(c.w[j][0]), a2h = tf32_hi_pinned(c.w[j][1]);
+            const float a0lf = c.w[j][0] - __uint_as_float(a0h), a2lf = c.w[j][1] - __uint_as_float(a2h);
+            const uint32_t a0l = __float_as_uint(a0lf), a2l = __float_as_uint(a2lf);
+            const uint32_t a1h = __float_as_uint(m * __uint_as_float(a0h)), a3h = __float_as_uint(m * __uint_as_float(a2h));
+            const uint32_t a1l = __float_as_uint(m * a0lf), a3l = __float_as_uint(m * a2lf);
+            mma_tf32(d, a0h, a1h, a2h, a3h, b0h, b1h);
+            mma_tf32(d, a0l, a1l, a2l, a3l, b0h, b1h);
+            mma_tf32(d, a0h, a1h, a2h, a3h, b0l, b1l);
+        }
+        {   // dpower group: rows 8-13 (a1, a3), exact constants, 2 passes
+            const float x0 = st.x[1][g][8 * j + t], xb = st.x[1][g][8 * j + t + 4];
+            const uint32_t b0h = tf32_hi(x0), b1h = tf32_hi(xb);
+            const uint32_t b0l = __float_as_uint(x0 - __uint_as_float(b0h)), b1l = __float_as_uint(xb - __uint_as_float(b1h));
+            const float py = (float)j - 1.5f;
+            const uint32_t a1 = __float_as_uint(u1 + py * (v1 + py * w2)), a3 = __float_as_uint(u3 + py * (v3 + py * w2));
+            mma_tf32(d, 0u, a1, 0u, a3, b0h, b1h);
+            mma_tf32(d, 0u, a1, 0u, a3, b0l, b1l);
+        }
+        asm volatile("" ::: "memory");      // one k-block at a time: keeps the fragment loads from piling up in registers
+    }
+    // d[0], d[1]: row g of splats 2t, 2t+1;  d[2], d[3]: row g+8.  Moments about the block centre -> about the splat centre
+    const int slot_lo = g < 7 ? g : AGS_REC_WDX;               // rows 0-6 sit at their record slots (AGS_REC_C0/N0/WD)
+    const int slot_hi = g == 0 ? AGS_REC_P1 : g == 1 ? AGS_REC_PDX : g == 2 ? AGS_REC_PDY : g == 3 ? AGS_REC_PXX
+                      : g == 4 ? AGS_REC_PXY : g == 5 ? AGS_REC_PYY : AGS_REC_WDY;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int n = 2 * t + e;
+        const float lo = d[e], hi = d[2 + e];
+        const float P1 = __shfl_sync(0xffffffffu, hi, t), Ppx = __shfl_sync(0xffffffffu, hi, 4 + t),
+                    Ppy = __shfl_sync(0xffffffffu, hi, 8 + t), WD = __shfl_sync(0xffffffffu, lo, 24 + t);
+        if (n < count) {
+            const int k = st.pend[n];
+            const float4 g0 = s_rec[k].g0;
+            const float gx = g0.x - cx, gy = g0.y - cy;          // splat centre relative to the block centre
+            float out_hi;
+            switch (g) {
+                case 0: out_hi = hi; break;
+                case 1: out_hi = gx * P1 - hi; break;
+                case 2: out_hi = gy * P1 - hi; break;
+                case 3: out_hi = gx * (gx * P1 - 2.f * Ppx) + hi; break;
+                case 4: out_hi = gx * (gy * P1 - Ppy) - gy * Ppx + hi; break;
+                case 5: out_hi = gy * (gy * P1 - 2.f * Ppy) + hi; break;
+                default: out_hi = (gy - 0.5f) * lo - hi; break;   // row 14 = sum w gD (py - 0.5); only g == 6 stores it
+            }
+            const float out_lo = g < 7 ? lo : gx * WD - lo;
+            float* rec = dsplat_view + (size_t)s_id[k] * 16;
+            atomicAdd(rec + slot_lo, out_lo);
+            if (g < 7) atomicAdd(rec + slot_hi, out_hi);
+        }
+    }
+    __syncwarp();
+}
+
 // K5.  CTA = one 16x16 tile of one view, 256 / PX threads: every warp owns a block of 8 x (4*PX) pixels,
 // every lane PX pixels of one column (rows y, y+4, ...).  The partials of a lane's pixels are summed in
 // registers BEFORE the cross-lane reduction, so a splat costs one reduction + one 15-lane RED per
@@ -629,11 +766,11 @@ __device__ __forceinline__ float bwd_pair_fold(BwdPix& s, const FoldLane& f, con
 // records (20 KB) into shared memory with ONE cp.async.bulk (TMA, completion on an mbarrier), double
 // buffered: the copy of batch b+1 is in flight while the warps composite batch b.
 template <int PX, bool HAS_CONF, int RED, bool TMA>
-__global__ void __launch_bounds__(256 / PX, PX == 1 ? AGS_BWD_MINB : (PX == 2 ? AGS_BWD_PX2_MINB : 8))
+__global__ void __launch_bounds__(256 / PX, PX == 1 ? (RED == 4 ? AGS_BWD_MMA_MINB : AGS_BWD_MINB) : (PX == 2 ? AGS_BWD_PX2_MINB : 8))
 composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
     constexpr int THREADS = 256 / PX, WARPS = 8 / PX;
-    constexpr int RED_FLOATS = RED == 0 ? 15 * RED_STRIDE : (RED == 1 ? RED1_FLOATS : 4);
-    static_assert(RED != 3 || PX == 1, "the folded butterfly is written for one pixel per lane");
+    constexpr int RED_FLOATS = RED == 0 ? 15 * RED_STRIDE : (RED == 1 ? RED1_FLOATS : (RED == 4 ? (int)(sizeof(MmaStage) / 4) : 4));
+    static_assert((RED != 3 && RED != 4) || PX == 1, "the folded butterfly and the MMA reduction are written for one pixel per lane");
     __shared__ __align__(128) SplatRec s_rec_all[TMA ? 2 * BATCH : BATCH];
     __shared__ __align__(8) uint64_t s_bar[2];
     SplatRec* s_rec = s_rec_all;
@@ -697,6 +834,10 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
         rec_lane = (lane & 1) == 0 && lane < 30;
     }
     float* const dsplat_lane = w.dsplat + vN * 16 + rec_slot;
+    MmaConsts mmac;
+    MmaStage& mst = *reinterpret_cast<MmaStage*>(&s_red[wid][0]);   // RED == 4: the warp's buffer parks (wgt, dpower) of 8 splats
+    int parked = 0;                                            // warp-uniform
+    if (RED == 4) mma_setup(mmac, mst, s[0], lane);
     if (TMA) {
         if (tid == 0) {
             mbar_init(&s_bar[0], 1);
@@ -775,6 +916,29 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
                 }
                 if (any == 0u) continue;
                 const float4 f0 = rec.f0, f1 = rec.f1;
+                if (RED == 4) {                              // PX == 1 only (launcher): park the two scalars, multiply every 8 splats
+                    BwdPix& sp = s[0];
+                    const float alpha = act[0] ? eA[0] : 0.f;
+                    const float G = act[0] ? eG[0] : 0.f;
+                    const float dy = eDy[0];
+                    const float wgt = alpha * sp.T;
+                    const float one_m = 1.f - alpha;
+                    const float dpix = f0.w - g1.z * dx - g1.w * dy;
+                    float sdot = sp.gC0 * f0.x + sp.gC1 * f0.y + sp.gC2 * f0.z + sp.gN0 * f1.x + sp.gN1 * f1.y + sp.gN2 * f1.z + sp.gD * dpix;
+                    if (HAS_CONF) sdot += sp.gCf * f1.w;
+                    sp.rem -= wgt * sdot;
+                    const float dalpha = sp.T * sdot - sp.rem * rcp_approx(one_m);
+                    sp.T *= one_m;
+                    const bool unclamped = (g1.y * G <= AGS_ALPHA_MAX);
+                    mst.x[0][parked][lane] = wgt;
+                    mst.x[1][parked][lane] = unclamped ? alpha * dalpha : 0.f;
+                    if (lane == 0) mst.pend[parked] = k;
+                    if (++parked == MMA_N) {
+                        mma_flush(mmac, mst, MMA_N, s_rec, s_id, w.dsplat + vN * 16, wb.x0 + 3.5f, wb.y0 + 1.5f, lane);
+                        parked = 0;
+                    }
+                    continue;
+                }
                 if (RED == 3) {                              // PX == 1 only (launcher)
                     const float r = bwd_pair_fold<HAS_CONF>(s[0], fold, g1, f0, f1, dx, eDy[0], eA[0], eG[0], act[0]);
                     if (rec_lane) atomicAdd(dsplat_lane + (size_t)s_id[k] * 16, r);
@@ -795,6 +959,10 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
                               : (RED == 1 ? warp_reduce15_half(val, red_st, red_ld, lane) : warp_reduce15_shfl(val, lane));
                 if ((lane & 1) == 0 && lane < 30) atomicAdd(dsplat_lane + (size_t)s_id[k] * 16, r);
             }
+        }
+        if (RED == 4 && parked > 0) {       // the parked splats refer to this batch's records: multiply them out before it is replaced
+            mma_flush(mmac, mst, parked, s_rec, s_id, w.dsplat + vN * 16, wb.x0 + 3.5f, wb.y0 + 1.5f, lane);
+            parked = 0;
         }
     }
 }
@@ -831,7 +999,7 @@ static int bwd_red() {
     if (red < 0) {
         const char* e = getenv("AGS_BWD_RED");
         red = e ? atoi(e) : AGS_BWD_RED_DEFAULT;
-        if (red < 0 || red > 3) red = AGS_BWD_RED_DEFAULT;
+        if (red < 0 || red > 4) red = AGS_BWD_RED_DEFAULT;
     }
     return red;
 }
@@ -854,6 +1022,7 @@ static void launch_bwd(const AgsRenderArgs& a, const AgsRenderGradArgs& g, const
         case 0: launch_bwd2<PX, 0>(a, g, w, grid); break;
         case 1: launch_bwd2<PX, 1>(a, g, w, grid); break;
         case 3: if (PX == 1) { launch_bwd2<1, 3>(a, g, w, grid); break; }   // else: fall through
+        case 4: if (PX == 1) { launch_bwd2<1, 4>(a, g, w, grid); break; }   // else: fall through
         default: launch_bwd2<PX, 2>(a, g, w, grid); break;
     }
 }

@@ -312,6 +312,11 @@ def run_ours(args, rank, world, local_rank):
     stages = stage_profile(ctx.eng, with_adam=(world == 1))      # no collective inside: every rank runs it
     clk = clocks.stop() if rank == 0 else None
     gm.end_training(ctx)
+    if args.quick:                                               # tuning runs: device arm + per-kernel times only
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms / args.steps, "instances": inst, "visible": vis,
+                              "kernels_us": {k: round(v * 1e3, 1) for k, v in stages.items()}}), flush=True)
+        return None
 
     # ---------------- end-to-end arm: the public call GaussianMap.update(dataframe) -- what
     # mapping/mapper.py:95-101 does per keyframe -- on NEW keyframes that arrive in pinned HOST memory:
@@ -397,7 +402,7 @@ def run_ours(args, rank, world, local_rank):
                                     "the HBM fraction is reported as BASELINE.json asks",
                             "peak_source": which, "share_of_step": stages[dom] / sum(stages.values())}
         line["kernels"] = kern
-    if world == 1:
+    if world == 1 and not args.no_update_profile:
         import contextlib
         with contextlib.redirect_stdout(sys.stderr):          # the reference's prune() prints to stdout
             update_loop_profile(dev)                           # first pass warms the allocator (a mapper is long-lived)
@@ -533,6 +538,8 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5],
                     help="SURVEY 8d config index: 2 = 200k/640x480 (headline), 3 = 500k/1280x720, 5 = 1M/1920x1080")
     ap.add_argument("--frames-per-gpu", type=int, default=8)
+    ap.add_argument("--no-update-profile", action="store_true", help="skip the per-keyframe update() phase timing (sweeps)")
+    ap.add_argument("--quick", action="store_true", help="tuning runs: device-resident arm and per-kernel times only")
     ap.add_argument("--device-arm-only", action="store_true",
                     help="profiling runs (ncu): stop after the device-resident arm, print nothing")
     args = ap.parse_args()

@@ -16,7 +16,8 @@ SELECT = "test_c1_forward_backward or test_room_cut_20k_160x120 or test_oversize
 
 @pytest.mark.parametrize("env", [
     {"AGS_BWD_TMA": "1"},                       # cp.async.bulk + mbarrier staging (default reduction)
-    {"AGS_BWD_RED": "0"}, {"AGS_BWD_RED": "1"}, {"AGS_BWD_RED": "2"},
+    {"AGS_BWD_RED": "0"}, {"AGS_BWD_RED": "1"}, {"AGS_BWD_RED": "2"}, {"AGS_BWD_RED": "3"},
+    {"AGS_BWD_RED": "4"},                       # tensor-core (mma.sync TF32 hi/lo) reduction
     {"AGS_BWD_PX": "2", "AGS_BWD_RED": "2"}, {"AGS_BWD_PX": "4", "AGS_BWD_RED": "0"},
 ], ids=lambda e: ",".join(f"{k[8:]}={v}" for k, v in e.items()))
 def test_backward_variant_parity(env):
