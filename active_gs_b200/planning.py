@@ -103,3 +103,35 @@ def low_confidence_voxels(voxel_map, gaussian_map, confidence_thres=0.3):
                                     [int(d) for d in voxel_map.dim], confidence_thres=confidence_thres,
                                     min_gaussian_per_voxel=voxel_map.min_gaussian_per_voxel)
     return normal, mask
+
+
+def dilate6(mask3d):
+    """6-neighbourhood binary dilation of a (X,Y,Z) bool tensor on its own device -- what
+    scipy.ndimage.binary_dilation(mask, generate_binary_structure(3, 1)) returns
+    (mapping/voxel_map.py:21,223-229,290-304), without the numpy round trip of the reference."""
+    m = mask3d.bool()
+    out = m.clone()
+    out[1:, :, :] |= m[:-1, :, :]; out[:-1, :, :] |= m[1:, :, :]
+    out[:, 1:, :] |= m[:, :-1, :]; out[:, :-1, :] |= m[:, 1:, :]
+    out[:, :, 1:] |= m[:, :, :-1]; out[:, :, :-1] |= m[:, :, 1:]
+    return out
+
+
+def update_utility(voxel_map, gaussian_map, use_confidence, confidence_thres=0.3):
+    """VoxelMap.update_utility (mapping/voxel_map.py:62-116) for a reference-shaped voxel map object (attributes
+    dim, bbox, size, min_gaussian_per_voxel, frontier_mask, free_mask): region-of-interest voxels = (frontier or
+    holding more than min_gaussian_per_voxel opaque low-confidence Gaussians) and next to free space.  The
+    Gaussian half is one scatter kernel (low_confidence_voxels), the dilation stays on the device.  Sets
+    voxel_map.voxel_normal / voxel_map.roi_mask like the reference and returns the mask."""
+    dim = [int(d) for d in voxel_map.dim]
+    M = dim[0] * dim[1] * dim[2]
+    dev = gaussian_map.device
+    voxel_map.voxel_normal = torch.zeros((M, 3), device=dev)
+    raw = voxel_map.frontier_mask.to(dev).bool().clone()
+    if use_confidence:
+        normal, upd = low_confidence_voxels(voxel_map, gaussian_map, confidence_thres)
+        voxel_map.voxel_normal = normal
+        raw |= upd
+    free = voxel_map.free_mask.to(dev).view(*dim)
+    voxel_map.roi_mask = raw & dilate6(free).view(-1)
+    return voxel_map.roi_mask

@@ -275,6 +275,19 @@ def test_voxel_roi_matches_oracle_and_reference_fixture(gold):
     count, _, _ = ops.voxel_roi(gm._means, gm._rotations, gm._opacities, gm.get_confidences, g["bbox"][0].tolist(),
                                 g["size"].tolist(), g["dim"].tolist(), min_gaussian_per_voxel=g["min_gaussian_per_voxel"])
     assert torch.equal(count.cpu().long(), count_ref)
+    # the whole update_utility (mapping/voxel_map.py:62-116): frontier | low-confidence voxels, next to free space
+    from scipy.ndimage import binary_dilation, generate_binary_structure
+    dim = [int(d) for d in g["dim"]]
+    M = dim[0] * dim[1] * dim[2]
+    gen = torch.Generator().manual_seed(9)
+    vm.frontier_mask = torch.rand(M, generator=gen) < 0.05
+    vm.free_mask = torch.rand(M, generator=gen) < 0.3
+    for use_conf in (True, False):
+        roi = planning.update_utility(vm, gm, use_conf, g["confidence_thres"])
+        raw = vm.frontier_mask | (upd_ref if use_conf else torch.zeros(M, dtype=torch.bool))
+        dil = binary_dilation(vm.free_mask.view(*dim).numpy(), structure=generate_binary_structure(3, 1))
+        assert torch.equal(roi.cpu(), raw & torch.from_numpy(dil).view(-1))
+        assert torch.allclose(vm.voxel_normal.cpu(), vn_ref if use_conf else torch.zeros(M, 3), atol=1e-5)
 
 
 def test_map_store_external_tensors_public_prune_and_growth(tmp_path):

@@ -151,3 +151,15 @@ def test_adam_first_step_is_sign(golden):
     q = torch.nn.Parameter(p.clone()); q.grad = gr.clone()
     torch.optim.Adam([q], lr=1e-2, eps=1e-15).step()
     close(q.detach(), p2, rtol=1e-6, atol=1e-7)
+
+
+def test_dilate6_matches_scipy_binary_dilation():
+    """planning.dilate6 == scipy.ndimage.binary_dilation with the 6-connected structure the reference uses
+    (mapping/voxel_map.py:21,290-304)"""
+    from scipy.ndimage import binary_dilation, generate_binary_structure
+    from active_gs_b200.planning import dilate6
+    g = torch.Generator().manual_seed(5)
+    for shape in [(7, 5, 3), (1, 4, 6), (12, 12, 12)]:
+        m = torch.rand(*shape, generator=g) < 0.15
+        want = binary_dilation(m.numpy(), structure=generate_binary_structure(3, 1))
+        assert np.array_equal(dilate6(m).numpy(), want)
