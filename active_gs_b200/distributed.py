@@ -55,7 +55,7 @@ class SymmetricAux:
         world = dist.get_world_size(group)
         self.P, self.nterm = P, nterm
         self.vis = symm.empty(P, dtype=torch.int32, device=device)
-        self.gather = symm.empty(world * nterm, dtype=torch.float32, device=device)
+        self.gather = symm.empty(2 * world * nterm, dtype=torch.float32, device=device)     # two halves: iteration parity
         self.vis.zero_(); self.gather.zero_()
         g = group if group is not None else dist.group.WORLD
         self.h_vis = symm.rendezvous(self.vis, g)

@@ -186,6 +186,8 @@ class _TrainEngine:
         self.host_stats = torch.empty(L.AGS_NUM_STATS, dtype=torch.int32).pin_memory()
         self.host_np, self.host_stats_np = self.host.numpy(), self.host_stats.numpy()
         self.event = torch.cuda.Event()
+        self.loss_done = torch.cuda.Event()
+        self.side_stream = torch.cuda.Stream(device=dev) if dist_ctx is not None else None
         self.aux = dist_ctx.aux_buffers(H * W, self.nterm, dev) if self.fused else None
         self.sync = dist_ctx.sync_buffers(dev) if (self.fused and dist_ctx.folded) else None
         self.sync_wait = None
@@ -379,7 +381,17 @@ class _TrainEngine:
             B_total=self.B_total, vis_count=vis, out=self.loss_outs[k], frame_weight=self.frame_w, want_maps=False)
         lo = self.loss_out = self.loss_outs[k]
         self._mark("loss")
-        if self.fused:
+        if self.fused and self.sync is not None:
+            # the exchange of the loss terms (a one-block kernel, a flag wait and the small D2H the host waits for) does
+            # not feed the backward: it runs on a side stream next to it instead of between the loss and the backward
+            main = torch.cuda.current_stream(self.dev)
+            self.loss_done.record(main)
+            with torch.cuda.stream(self.side_stream):
+                self.side_stream.wait_event(self.loss_done)
+                self._fused_terms_gather(lib, L.current_stream(self.dev), lo)
+                self.host_stats.copy_(rb.stats, non_blocking=True)
+                self.event.record(self.side_stream)
+        elif self.fused:
             self._fused_terms_gather(lib, st, lo)
         elif self.dist is not None:
             # loss terms + per-frame performance of every rank, gathered on the stream before the
@@ -392,8 +404,9 @@ class _TrainEngine:
             self.host.copy_(self.terms_all, non_blocking=True)
         else:
             self.host[:4 + 2 * self.B].copy_(lo.terms, non_blocking=True)
-        self.host_stats.copy_(rb.stats, non_blocking=True)
-        self.event.record(torch.cuda.current_stream(self.dev))
+        if not (self.fused and self.sync is not None):
+            self.host_stats.copy_(rb.stats, non_blocking=True)
+            self.event.record(torch.cuda.current_stream(self.dev))
         single = self.dist is None
         if self.grad_args[k] is None:
             g = L.RenderGradArgs()
@@ -466,11 +479,15 @@ class _TrainEngine:
         if a is None:
             a = L.DistTermsArgs()
             a.world, a.rank, a.nterm, a.nview = d.world, d.rank, self.nterm, self.B
-            for p in range(d.world):
-                a.gather_peers[p] = x.gather_ptrs[p]
-            a.gather_multicast = x.gather_mc if (d.use_multicast and x.gather_mc) else None
             self._fill_sync(a.sync)
             self.terms_args = a
+        # the gather buffer is double buffered by iteration parity: a fast peer may already push the terms of the
+        # next iteration while this rank's D2H of the current ones is still queued on the side stream
+        half = (self.sync.epoch & 1) if self.sync is not None else 0
+        off = half * d.world * self.nterm * 4
+        for p in range(d.world):
+            a.gather_peers[p] = x.gather_ptrs[p] + off
+        a.gather_multicast = (x.gather_mc + off) if (d.use_multicast and x.gather_mc) else None
         a.stats = L.ptr(self.rb.stats)
         a.terms = L.ptr(lo.terms)
         a.stream = st
@@ -481,8 +498,10 @@ class _TrainEngine:
             x.barrier()
         else:
             self._wait(lib, L.SYNC_TERMS, st)          # every rank's terms have landed in the local gather buffer
-        self._mark("terms put + barrier T")
-        self.host.copy_(x.gather, non_blocking=True)
+        if self.sync is None:
+            self._mark("terms put + barrier T")        # (folded mode: this runs on the side stream, off the critical path)
+        n = d.world * self.nterm
+        self.host.copy_(x.gather[half * n:(half + 1) * n], non_blocking=True)
 
     def _fused_exchange_and_adam(self, lib, st):
         """reduce-scatter(grads) -> Adam(shard) -> all-gather(params) in one kernel, between two

@@ -194,14 +194,14 @@ def stage_profile(eng, reps=5, with_adam=True):
     return {n: v / reps for n, v in acc.items()}
 
 
-def update_loop_profile(dev, keyframes=12):
+def update_loop_profile(dev, keyframes=12, cfg_idx=2):
     """BASELINE config[1] names the full mapper.update loop: time GaussianMap.update() (spawn from the
     RGB-D keyframe -> 10 optimisation iterations -> confidence bookkeeping / prune,
     mapping/gaussian_map.py:62-64) on a stream of office0-shaped keyframes rendered from the generating
     scene.  Reported: mean over the keyframes that train with the full batch of 8 (steady state)."""
     from active_gs_b200 import operations as O
     from active_gs_b200.gaussian_map import GaussianMap
-    box, H, W, N = syn.ROOMS[2]
+    box, H, W, N = syn.ROOMS[cfg_idx]
     gen = syn.make_room_scene(N, box=box, seed=5)
     ext, K = syn.make_cameras(keyframes, box=box, H=H, W=W, seed=6)
     src = GaussianMap(default_gaussian_map_config(), dev)
@@ -233,8 +233,9 @@ def update_loop_profile(dev, keyframes=12):
     mean = lambda k: float(np.mean([r[k] for r in full]))
     return {"ms_per_keyframe": mean(2) + mean(3) + mean(4), "spawn_ms": mean(2), "train_ms": mean(3), "post_ms": mean(4),
             "iters_per_update": gm.optimization_steps, "keyframes_timed": len(full), "gaussians_end": rows[-1][1],
+            "prune_updates_timed": int(sum(1 for r in full if r[5])),
             "what": "GaussianMap.update(): add_gaussians + 10 train iterations (batch 8) + post_processing (prune every 5th), "
-                    "640x480 keyframes of the office0-shaped scene, wall clock with device sync around each phase"}
+                    f"{W}x{H} keyframes of the synthetic room ({N} generating surfels), wall clock with device sync around each phase"}
 
 
 def algorithmic_bytes(N, B, P, I, V, tiles):
@@ -405,8 +406,8 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and not args.no_update_profile:
         import contextlib
         with contextlib.redirect_stdout(sys.stderr):          # the reference's prune() prints to stdout
-            update_loop_profile(dev)                           # first pass warms the allocator (a mapper is long-lived)
-            line["update"] = update_loop_profile(dev)
+            update_loop_profile(dev, cfg_idx=CONFIG_IDX)       # first pass warms the allocator (a mapper is long-lived)
+            line["update"] = update_loop_profile(dev, cfg_idx=CONFIG_IDX)
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_reference_run(1, [{k: (v.cpu() if torch.is_tensor(v) else v) for k, v in f.items()}
                                                      for f in frames[:4]], start, H, W, quiet=True, warmup=1)
