@@ -187,7 +187,7 @@ class _TrainEngine:
         self.host_np, self.host_stats_np = self.host.numpy(), self.host_stats.numpy()
         self.event = torch.cuda.Event()
         self.loss_done = torch.cuda.Event()
-        self.side_stream = torch.cuda.Stream(device=dev) if dist_ctx is not None else None
+        self.side_stream = torch.cuda.Stream(device=dev) if (dist_ctx is not None and os.environ.get("AGS_DIST_SIDE", "1") != "0") else None
         self.aux = dist_ctx.aux_buffers(H * W, self.nterm, dev) if self.fused else None
         self.sync = dist_ctx.sync_buffers(dev) if (self.fused and dist_ctx.folded) else None
         self.sync_wait = None
@@ -381,7 +381,7 @@ class _TrainEngine:
             B_total=self.B_total, vis_count=vis, out=self.loss_outs[k], frame_weight=self.frame_w, want_maps=False)
         lo = self.loss_out = self.loss_outs[k]
         self._mark("loss")
-        if self.fused and self.sync is not None:
+        if self.fused and self.sync is not None and self.side_stream is not None:
             # the exchange of the loss terms (a one-block kernel, a flag wait and the small D2H the host waits for) does
             # not feed the backward: it runs on a side stream next to it instead of between the loss and the backward
             main = torch.cuda.current_stream(self.dev)
@@ -404,7 +404,7 @@ class _TrainEngine:
             self.host.copy_(self.terms_all, non_blocking=True)
         else:
             self.host[:4 + 2 * self.B].copy_(lo.terms, non_blocking=True)
-        if not (self.fused and self.sync is not None):
+        if not (self.fused and self.sync is not None and self.side_stream is not None):
             self.host_stats.copy_(rb.stats, non_blocking=True)
             self.event.record(torch.cuda.current_stream(self.dev))
         single = self.dist is None
@@ -793,25 +793,33 @@ class GaussianMap:
     def post_processing(self):
         """:141-232.  One count-only render of the newest keyframe (all T keyframes every
         prune_interval-th time, in chunks) from the raw parameters, the confidence bookkeeping in one
-        kernel (ags_view_stats_update) and the prune as one ordered compaction (ags_prune_compact)."""
+        kernel (ags_view_stats_update) and the prune as one ordered compaction (ags_prune_compact).
+        With a process group the T-1 older keyframes of a prune pass are sharded round robin over the ranks and
+        the per-Gaussian "counted in some view" sums are all-reduced (4 B per Gaussian): the reference renders
+        all T frames every 5th keyframe, T grows without bound."""
         T = len(self.training_data)
         require_prune = T % self.prune_interval == 0
-        ids = list(range(T)) if require_prune else [T - 1]
         self._make_contiguous()
         _, H, W = self.training_data[-1]["depth"].shape
         N = self._means.shape[0]
-        seen = None                                   # (1,N) int32: times counted over all views but the last chunk
-        last = None
-        step = views_per_chunk(N, H, W, per_gaussian=self._cap_per_gaussian, cap=self.POST_CHUNK)
-        for c0 in range(0, len(ids), step):
-            chunk = ids[c0:c0 + step]
-            dgt = torch.stack([self.training_data[i]["depth"] for i in chunk]).to(self.device)
-            rb = self._render_raw(chunk, H, W, render_mask=(dgt > 0.0).float(), require_importance=True,
-                                  front_only=True)
-            if last is not None:
-                part = last.sum(0, keepdim=True, dtype=torch.int32)
-                seen = part if seen is None else seen + part
-            last = rb.count
+        seen = None                                   # (1,N) int32: times counted over the keyframes before the newest
+        if require_prune and T > 1:
+            older = list(range(T - 1))
+            if self.dist is not None:
+                older = older[self.dist.rank::self.dist.world]
+            step = views_per_chunk(N, H, W, per_gaussian=self._cap_per_gaussian, cap=self.POST_CHUNK)
+            seen = torch.zeros(1, N, device=self.device, dtype=torch.int32)
+            for c0 in range(0, len(older), step):
+                chunk = older[c0:c0 + step]
+                dgt = torch.stack([self.training_data[i]["depth"] for i in chunk]).to(self.device)
+                rb = self._render_raw(chunk, H, W, render_mask=(dgt > 0.0).float(), require_importance=True,
+                                      front_only=True)
+                seen += rb.count.sum(0, keepdim=True, dtype=torch.int32)
+            if self.dist is not None:
+                self.dist.all_reduce_sum_(seen)
+        dgt = self.training_data[T - 1]["depth"][None].to(self.device)
+        rb = self._render_raw([T - 1], H, W, render_mask=(dgt > 0.0).float(), require_importance=True, front_only=True)
+        last = rb.count                               # (1,N): the newest keyframe, rendered by every rank
         for n in ["view_scores", "view_supports", "view_means"]:
             setattr(self, n, getattr(self, n).float().contiguous())
         ops.view_stats_update(last[-1], self._means, self._rotations, self._camera(T - 1)["campos"],
