@@ -244,7 +244,9 @@ loss_fused_kernel(AgsLossArgs a, LossFrames fr, const float* __restrict__ msum_p
             const F3 pl = (f3((rx - g.ik00) * dl, ry * dl, dl) - pc) * ml;
             const F3 pb = (f3(rx * db, (ry + g.ik11) * db, db) - pc) * mb;
             const F3 pr = (f3((rx + g.ik00) * dr, ry * dr, dr) - pc) * mr;
-            const F3 ns = cross(pu, pl) + cross(pr, pu) + cross(pb, pr) + cross(pl, pb);
+            // cross(pu,pl) + cross(pr,pu) + cross(pb,pr) + cross(pl,pb) = (pu - pb) x (pl - pr): one cross product
+            const F3 ev = pu - pb, eh = pl - pr;
+            const F3 ns = cross(ev, eh);
             const float insn = rsqrtf(fmaxf(dot(ns, ns), 1e-24f));
             const F3 u = ns * insn;
             d2n = u * mc;
@@ -254,10 +256,12 @@ loss_fused_kernel(AgsLossArgs a, LossFrames fr, const float* __restrict__ msum_p
                 const float wc = -a.w_cons * msum * inv_cons;                // dL/d(nu . d2n)
                 const F3 gd = nu * wc;                                       // dL/d u  (d2n = u*m2, m2 = 1)
                 const F3 gq = (gd - u * dot(u, gd)) * insn;
-                const F3 dpu = (cross(pl, gq) + cross(gq, pr)) * mu;
-                const F3 dpl = (cross(gq, pu) + cross(pb, gq)) * ml;
-                const F3 dpb = (cross(pr, gq) + cross(gq, pl)) * mb;
-                const F3 dpr = (cross(pu, gq) + cross(gq, pb)) * mr;
+                // adjoint of ns = ev x eh:  d ev = eh x gq,  d eh = gq x ev;  ev = pu - pb, eh = pl - pr
+                const F3 dev = cross(eh, gq), deh = cross(gq, ev);
+                const F3 dpu = dev * mu;
+                const F3 dpl = deh * ml;
+                const F3 dpb = dev * (-mb);
+                const F3 dpr = deh * (-mr);
                 const F3 dpc = (dpu + dpl + dpb + dpr) * (-mc);
                 a_own = dpc.x * rx + dpc.y * ry + dpc.z;
                 a_up = dpu.x * rx + dpu.y * (ry - g.ik11) + dpu.z;           // zero when mu == 0

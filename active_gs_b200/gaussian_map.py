@@ -112,7 +112,8 @@ class _MapStore:
             # grow geometrically (2x + room for the keyframe about to be added): a re-allocation is a
             # cudaMalloc per field, which with peer mappings enabled costs milliseconds per GPU of the box
             self.cap = max(2 * (N + extra) + 1024, 262144)
-            dst, self.alt = self._alloc(self.cap), None
+            # both halves of the ping-pong pair now: the first prune would otherwise pay eight cudaMallocs
+            dst, self.alt = self._alloc(self.cap), self._alloc(self.cap)
         for n, w in ops.MAP_FIELDS:
             src = getattr(gm, _ATTR[n]).detach().reshape((N, w) if w > 1 else (N,))
             if src.data_ptr() != dst[n].data_ptr():
