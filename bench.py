@@ -398,9 +398,9 @@ def run_ours(args, rank, world, local_rank):
             traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
         line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peaks["hbm_gbs"],
                             "unit": "GB/s", "frac": kern[dom]["gbs"] / peaks["hbm_gbs"], "traffic": traffic,
-                            "note": "composite_bwd is bound by instruction issue (ncu: 76 % issue-active) and the shared-memory "
-                                    "data pipe (80 % of peak: the 15-value warp reduction), 9 % DRAM throughput; "
-                                    "the HBM fraction is reported as BASELINE.json asks",
+                            "note": "composite_bwd is bound by instruction issue (ncu: 83 % issue-active, ~125 warp instructions "
+                                    "per (warp, splat) pair, half of them the 15-value cross-lane reduction), 9 % DRAM throughput, DRAM "
+                                    "traffic = 1.04x the algorithmic bytes; the HBM fraction is reported as BASELINE.json asks",
                             "peak_source": which, "share_of_step": stages[dom] / sum(stages.values())}
         line["kernels"] = kern
     if world == 1 and not args.no_update_profile:
