@@ -773,7 +773,9 @@ class GaussianMap:
             setattr(self, n, getattr(self, n).detach().float().contiguous())
 
     # ------------------------------------------------------------------ :141-246
-    POST_CHUNK = 16          # views per count-render launch when all T keyframes are re-rendered
+    POST_CHUNK = 4           # views per count-render launch when all T keyframes are re-rendered: the transient
+                             # workspace is ~80 MB per view at 330 k surfels, and the first prune pass of a mission pays
+                             # for allocating it (16 views: 1.4 GB, ~60 ms once; 4 views: four launches, ~0.2 ms more)
 
     def _render_raw(self, ids, H, W, *, render_mask=None, require_importance=False, front_only=False,
                     with_confidence=False):
