@@ -62,19 +62,29 @@ __device__ __forceinline__ float rcp_approx(float x) {      // MUFU.RCP
     return r;
 }
 
-// The staged record carries the conic pre-multiplied by log2(e), so the exponent feeds MUFU.EX2
-// directly: G = exp(power) = 2^(power2), power2 = -0.5 (a' dx^2 + c' dy^2) - b' dx dy.
+// The staged record carries the conic pre-multiplied by -0.5*log2(e) (a, c) and -log2(e) (b), the two diagonal terms
+// next to each other: g0 = (x, y, a', c'), g1 = (b', opacity, slope_x, slope_y).  The exponent then feeds MUFU.EX2
+// directly, G = exp(power) = 2^(power2), power2 = a' dx^2 + c' dy^2 + b' dx dy, and its evaluation is three packed
+// fp32x2 instructions on natural register pairs: (dx,dy) = (x,y) - (px,py); (dx^2,dy^2); (a' dx^2, c' dy^2).
 // `power` below is power2 (same sign as the natural exponent); `G` is the un-clamped Gaussian.
+__device__ __forceinline__ void stage_geom(SplatRec& r, const float4 g0, const float4 g1) {   // from K1's (x,y,a,b) (c,o,sx,sy)
+    r.g0 = make_float4(g0.x, g0.y, g0.z * (-0.5f * AGS_LOG2E), g1.x * (-0.5f * AGS_LOG2E));
+    r.g1 = make_float4(g0.w * (-AGS_LOG2E), g1.y, g1.z, g1.w);
+}
+__device__ __forceinline__ float splat_power(const float4 g0, const float4 g1, float2 neg_pix, float& dx, float& dy) {
+    const float2 d = __fadd2_rn(make_float2(g0.x, g0.y), neg_pix);
+    const float2 q = __fmul2_rn(make_float2(g0.z, g0.w), __fmul2_rn(d, d));
+    dx = d.x; dy = d.y;
+    return fmaf(g1.x * d.x, d.y, q.x + q.y);
+}
 struct SplatEval {
     float dx, dy, power, G, alpha;
     bool skip;
 };
 
-__device__ __forceinline__ SplatEval eval_alpha(const float4 g0, const float4 g1, float pxf, float pyf) {
+__device__ __forceinline__ SplatEval eval_alpha(const float4 g0, const float4 g1, float2 neg_pix) {
     SplatEval e;
-    e.dx = g0.x - pxf;
-    e.dy = g0.y - pyf;
-    e.power = -0.5f * (g0.z * e.dx * e.dx + g1.x * e.dy * e.dy) - g0.w * e.dx * e.dy;
+    e.power = splat_power(g0, g1, neg_pix, e.dx, e.dy);
     e.G = ex2_approx(e.power);
     e.alpha = fminf(AGS_ALPHA_MAX, g1.y * e.G);
     e.skip = (e.power > 0.f) || (e.alpha < AGS_ALPHA_MIN);
@@ -213,7 +223,7 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
     const WarpBlock wb = warp_block(blockIdx.x, blockIdx.y, tid);
     const int px = wb.px, py = wb.py;
     const bool inside = (px < a.W) && (py < a.H);
-    const float pxf = (float)px, pyf = (float)py;
+    const float2 neg_pix = make_float2(-(float)px, -(float)py);
     const bool overflow = w.counters[0] > a.inst_cap;
     const int n = overflow ? 0 : w.tile_count[gt];
     const int off = overflow ? 0 : w.tile_offset[gt];
@@ -246,8 +256,7 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
         if (tid < n) {
             s_id[rank] = id;
             SplatRec& r = s_rec[rank];
-            r.g0 = make_float4(g0.x, g0.y, g0.z * AGS_LOG2E, g0.w * AGS_LOG2E);   // conic * log2(e)
-            r.g1 = make_float4(g1.x * AGS_LOG2E, g1.y, g1.z, g1.w);
+            stage_geom(r, g0, g1);
             r.f0 = ldg4(w.feat0 + vN + id);
             r.f1 = ldg4(w.feat1 + vN + id);
             r.bb = splat_bbox(g0, g1);
@@ -309,7 +318,10 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
     if (WANT_IMP && inside) imp_pix = a.render_mask ? (a.render_mask[(size_t)v * P + pix] == 1.f) : true;
 
     float T = 1.f;
-    float C0 = 0.f, C1 = 0.f, C2 = 0.f, N0 = 0.f, N1 = 0.f, N2 = 0.f, D = 0.f, Cf = 0.f;
+    // accumulators as register pairs: the eight weighted sums of a splat are four packed FFMA2 (sm_100 fp32x2: two
+    // FMAs per issue slot; the kernel is issue-bound, not FP32-pipe-bound) over the natural halves of the 128-bit
+    // record loads: (r,g) (b,plane depth) (nx,ny) (nz,confidence)
+    float2 CA = make_float2(0.f, 0.f), CB = CA, NA = CA, NB = CA;     // (C0,C1) (C2,D) (N0,N1) (N2,Cf)
     int last = 0;
     bool done = !inside;
     bool warp_done = __all_sync(0xffffffffu, done);
@@ -322,8 +334,7 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
             const float4 g0 = ldg4(w.geom0 + idx), g1 = ldg4(w.geom1 + idx);
             s_id[tid] = id;
             SplatRec& r = s_rec[tid];
-            r.g0 = make_float4(g0.x, g0.y, g0.z * AGS_LOG2E, g0.w * AGS_LOG2E);   // conic * log2(e)
-            r.g1 = make_float4(g1.x * AGS_LOG2E, g1.y, g1.z, g1.w);
+            stage_geom(r, g0, g1);
             r.f0 = ldg4(w.feat0 + idx);
             r.f1 = ldg4(w.feat1 + idx);
             r.bb = splat_bbox(g0, g1);
@@ -339,7 +350,7 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
                 mask &= mask - 1;
                 const SplatRec& rec = s_rec[k];
                 const float4 g0 = rec.g0, g1 = rec.g1;
-                const SplatEval e = eval_alpha(g0, g1, pxf, pyf);
+                const SplatEval e = eval_alpha(g0, g1, neg_pix);
                 // branch-free per lane: a lane that is done, skips the splat or stops here runs the same
                 // arithmetic with weight 0 (one warp-uniform early-out when nobody takes the splat)
                 const bool use = !done && !e.skip;
@@ -350,10 +361,12 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
                 done = done || stop;
                 const float wgt = take ? e.alpha * T : 0.f;
                 const float4 f0 = rec.f0, f1 = rec.f1;
-                C0 += wgt * f0.x; C1 += wgt * f0.y; C2 += wgt * f0.z;
-                D += wgt * (f0.w - g1.z * e.dx - g1.w * e.dy);
-                N0 += wgt * f1.x; N1 += wgt * f1.y; N2 += wgt * f1.z;
-                Cf += wgt * f1.w;
+                const float2 ww = make_float2(wgt, wgt);
+                const float dpix = f0.w - g1.z * e.dx - g1.w * e.dy;
+                CA = __ffma2_rn(ww, make_float2(f0.x, f0.y), CA);
+                CB = __ffma2_rn(ww, make_float2(f0.z, dpix), CB);
+                NA = __ffma2_rn(ww, make_float2(f1.x, f1.y), NA);
+                NB = __ffma2_rn(ww, make_float2(f1.z, f1.w), NB);
                 T = take ? test_T : T;
                 last = take ? base + k + 1 : last;
                 if (WANT_IMP) {
@@ -370,12 +383,12 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
         const float A = 1.f - T;
         const float bg0 = __ldg(a.bg), bg1 = __ldg(a.bg + 1), bg2 = __ldg(a.bg + 2);
         float* o = a.out_rgb + (size_t)v * 3 * P + pix;
-        o[0] = C0 + T * bg0; o[P] = C1 + T * bg1; o[2 * P] = C2 + T * bg2;
+        o[0] = CA.x + T * bg0; o[P] = CA.y + T * bg1; o[2 * P] = CB.x + T * bg2;
         o = a.out_normal + (size_t)v * 3 * P + pix;
-        o[0] = N0; o[P] = N1; o[2 * P] = N2;
-        a.out_depth[(size_t)v * P + pix] = (A > 0.f) ? D / A : 0.f;
+        o[0] = NA.x; o[P] = NA.y; o[2 * P] = NB.x;
+        a.out_depth[(size_t)v * P + pix] = (A > 0.f) ? CB.y / A : 0.f;
         a.out_opacity[(size_t)v * P + pix] = A;
-        a.out_confidence[(size_t)v * P + pix] = Cf;
+        a.out_confidence[(size_t)v * P + pix] = NB.y;
         w.final_T[(size_t)v * P + pix] = T;
         w.n_contrib[(size_t)v * P + pix] = last;
     }
@@ -574,14 +587,21 @@ template <bool HAS_CONF>
 __device__ __forceinline__ float bwd_pair_fold(BwdPix& s, const FoldLane& f, const float4 g1, const float4 f0,
                                                const float4 f1, float dx, float dy, float e_alpha, float e_G,
                                                bool active) {
+    // Packed fp32x2 (FFMA2 / FMUL2 / FADD2, sm_100): two fp32 operations per issue slot on natural register pairs --
+    // the halves of the 128-bit record loads, the per-pixel constants, the permuted constants.  The kernel is
+    // issue-bound (83 % issue-active, FP32 pipe 32 %), so every pair saves a slot.
     const unsigned FULL = 0xffffffffu;
     const float alpha = active ? e_alpha : 0.f;
     const float G = active ? e_G : 0.f;
     const float wgt = alpha * s.T;
     const float one_m = 1.f - alpha;
     const float dpix = f0.w - g1.z * dx - g1.w * dy;
-    float sdot = s.gC0 * f0.x + s.gC1 * f0.y + s.gC2 * f0.z + s.gN0 * f1.x + s.gN1 * f1.y + s.gN2 * f1.z + s.gD * dpix;
-    if (HAS_CONF) sdot += s.gCf * f1.w;
+    float2 acc = __fmul2_rn(make_float2(s.gC0, s.gC1), make_float2(f0.x, f0.y));
+    acc = __ffma2_rn(make_float2(s.gC2, s.gD), make_float2(f0.z, dpix), acc);
+    acc = __ffma2_rn(make_float2(s.gN0, s.gN1), make_float2(f1.x, f1.y), acc);
+    if (HAS_CONF) acc = __ffma2_rn(make_float2(s.gN2, s.gCf), make_float2(f1.z, f1.w), acc);
+    else acc.x = fmaf(s.gN2, f1.z, acc.x);
+    const float sdot = acc.x + acc.y;
     s.rem -= wgt * sdot;
     const float dalpha = s.T * sdot - s.rem * rcp_approx(one_m);         // one_m >= 0.01
     s.T *= one_m;
@@ -589,29 +609,36 @@ __device__ __forceinline__ float bwd_pair_fold(BwdPix& s, const FoldLane& f, con
     const float dpower = unclamped ? alpha * dalpha : 0.f;
     const float wgD = wgt * s.gD;
     // ---- level 1 (xor 16)
-    float W[4], P[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) W[t] = wgt * f.Kp[t] + __shfl_xor_sync(FULL, wgt * f.Kp[t + 4], 16);
+    const float2 ww = make_float2(wgt, wgt);
+    const float2 s01 = __fmul2_rn(ww, make_float2(f.Kp[4], f.Kp[5]));
+    const float2 s23 = __fmul2_rn(ww, make_float2(f.Kp[6], f.Kp[7]));
+    const float2 r01 = make_float2(__shfl_xor_sync(FULL, s01.x, 16), __shfl_xor_sync(FULL, s01.y, 16));
+    const float2 r23 = make_float2(__shfl_xor_sync(FULL, s23.x, 16), __shfl_xor_sync(FULL, s23.y, 16));
+    const float2 W01 = __ffma2_rn(ww, make_float2(f.Kp[0], f.Kp[1]), r01);
+    const float2 W23 = __ffma2_rn(ww, make_float2(f.Kp[2], f.Kp[3]), r23);
+    float P[4];
     {
-        const float d1 = f.r1 ? dy : dx, d2 = f.r1 ? dx : dy;
-        const float k0 = dpower * d1, s0 = dpower * d2;          // sum dpower*dx | dpower*dy
-        const float pxy = k0 * d2;                                // dpower*dx*dy
-        P[0] = k0 + __shfl_xor_sync(FULL, s0, 16);
-        P[1] = k0 * d1 + __shfl_xor_sync(FULL, s0 * d2, 16);      // dpower*dx^2 | dpower*dy^2
-        P[2] = wgD * d1 + __shfl_xor_sync(FULL, wgD * d2, 16);    // wgD*dx | wgD*dy
+        const float2 dd = make_float2(f.r1 ? dy : dx, f.r1 ? dx : dy);   // (d1, d2)
+        const float2 A = __fmul2_rn(make_float2(dpower, dpower), dd);    // (sum dpower*dx | dpower*dy)
+        const float2 Bq = __fmul2_rn(A, dd);                             // (dpower*dx^2 | dpower*dy^2)
+        const float2 Cq = __fmul2_rn(make_float2(wgD, wgD), dd);         // (wgD*dx | wgD*dy)
+        const float pxy = A.x * dd.y;                                    // dpower*dx*dy
+        P[0] = A.x + __shfl_xor_sync(FULL, A.y, 16);
+        P[1] = Bq.x + __shfl_xor_sync(FULL, Bq.y, 16);
+        P[2] = Cq.x + __shfl_xor_sync(FULL, Cq.y, 16);
         const float k3 = f.r1 ? dpower : pxy, s3 = f.r1 ? pxy : dpower;
-        P[3] = k3 + __shfl_xor_sync(FULL, s3, 16);                // dpower*dx*dy | dpower
+        P[3] = k3 + __shfl_xor_sync(FULL, s3, 16);                       // dpower*dx*dy | dpower
     }
     // ---- level 2 (xor 8)
-    float W2[2], P2[2];
+    const float2 W2 = __fadd2_rn(W01, make_float2(__shfl_xor_sync(FULL, W23.x, 8), __shfl_xor_sync(FULL, W23.y, 8)));
+    float P2[2];
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
-        W2[t] = W[t] + __shfl_xor_sync(FULL, W[t + 2], 8);
         const float send = f.r2 ? P[t] : P[t + 2], keep = f.r2 ? P[t + 2] : P[t];
         P2[t] = keep + __shfl_xor_sync(FULL, send, 8);
     }
     // ---- level 3 (xor 4)
-    const float W1 = W2[0] + __shfl_xor_sync(FULL, W2[1], 4);
+    const float W1 = W2.x + __shfl_xor_sync(FULL, W2.y, 4);
     const float send3 = f.r3 ? P2[0] : P2[1], keep3 = f.r3 ? P2[1] : P2[0];
     const float P1 = keep3 + __shfl_xor_sync(FULL, send3, 4);
     // ---- level 4 (xor 2): the lane keeps the W-group value (r4 = 0) or the P-group value (r4 = 1)
@@ -876,8 +903,7 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
                     const float4 g0 = ldg4(w.geom0 + idx), g1 = ldg4(w.geom1 + idx);
                     s_id[t] = id;
                     SplatRec& r = s_rec[t];
-                    r.g0 = make_float4(g0.x, g0.y, g0.z * AGS_LOG2E, g0.w * AGS_LOG2E);   // conic * log2(e)
-                    r.g1 = make_float4(g1.x * AGS_LOG2E, g1.y, g1.z, g1.w);
+                    stage_geom(r, g0, g1);
                     r.f0 = ldg4(w.feat0 + idx);
                     r.f1 = ldg4(w.feat1 + idx);
                     r.bb = splat_bbox(g0, g1);
@@ -894,7 +920,7 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
                 mask &= mask - 1;
                 const SplatRec& rec = s_rec[k];
                 const float4 g0 = rec.g0, g1 = rec.g1;
-                const float dx = g0.x - pxf;
+                float dx = g0.x - pxf;            // shared by the lane's pixels of one column (PX == 1: replaced by the packed form's)
                 // evaluate alpha for the lane's pixels; a sub-block (8x4) nobody is active in costs nothing more
                 float eA[PX], eG[PX], eDy[PX];
                 bool act[PX];
@@ -905,8 +931,9 @@ composite_bwd_kernel(AgsRenderArgs a, AgsRenderGradArgs gr, AgsWorkspace w) {
                 for (int j = 0; j < PX; ++j) {
                     act[j] = false; eA[j] = 0.f; eG[j] = 0.f; eDy[j] = 0.f;
                     if (PX > 1 && !((bz <= wb.y0 + (float)(4 * j + 3)) && (bw >= wb.y0 + (float)(4 * j)))) continue;
-                    const float dy = g0.y - s[j].pyf;
-                    const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+                    float dxj, dy;
+                    const float power = splat_power(g0, g1, make_float2(-pxf, -s[j].pyf), dxj, dy);
+                    if (PX == 1) dx = dxj;
                     const float G = ex2_approx(power);
                     const float alpha = fminf(AGS_ALPHA_MAX, g1.y * G);
                     const bool skip = (power > 0.f) || (alpha < AGS_ALPHA_MIN);
