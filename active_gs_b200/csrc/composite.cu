@@ -592,7 +592,7 @@ __device__ __forceinline__ float bwd_pair_fold(BwdPix& s, const FoldLane& f, con
     // issue-bound (83 % issue-active, FP32 pipe 32 %), so every pair saves a slot.
     const unsigned FULL = 0xffffffffu;
     const float alpha = active ? e_alpha : 0.f;
-    const float G = active ? e_G : 0.f;
+    const float G = e_G;          // no select: an inactive lane has alpha = 0, so its dpower = alpha * dalpha is 0 either way
     const float wgt = alpha * s.T;
     const float one_m = 1.f - alpha;
     const float dpix = f0.w - g1.z * dx - g1.w * dy;
