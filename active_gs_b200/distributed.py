@@ -107,6 +107,19 @@ class FrameShard:
         # instead of separate barrier launches; AGS_DIST_BARRIER=1 keeps the barrier launches (A/B runs)
         import os
         self.folded = os.environ.get("AGS_DIST_BARRIER", "0") != "1"
+        self._nccl_warm = False
+
+    def warm_up(self, device):
+        """NCCL connects its channels lazily, on the first collective of each kind and size class: measured 259 ms
+        for the first all-reduce of the sharded prune pass (one per mission, but it would land inside a keyframe
+        update).  Pay it when the shard is set up: one small and one Gaussian-count-sized int32 all-reduce."""
+        if self._nccl_warm or dist.get_backend(self.group) != "nccl":
+            return
+        for n in (1, 1 << 20):
+            t = torch.zeros(n, dtype=torch.int32, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        torch.cuda.synchronize(device)
+        self._nccl_warm = True
 
     def flat_buffers(self, numel, device):
         """symmetric buffers with head-room, re-allocated (collective!) only when the map outgrows them"""

@@ -189,6 +189,8 @@ class _TrainEngine:
         self.event = torch.cuda.Event()
         self.loss_done = torch.cuda.Event()
         self.side_stream = torch.cuda.Stream(device=dev) if (dist_ctx is not None and os.environ.get("AGS_DIST_SIDE", "1") != "0") else None
+        if dist_ctx is not None:
+            dist_ctx.warm_up(dev)                    # NCCL's lazy channel set-up, outside any keyframe update
         self.aux = dist_ctx.aux_buffers(H * W, self.nterm, dev) if self.fused else None
         self.sync = dist_ctx.sync_buffers(dev) if (self.fused and dist_ctx.folded) else None
         self.sync_wait = None

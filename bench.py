@@ -331,6 +331,38 @@ def run_ours(args, rank, world, local_rank):
     iters = ITERS if args.steps >= ITERS else args.steps
     gm2.optimization_steps = iters
     host_new = [{k: (v.pin_memory() if k in ("rgb", "depth") else v) for k, v in f.items()} for f in new_frames]
+    phase_acc = {}
+    if os.environ.get("AGS_E2E_PHASES"):                         # diagnosis: host wall clock of every phase of update() (adds syncs)
+        def _timed(obj, name, label=None):
+            fn = getattr(obj, name)
+
+            def w(*a, **k):
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                r = fn(*a, **k)
+                torch.cuda.synchronize(); phase_acc.setdefault(label or name, []).append(round(1e3 * (time.perf_counter() - t0), 2))
+                return r
+            setattr(obj, name, w)
+        from active_gs_b200 import ops as _ops
+        for n in ["add_gaussians", "begin_training", "end_training", "post_processing", "train_step", "_render_raw", "_compact"]:
+            _timed(gm2, n)
+        _timed(gm2._store, "adopt", "store.adopt")
+        _timed(gm2._pool, "get", "pool.get")
+        _timed(_ops, "spawn", "ops.spawn")
+        if shard is not None:
+            _timed(shard, "flat_buffers"); _timed(shard, "all_reduce_sum_")
+    trace = []
+    if os.environ.get("AGS_E2E_TRACE"):                          # diagnosis without added syncs: host time inside each phase
+        def _trace(obj, name):
+            fn = getattr(obj, name)
+
+            def w(*a, **k):
+                t0 = time.perf_counter()
+                r = fn(*a, **k)
+                trace.append((name, round(1e3 * (time.perf_counter() - t0), 2)))
+                return r
+            setattr(obj, name, w)
+        for n in ["add_gaussians", "begin_training", "train_step", "end_training", "post_processing"]:
+            _trace(gm2, n)
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):               # prune() prints like the reference
         for f in host_new[:WARM_UPD]:
@@ -346,6 +378,10 @@ def run_ours(args, rank, world, local_rank):
         f1.record()
         barrier()
     ms_e2e = f0.elapsed_time(f1)
+    if trace:
+        print(f"[rank {rank}] e2e host trace (ms):", trace[-2 * 14:], file=sys.stderr, flush=True)
+    if phase_acc:
+        print(f"[rank {rank}] e2e phases (ms, warm-up updates included):", {k: v for k, v in phase_acc.items()}, file=sys.stderr, flush=True)
     steps_e2e = iters * n_upd
     n_end = int(gm2._means.shape[0])
 
