@@ -317,14 +317,14 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
     bool imp_pix = false;
     if (WANT_IMP && inside) imp_pix = a.render_mask ? (a.render_mask[(size_t)v * P + pix] == 1.f) : true;
 
-    float T = 1.f;
+    // T > 0: the pixel is live; T < 0: finished, |T| is its final transmittance (pixels outside the image start finished)
+    float T = inside ? 1.f : -1.f;
     // accumulators as register pairs: the eight weighted sums of a splat are four packed FFMA2 (sm_100 fp32x2: two
     // FMAs per issue slot; the kernel is issue-bound, not FP32-pipe-bound) over the natural halves of the 128-bit
     // record loads: (r,g) (b,plane depth) (nx,ny) (nz,confidence)
     float2 CA = make_float2(0.f, 0.f), CB = CA, NA = CA, NB = CA;     // (C0,C1) (C2,D) (N0,N1) (N2,Cf)
     int last = 0;
-    bool done = !inside;
-    bool warp_done = __all_sync(0xffffffffu, done);
+    bool warp_done = __all_sync(0xffffffffu, !(T > 0.f));
     for (int base = 0; base < n; base += BATCH) {
         if (__syncthreads_and(warp_done)) break;
         const int j = base + tid;
@@ -353,12 +353,11 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
                 const SplatEval e = eval_alpha(g0, g1, neg_pix);
                 // branch-free per lane: a lane that is done, skips the splat or stops here runs the same
                 // arithmetic with weight 0 (one warp-uniform early-out when nobody takes the splat)
-                const bool use = !done && !e.skip;
+                const bool use = (T > 0.f) && !e.skip;
                 if (__ballot_sync(0xffffffffu, use) == 0u) continue;
                 const float test_T = T * (1.f - e.alpha);
                 const bool stop = use && (test_T < AGS_T_EPS);      // stop BEFORE applying this splat
                 const bool take = use && !stop;
-                done = done || stop;
                 const float wgt = take ? e.alpha * T : 0.f;
                 const float4 f0 = rec.f0, f1 = rec.f1;
                 const float2 ww = make_float2(wgt, wgt);
@@ -367,7 +366,7 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
                 CB = __ffma2_rn(ww, make_float2(f0.z, dpix), CB);
                 NA = __ffma2_rn(ww, make_float2(f1.x, f1.y), NA);
                 NB = __ffma2_rn(ww, make_float2(f1.z, f1.w), NB);
-                T = take ? test_T : T;
+                T = take ? test_T : (stop ? -T : T);
                 last = take ? base + k + 1 : last;
                 if (WANT_IMP) {
                     if (imp_pix && wgt > a.weight_thres) {
@@ -376,10 +375,11 @@ composite_fwd_kernel(AgsRenderArgs a, AgsWorkspace w) {
                     }
                 }
             }
-            warp_done = __all_sync(0xffffffffu, done);
+            warp_done = __all_sync(0xffffffffu, !(T > 0.f));
         }
     }
     if (inside) {
+        T = fabsf(T);
         const float A = 1.f - T;
         const float bg0 = __ldg(a.bg), bg1 = __ldg(a.bg + 1), bg2 = __ldg(a.bg + 2);
         float* o = a.out_rgb + (size_t)v * 3 * P + pix;
@@ -561,26 +561,40 @@ __device__ __forceinline__ void bwd_accumulate(float (&val)[15], BwdPix& s, cons
 //   roles: r1 = lane bit 4 (xor 16), r2 = bit 3 (xor 8), r3 = bit 2 (xor 4), r4 = bit 1 (xor 2); bit 0 is summed.
 //   the lane ends with record slot q = r4*8 + r1*4 + r2*2 + r3 (AGS_REC_* in ags_common.cuh).
 struct FoldLane {
-    float Kp[8];       // permuted per-pixel constants: K = (gC0, gC1, gC2, gN0, gN1, gN2, gD, 0)
+    float Kp[4];       // permuted per-pixel constants of the four W-slots this lane keeps at level 1: K[t ^ m(lane)],
+                       // K = (gC0, gC1, gC2, gN0, gN1, gN2, gD, 0)
+    float Kq[4];       // the same four slots of the level-1 PARTNER pixel (lane ^ 16: same column, two rows away)
+    float gDq;         // the partner pixel's depth gradient
+    float2 cc;         // partner's coordinates relative to this lane's, in the lane's role axes: (0,-2) | (+2,0)
     bool r1, r2, r3, r4;
 };
 
+// Level 1 of the butterfly does not exchange PRODUCTS (8 shuffles) but the two scalars they are made of (w = alpha*T and
+// dL/d(exponent): 2 shuffles): the partner's share of every kept sum is that scalar times a constant of the partner
+// PIXEL -- its gradient constants, fetched once per tile here, and its coordinates, which differ from this lane's by a
+// known offset (same column, row +-2).
 __device__ __forceinline__ void fold_setup(FoldLane& f, const BwdPix& s, int lane) {
+    const unsigned FULL = 0xffffffffu;
     f.r1 = (lane & 16) != 0; f.r2 = (lane & 8) != 0; f.r3 = (lane & 4) != 0; f.r4 = (lane & 2) != 0;
     float K[8] = {s.gC0, s.gC1, s.gC2, s.gN0, s.gN1, s.gN2, s.gD, 0.f};
+    float Kp[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const float a0 = f.r1 ? K[t ^ 4] : K[t];
-        f.Kp[t] = a0;
+    for (int t = 0; t < 8; ++t) Kp[t] = f.r1 ? K[t ^ 4] : K[t];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) K[t] = Kp[t];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) Kp[t] = f.r2 ? K[t ^ 2] : K[t];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) K[t] = Kp[t];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) Kp[t] = f.r3 ? K[t ^ 1] : K[t];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        f.Kp[t] = Kp[t];
+        f.Kq[t] = __shfl_xor_sync(FULL, Kp[t + 4], 16);      // what the partner used to multiply its w with before sending
     }
-#pragma unroll
-    for (int t = 0; t < 8; ++t) K[t] = f.Kp[t];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) f.Kp[t] = f.r2 ? K[t ^ 2] : K[t];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) K[t] = f.Kp[t];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) f.Kp[t] = f.r3 ? K[t ^ 1] : K[t];
+    f.gDq = __shfl_xor_sync(FULL, s.gD, 16);
+    f.cc = f.r1 ? make_float2(2.f, 0.f) : make_float2(0.f, -2.f);
 }
 
 template <bool HAS_CONF>
@@ -608,26 +622,22 @@ __device__ __forceinline__ float bwd_pair_fold(BwdPix& s, const FoldLane& f, con
     const bool unclamped = (g1.y * G <= AGS_ALPHA_MAX);                   // alpha = min(0.99, o*G): clamped -> no gradient
     const float dpower = unclamped ? alpha * dalpha : 0.f;
     const float wgD = wgt * s.gD;
-    // ---- level 1 (xor 16)
-    const float2 ww = make_float2(wgt, wgt);
-    const float2 s01 = __fmul2_rn(ww, make_float2(f.Kp[4], f.Kp[5]));
-    const float2 s23 = __fmul2_rn(ww, make_float2(f.Kp[6], f.Kp[7]));
-    const float2 r01 = make_float2(__shfl_xor_sync(FULL, s01.x, 16), __shfl_xor_sync(FULL, s01.y, 16));
-    const float2 r23 = make_float2(__shfl_xor_sync(FULL, s23.x, 16), __shfl_xor_sync(FULL, s23.y, 16));
-    const float2 W01 = __ffma2_rn(ww, make_float2(f.Kp[0], f.Kp[1]), r01);
-    const float2 W23 = __ffma2_rn(ww, make_float2(f.Kp[2], f.Kp[3]), r23);
+    // ---- level 1 (xor 16): two scalars cross the lanes, the partner's products are formed here
+    const float wgq = __shfl_xor_sync(FULL, wgt, 16), dpq = __shfl_xor_sync(FULL, dpower, 16);
+    const float2 W01 = __ffma2_rn(make_float2(wgq, wgq), make_float2(f.Kq[0], f.Kq[1]),
+                                  __fmul2_rn(make_float2(wgt, wgt), make_float2(f.Kp[0], f.Kp[1])));
+    const float2 W23 = __ffma2_rn(make_float2(wgq, wgq), make_float2(f.Kq[2], f.Kq[3]),
+                                  __fmul2_rn(make_float2(wgt, wgt), make_float2(f.Kp[2], f.Kp[3])));
     float P[4];
     {
-        const float2 dd = make_float2(f.r1 ? dy : dx, f.r1 ? dx : dy);   // (d1, d2)
-        const float2 A = __fmul2_rn(make_float2(dpower, dpower), dd);    // (sum dpower*dx | dpower*dy)
-        const float2 Bq = __fmul2_rn(A, dd);                             // (dpower*dx^2 | dpower*dy^2)
-        const float2 Cq = __fmul2_rn(make_float2(wgD, wgD), dd);         // (wgD*dx | wgD*dy)
-        const float pxy = A.x * dd.y;                                    // dpower*dx*dy
-        P[0] = A.x + __shfl_xor_sync(FULL, A.y, 16);
-        P[1] = Bq.x + __shfl_xor_sync(FULL, Bq.y, 16);
-        P[2] = Cq.x + __shfl_xor_sync(FULL, Cq.y, 16);
-        const float k3 = f.r1 ? dpower : pxy, s3 = f.r1 ? pxy : dpower;
-        P[3] = k3 + __shfl_xor_sync(FULL, s3, 16);                       // dpower*dx*dy | dpower
+        const float2 dd = make_float2(f.r1 ? dy : dx, f.r1 ? dx : dy);   // (d1, d2): this pixel, role axis first
+        const float2 dq = __fadd2_rn(dd, f.cc);                          // the partner pixel's (d1, d2)
+        const float k0 = dpower * dd.x, k0q = dpq * dq.x;                // dpower*d1 of both pixels
+        const float2 B = __fadd2_rn(__fmul2_rn(make_float2(k0, k0), dd), __fmul2_rn(make_float2(k0q, k0q), dq));
+        P[0] = k0 + k0q;                                                 // sum dpower*dx   | dpower*dy
+        P[1] = B.x;                                                      // sum dpower*dx^2 | dpower*dy^2
+        P[2] = fmaf(wgq * f.gDq, dq.x, wgD * dd.x);                      // sum wgD*dx      | wgD*dy
+        P[3] = f.r1 ? dpower + dpq : B.y;                                // sum dpower*dx*dy | dpower
     }
     // ---- level 2 (xor 8)
     const float2 W2 = __fadd2_rn(W01, make_float2(__shfl_xor_sync(FULL, W23.x, 8), __shfl_xor_sync(FULL, W23.y, 8)));
