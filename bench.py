@@ -370,11 +370,17 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        upd_ms, t_prev = [], time.perf_counter()
+        upd_ms, upd_cpu, upd_alloc, t_prev = [], [], [], time.perf_counter()
+        c_prev = time.process_time()
+        a_prev = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
         for f in host_new[WARM_UPD:WARM_UPD + n_upd]:
             gm2.update(f)
             t_now = time.perf_counter()                       # host clock per update: shows one-off set-up spikes
             upd_ms.append(round(1e3 * (t_now - t_prev), 3)); t_prev = t_now
+            c_now = time.process_time()                       # CPU time of this process: wall >> cpu = the host was blocked
+            upd_cpu.append(round(1e3 * (c_now - c_prev), 3)); c_prev = c_now
+            a_now = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)       # cudaMalloc calls of the caching allocator
+            upd_alloc.append(int(a_now - a_prev)); a_prev = a_now
         f1.record()
         barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -412,7 +418,8 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": (P * 16 + 34 * 4 * (T + n_upd)) // iters,
                 "d2h_bytes_per_step": (4 + 2 * B) * 4 + AGS_STATS_BYTES + 16 // iters, "ms_per_step": ms_e2e / steps_e2e,
                 "steps": steps_e2e, "updates": n_upd, "gaussians_end": n_end,
-                "host_ms_per_update": upd_ms[:8], "symmetric_allocations": (shard.flat_allocations if shard else 0),
+                "host_ms_per_update": upd_ms[:8], "cpu_ms_per_update": upd_cpu[:8], "device_allocs_per_update": upd_alloc[:8],
+                "symmetric_allocations": (shard.flat_allocations if shard else 0),
                 "what": "GaussianMap.update(dataframe) per NEW keyframe from pinned host memory (mapper.py:95-101): H2D of the "
                         "keyframe (resident in HBM afterwards), spawn, %d iterations over %d keyframes per GPU with D2H of the "
                         "loss terms each, confidence bookkeeping / prune; Mpix/s counts the training renders only" % (iters, B)},
